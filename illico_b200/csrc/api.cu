@@ -1,0 +1,187 @@
+// api.cu -- extern "C" entry points of libillico_b200.so (see include/illico_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace illico {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// kernels' host launchers (stage.cu, rank_ovr.cu, rank_ovo.cu)
+int launch_stage_dense(const float*, long long, int, int, const illico_plan_t*, float*, uint32_t*, cudaStream_t);
+int launch_stage_csr(const float*, const int32_t*, const long long*, int, int, const illico_plan_t*, float*, uint32_t*,
+                     cudaStream_t);
+int launch_stage_csc(const float*, const int32_t*, const long long*, int, int, const illico_plan_t*, float*, uint32_t*,
+                     cudaStream_t);
+int launch_check_csr_sorted(const int32_t*, const long long*, long long, int*, int*, cudaStream_t);
+int launch_ovr(const float*, const uint32_t*, int, const illico_plan_t*, const illico_flags_t*, double*, long long, void*,
+               size_t, const illico_debug_t*, cudaStream_t);
+int launch_ovo(const float*, const uint32_t*, int, const illico_plan_t*, const illico_flags_t*, double*, long long, void*,
+               size_t, const illico_debug_t*, cudaStream_t);
+size_t ovr_slab_qwords(const illico_plan_t*);
+
+static int check_plan(const illico_plan_t* p) {
+    if (!p) { set_error("plan is NULL"); return 1; }
+    if (p->n_cells <= 0 || p->n_groups <= 0 || p->n_segments < p->n_groups) { set_error("plan has invalid sizes"); return 1; }
+    if (!p->perm || !p->cell_seg || !p->seg_pos || !p->seg_base || !p->seg_group || !p->group_seg || !p->group_size) {
+        set_error("plan has NULL tables");
+        return 1;
+    }
+    if (p->ref_group >= p->n_groups) { set_error("plan.ref_group out of range"); return 1; }
+    return 0;
+}
+
+static int max_resident_ctas() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * 2;
+}
+
+}  // namespace illico
+
+using namespace illico;
+
+extern "C" {
+
+int illico_abi_version(void) { return ILLICO_ABI_VERSION; }
+const char* illico_last_error(void) { return g_err; }
+int64_t illico_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int illico_stage_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t n_genes_batch, const illico_plan_t* plan,
+                           float* ir_vals, uint32_t* ir_cnt, void* stream) {
+    if (check_plan(plan)) return 1;
+    if (!X || !ir_vals || !ir_cnt) { set_error("illico_stage_dense_f32: NULL buffer"); return 1; }
+    return launch_stage_dense(X, ld, gene_lb, n_genes_batch, plan, ir_vals, ir_cnt, (cudaStream_t)stream);
+}
+
+int illico_zero_counts(uint32_t* ir_cnt, int32_t n_genes_batch, const illico_plan_t* plan, void* stream) {
+    if (check_plan(plan)) return 1;
+    ILLICO_CUDA_OK(cudaMemsetAsync(ir_cnt, 0, (size_t)n_genes_batch * plan->n_segments * sizeof(uint32_t),
+                                   (cudaStream_t)stream));
+    return 0;
+}
+
+int illico_stage_csr_f32(const float* data, const int32_t* indices, const int64_t* indptr, int32_t gene_lb,
+                         int32_t n_genes_batch, const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, void* stream) {
+    if (check_plan(plan)) return 1;
+    if (!indptr || !ir_vals || !ir_cnt) { set_error("illico_stage_csr_f32: NULL buffer"); return 1; }
+    return launch_stage_csr(data, indices, (const long long*)indptr, gene_lb, n_genes_batch, plan, ir_vals, ir_cnt,
+                            (cudaStream_t)stream);
+}
+
+int illico_stage_csc_f32(const float* data, const int32_t* indices, const int64_t* indptr, int32_t gene_lb,
+                         int32_t n_genes_batch, const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, void* stream) {
+    if (check_plan(plan)) return 1;
+    if (!indptr || !ir_vals || !ir_cnt) { set_error("illico_stage_csc_f32: NULL buffer"); return 1; }
+    return launch_stage_csc(data, indices, (const long long*)indptr, gene_lb, n_genes_batch, plan, ir_vals, ir_cnt,
+                            (cudaStream_t)stream);
+}
+
+int illico_check_csr_sorted(const int32_t* indices, const int64_t* indptr, int64_t n_rows, int32_t* d_flag, void* stream) {
+    int sorted = -1;
+    if (launch_check_csr_sorted(indices, (const long long*)indptr, n_rows, d_flag, &sorted, (cudaStream_t)stream)) return -1;
+    return sorted;
+}
+
+size_t illico_rank_workspace_bytes(const illico_plan_t* plan, int32_t n_genes_batch) {
+    if (check_plan(plan)) return 0;
+    size_t ctas = (size_t)max_resident_ctas();
+    if ((size_t)n_genes_batch < ctas) ctas = (size_t)(n_genes_batch > 0 ? n_genes_batch : 1);
+    size_t per_cta = plan->ref_group >= 0 ? 4 * (size_t)plan->max_group_size * sizeof(uint32_t)
+                                          : ovr_slab_qwords(plan) * 8;
+    return ctas * per_cta + 256;
+}
+
+int illico_rank_ovr(const float* ir_vals, const uint32_t* ir_cnt, int32_t n_genes_batch, const illico_plan_t* plan,
+                    const illico_flags_t* flags, double* results, int64_t result_group_stride, void* workspace,
+                    size_t workspace_bytes, const illico_debug_t* dbg, void* stream) {
+    if (check_plan(plan)) return 1;
+    if (plan->ref_group >= 0) { set_error("illico_rank_ovr: plan has a reference group"); return 1; }
+    if (!flags || !results || !workspace) { set_error("illico_rank_ovr: NULL argument"); return 1; }
+    return launch_ovr(ir_vals, ir_cnt, n_genes_batch, plan, flags, results, result_group_stride, workspace,
+                      workspace_bytes, dbg, (cudaStream_t)stream);
+}
+
+int illico_rank_ovo(const float* ir_vals, const uint32_t* ir_cnt, int32_t n_genes_batch, const illico_plan_t* plan,
+                    const illico_flags_t* flags, double* results, int64_t result_group_stride, void* workspace,
+                    size_t workspace_bytes, const illico_debug_t* dbg, void* stream) {
+    if (check_plan(plan)) return 1;
+    if (plan->ref_group < 0) { set_error("illico_rank_ovo: plan has no reference group"); return 1; }
+    if (!flags || !results || !workspace) { set_error("illico_rank_ovo: NULL argument"); return 1; }
+    return launch_ovo(ir_vals, ir_cnt, n_genes_batch, plan, flags, results, result_group_stride, workspace,
+                      workspace_bytes, dbg, (cudaStream_t)stream);
+}
+
+// ---- the six dispatchers ------------------------------------------------------------------------------
+#define ILLICO_CHECK_BUF(b)                                                            \
+    if (!(b) || !(b)->ir_vals || !(b)->ir_cnt || !(b)->workspace) {                    \
+        set_error("batch buffers missing");                                            \
+        return 1;                                                                      \
+    }
+
+int illico_ovr_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t nb, const illico_plan_t* plan,
+                         const illico_flags_t* flags, const illico_batch_buffers_t* buf, double* results,
+                         int64_t gstride, const illico_debug_t* dbg, void* stream) {
+    ILLICO_CHECK_BUF(buf);
+    if (illico_stage_dense_f32(X, ld, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
+    return illico_rank_ovr(buf->ir_vals, buf->ir_cnt, nb, plan, flags, results, gstride, buf->workspace,
+                           buf->workspace_bytes, dbg, stream);
+}
+int illico_ovo_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t nb, const illico_plan_t* plan,
+                         const illico_flags_t* flags, const illico_batch_buffers_t* buf, double* results,
+                         int64_t gstride, const illico_debug_t* dbg, void* stream) {
+    ILLICO_CHECK_BUF(buf);
+    if (illico_stage_dense_f32(X, ld, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
+    return illico_rank_ovo(buf->ir_vals, buf->ir_cnt, nb, plan, flags, results, gstride, buf->workspace,
+                           buf->workspace_bytes, dbg, stream);
+}
+int illico_ovr_csr_f32(const float* data, const int32_t* indices, const int64_t* indptr, int32_t gene_lb, int32_t nb,
+                       const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf,
+                       double* results, int64_t gstride, const illico_debug_t* dbg, void* stream) {
+    ILLICO_CHECK_BUF(buf);
+    if (illico_zero_counts(buf->ir_cnt, nb, plan, stream)) return 1;
+    if (illico_stage_csr_f32(data, indices, indptr, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
+    return illico_rank_ovr(buf->ir_vals, buf->ir_cnt, nb, plan, flags, results, gstride, buf->workspace,
+                           buf->workspace_bytes, dbg, stream);
+}
+int illico_ovo_csr_f32(const float* data, const int32_t* indices, const int64_t* indptr, int32_t gene_lb, int32_t nb,
+                       const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf,
+                       double* results, int64_t gstride, const illico_debug_t* dbg, void* stream) {
+    ILLICO_CHECK_BUF(buf);
+    if (illico_zero_counts(buf->ir_cnt, nb, plan, stream)) return 1;
+    if (illico_stage_csr_f32(data, indices, indptr, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
+    return illico_rank_ovo(buf->ir_vals, buf->ir_cnt, nb, plan, flags, results, gstride, buf->workspace,
+                           buf->workspace_bytes, dbg, stream);
+}
+int illico_ovr_csc_f32(const float* data, const int32_t* indices, const int64_t* indptr, int32_t gene_lb, int32_t nb,
+                       const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf,
+                       double* results, int64_t gstride, const illico_debug_t* dbg, void* stream) {
+    ILLICO_CHECK_BUF(buf);
+    if (illico_zero_counts(buf->ir_cnt, nb, plan, stream)) return 1;
+    if (illico_stage_csc_f32(data, indices, indptr, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
+    return illico_rank_ovr(buf->ir_vals, buf->ir_cnt, nb, plan, flags, results, gstride, buf->workspace,
+                           buf->workspace_bytes, dbg, stream);
+}
+int illico_ovo_csc_f32(const float* data, const int32_t* indices, const int64_t* indptr, int32_t gene_lb, int32_t nb,
+                       const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf,
+                       double* results, int64_t gstride, const illico_debug_t* dbg, void* stream) {
+    ILLICO_CHECK_BUF(buf);
+    if (illico_zero_counts(buf->ir_cnt, nb, plan, stream)) return 1;
+    if (illico_stage_csc_f32(data, indices, indptr, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
+    return illico_rank_ovo(buf->ir_vals, buf->ir_cnt, nb, plan, flags, results, gstride, buf->workspace,
+                           buf->workspace_bytes, dbg, stream);
+}
+
+}  // extern "C"

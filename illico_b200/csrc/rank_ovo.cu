@@ -1,0 +1,356 @@
+// rank_ovo.cu -- one-versus-reference Mann-Whitney U on group-segmented non-zero lists (sm_100a).
+//
+// Replaces illico/ovo/dense_ovo.py:15-137, illico/ovo/sparse_ovo.py:22-158 and the merge
+// illico/utils/ranking.py:52-158.  The reference re-walks the whole sorted control column for every
+// perturbation (G x n_ref steps per gene).  Here the control's non-zero values are sorted ONCE per gene
+// into shared memory and every perturbation value is ranked against it by binary search:
+//
+//     2U_g = sum_{v in g} ( 2 #{ref > v} + #{ref == v} )                      
+//     T_g  = T_ref + sum_{distinct v in g} [ (a+b)^3 - (a+b) - (a^3 - a) ] + (Z^3 - Z)
+//
+// with a / b the multiplicity of v in the control / the perturbation and Z the number of zeros of the
+// pair (zeros are never stored: they are one analytic tie block, for dense input too).  Everything is
+// exact integer arithmetic; the f64 epilogue follows illico/utils/math.py:95-118 operation by operation.
+//
+// One CTA per gene (persistent, grid-strided).  Perturbations are processed in three tiers by their
+// number of non-zeros m:  m <= small_cap  one THREAD per group (insertion sort in a private shared
+// column), m <= WARP_CAP one WARP per group (bitonic sort in shared memory), larger groups one at a time
+// by the whole CTA (radix sort in the CTA's global slab).
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "sort.cuh"
+
+namespace illico {
+
+constexpr int OVO_THREADS = 512;
+constexpr int OVO_NW = OVO_THREADS / 32;
+constexpr int WARP_CAP = 1024;   // keys per warp buffer in the warp tier
+constexpr int GROUP_CHUNK = 1024;  // groups handled per sweep (bounds the deferred lists)
+
+struct OvoParams {
+    const float* ir_vals;
+    const uint32_t* ir_cnt;
+    int n_genes;
+    illico_plan_t plan;
+    illico_flags_t flags;
+    double* results;
+    long long gstride;
+    uint32_t* slab;          // global scratch, slab_words per CTA
+    long long slab_words;
+    int ref_cap;             // capacity (keys) of each of the two control buffers
+    int small_cap;           // thread-tier capacity (keys per thread)
+    int scratch_words;       // shared scratch (control ping-pong partner, later the tier buffers)
+    long long* dbg_u2;
+    double* dbg_tie;
+    long long* dbg_tie_exact;
+};
+
+struct RefInfo {
+    const uint32_t* keys;  // sorted non-zero control keys
+    int nnz;               // how many
+    int npos;              // control values > 0
+    long long zeros;       // control zeros
+    long long n_ref;
+    unsigned long long tie;  // sum over control non-zero runs of a^3 - a
+    double sum;              // sum of f(x) over the control
+};
+
+// contribution of one distinct perturbation value (key, multiplicity b)
+__device__ __forceinline__ void rank_value(const RefInfo& R, uint32_t key, long long b, unsigned long long& u2,
+                                           unsigned long long& tie) {
+    int lo = lower_bound_u32(R.keys, R.nnz, key);
+    int hi = lo;
+    if (lo < R.nnz && R.keys[lo] == key) hi = upper_bound_u32(R.keys, R.nnz, key);
+    long long a = hi - lo;
+    long long gt = (long long)(R.nnz - hi) + ((key < KEY_ZERO) ? R.zeros : 0);
+    u2 += (unsigned long long)(b * (2 * gt + a));
+    long long t = a + b;
+    tie += (unsigned long long)(cube_minus(t) - cube_minus(a));
+}
+
+__device__ __forceinline__ void finalize_group(const OvoParams& P, const RefInfo& R, int j, int g, long long m,
+                                               unsigned long long u2, unsigned long long tie_nz, double sum) {
+    const long long n_t = P.plan.group_size[g];
+    const long long z_t = n_t - m;
+    const long long Z = R.zeros + z_t;
+    u2 += (unsigned long long)(z_t * (2ll * R.npos + R.zeros));
+    const unsigned long long tie_exact = R.tie + tie_nz + (unsigned long long)cube_minus(Z);
+    // Every partial sum of the reference's sequential f64 accumulation is an exact integer while the
+    // total stays below 2^53 (pairs of up to 208 063 cells), so the exact sum converts without rounding.
+    const double tie = (double)tie_exact;
+    const double U = (double)u2 / 2.0;
+    const double mu = (double)(R.n_ref * n_t) / 2.0;
+    const double cc = P.flags.use_continuity ? 0.5 : 0.0;
+    const double p = compute_pval(R.n_ref, n_t, R.n_ref + n_t, P.flags.tie_correct ? tie : 0.0, U, mu, cc,
+                                  P.flags.alternative);
+    const double mean_t = sum / (double)n_t;
+    const double mean_r = R.sum / (double)R.n_ref;
+    const double fc = (mean_r == 0.0) ? INFINITY : mean_t / mean_r;
+    double* o = P.results + (long long)g * P.gstride + (long long)j * 3;
+    o[0] = p; o[1] = U; o[2] = fc;
+    const long long di = (long long)g * P.n_genes + j;
+    if (P.dbg_u2) P.dbg_u2[di] = (long long)u2;
+    if (P.dbg_tie) P.dbg_tie[di] = tie;
+    if (P.dbg_tie_exact) P.dbg_tie_exact[di] = (long long)tie_exact;
+}
+
+__global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const illico_plan_t& pl = P.plan;
+    const int S = pl.n_segments, G = pl.n_groups, ref = pl.ref_group;
+
+    // ---- shared carve-up
+    uint32_t* refA = smem;                                  // [ref_cap]
+    uint32_t* scratch = refA + P.ref_cap;                   // [scratch_words] (>= ref_cap)
+    uint32_t* hist = scratch + P.scratch_words;             // [OVO_NW * 256]
+    uint32_t* aux = hist + OVO_NW * 256;                    // [RADIX_AUX_WORDS]
+    int* mlist = (int*)(aux + RADIX_AUX_WORDS);             // [GROUP_CHUNK]
+    int* blist = mlist + GROUP_CHUNK;                       // [GROUP_CHUNK]
+    int* counters = blist + GROUP_CHUNK;                    // [4]
+    double* redd = (double*)(counters + 4);                 // [32]
+    unsigned long long* redu = (unsigned long long*)(redd + 32);  // [32]
+
+    uint32_t* slab = P.slab + (long long)blockIdx.x * P.slab_words;
+    const int maxg = pl.max_group_size;
+    uint32_t* gA = slab;            // block-tier group buffers (global)
+    uint32_t* gB = slab + maxg;
+    const int nwb = min(OVO_NW, P.scratch_words / WARP_CAP);  // warps that own a warp-tier buffer
+
+    const int ref_s0 = pl.group_seg[ref], ref_s1 = pl.group_seg[ref + 1];
+
+    for (int j = blockIdx.x; j < P.n_genes; j += gridDim.x) {
+        const uint32_t* cnt = P.ir_cnt + (long long)j * S;
+        const float* vals = P.ir_vals + (long long)j * pl.slot_cap;
+
+        // ================= phase 1: control keys, sorted once per gene =================
+        // offsets of the control's segments (few): serial prefix by thread 0 into hist[] (free now)
+        if (tid == 0) {
+            uint32_t acc = 0;
+            for (int s = ref_s0; s < ref_s1; ++s) { hist[s - ref_s0] = acc; acc += cnt[s]; }
+            hist[ref_s1 - ref_s0] = acc;
+        }
+        __syncthreads();
+        const int nref_nz = (int)hist[ref_s1 - ref_s0];
+        // control keys live in shared memory when they fit, else in this CTA's global slab
+        const bool ref_smem = nref_nz <= P.ref_cap;
+        uint32_t* rA = ref_smem ? refA : slab + 2ll * maxg;
+        uint32_t* rB = ref_smem ? scratch : slab + 3ll * maxg;
+        double rsum = 0.0;
+        for (int s = ref_s0 + w; s < ref_s1; s += OVO_NW) {
+            const uint32_t off = hist[s - ref_s0];
+            const int c = (int)cnt[s];
+            const float* src = vals + pl.seg_base[s];
+            for (int i = lane; i < c; i += 32) {
+                float v = src[i];
+                rA[off + i] = f2key(v);
+                rsum += fc_value(v, P.flags.is_log1p);
+            }
+        }
+        __syncthreads();
+        rsum = block_sum<double>(rsum, redd);
+        const uint32_t* rk = block_radix_sort(rA, rB, nref_nz, hist, aux);
+        if (rk != rA) {  // keep the sorted keys in rA: rB is recycled as tier scratch
+            for (int i = tid; i < nref_nz; i += OVO_THREADS) rA[i] = rB[i];
+            __syncthreads();
+        }
+        RefInfo R;
+        R.keys = rA;
+        R.nnz = nref_nz;
+        R.n_ref = pl.group_size[ref];
+        R.zeros = R.n_ref - nref_nz;
+        R.npos = nref_nz - upper_bound_u32(rA, nref_nz, KEY_ZERO);
+        R.sum = rsum;
+        {
+            unsigned long long t = 0;
+            for (int i = tid; i < nref_nz; i += OVO_THREADS) {
+                uint32_t k = rA[i];
+                if (i == 0 || rA[i - 1] != k) {
+                    long long a = upper_bound_u32(rA, nref_nz, k) - i;
+                    t += (unsigned long long)cube_minus(a);
+                }
+            }
+            R.tie = block_sum<unsigned long long>(t, redu);
+        }
+
+        // ================= phase 2: perturbations, in chunks of GROUP_CHUNK groups =================
+        for (int g0 = 0; g0 < G; g0 += GROUP_CHUNK) {
+            const int g1 = min(G, g0 + GROUP_CHUNK);
+            if (tid == 0) { counters[0] = 0; counters[1] = 0; }
+            __syncthreads();
+            // ---- thread tier
+            for (int g = g0 + tid; g < g1; g += OVO_THREADS) {
+                if (g == ref) {
+                    // control row: the sparse kernels' convention (ovo/sparse_ovo.py:140-143); fold change of the
+                    // control against itself (utils/math.py:191-192)
+                    double* o = P.results + (long long)g * P.gstride + (long long)j * 3;
+                    double mean_r = R.sum / (double)R.n_ref;
+                    o[0] = 1.0; o[1] = -1.0; o[2] = (mean_r == 0.0) ? INFINITY : mean_r / mean_r;
+                    const long long di = (long long)g * P.n_genes + j;
+                    if (P.dbg_u2) P.dbg_u2[di] = -2;
+                    if (P.dbg_tie) P.dbg_tie[di] = 0.0;
+                    if (P.dbg_tie_exact) P.dbg_tie_exact[di] = 0;
+                    continue;
+                }
+                const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
+                int m = 0;
+                for (int s = s0; s < s1; ++s) m += (int)cnt[s];
+                if (m > P.small_cap) {
+                    mlist[atomicAdd(&counters[0], 1)] = g;
+                    continue;
+                }
+                uint32_t* col = scratch + tid;  // private column: element k at col[k * OVO_THREADS]
+                double sum = 0.0;
+                int k = 0;
+                for (int s = s0; s < s1; ++s) {
+                    const int c = (int)cnt[s];
+                    const float* src = vals + pl.seg_base[s];
+                    for (int i = 0; i < c; ++i) {
+                        float v = src[i];
+                        uint32_t key = f2key(v);
+                        // insertion sort, ascending
+                        int q = k - 1;
+                        while (q >= 0 && col[q * OVO_THREADS] > key) { col[(q + 1) * OVO_THREADS] = col[q * OVO_THREADS]; --q; }
+                        col[(q + 1) * OVO_THREADS] = key;
+                        ++k;
+                    }
+                }
+                unsigned long long u2 = 0, tie = 0;
+                int i = 0;
+                while (i < m) {
+                    uint32_t key = col[i * OVO_THREADS];
+                    int r = i + 1;
+                    while (r < m && col[r * OVO_THREADS] == key) ++r;
+                    rank_value(R, key, r - i, u2, tie);
+                    sum += (double)(r - i) * fc_value(key2f(key), P.flags.is_log1p);
+                    i = r;
+                }
+                finalize_group(P, R, j, g, m, u2, tie, sum);
+            }
+            __syncthreads();
+            // ---- warp tier
+            const int nm = counters[0];
+            for (int e = w; e < nm && w < nwb; e += nwb) {
+                const int g = mlist[e];
+                const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
+                int m = 0;
+                for (int s = s0; s < s1; ++s) m += (int)cnt[s];
+                if (m > WARP_CAP) {
+                    if (lane == 0) blist[atomicAdd(&counters[1], 1)] = g;
+                    continue;
+                }
+                uint32_t* buf = scratch + w * WARP_CAP;
+                int k = 0;
+                for (int s = s0; s < s1; ++s) {
+                    const int c = (int)cnt[s];
+                    const float* src = vals + pl.seg_base[s];
+                    for (int i = lane; i < c; i += 32) buf[k + i] = f2key(src[i]);
+                    k += c;
+                }
+                const int Pw = next_pow2(m);
+                for (int i = m + lane; i < Pw; i += 32) buf[i] = 0xffffffffu;
+                __syncwarp();
+                warp_bitonic_sort(buf, Pw, lane);
+                unsigned long long u2 = 0, tie = 0;
+                double sum = 0.0;
+                for (int i = lane; i < m; i += 32) {
+                    uint32_t key = buf[i];
+                    sum += fc_value(key2f(key), P.flags.is_log1p);
+                    if (i == 0 || buf[i - 1] != key) {
+                        long long b = upper_bound_u32(buf, m, key) - i;
+                        rank_value(R, key, b, u2, tie);
+                    }
+                }
+                u2 = warp_sum_u64(u2);
+                tie = warp_sum_u64(tie);
+                sum = warp_sum_f64(sum);
+                if (lane == 0) finalize_group(P, R, j, g, m, u2, tie, sum);
+                __syncwarp();
+            }
+            __syncthreads();
+            // ---- block tier: one group at a time, sorted in the CTA's global slab
+            const int nb = counters[1];
+            for (int e = 0; e < nb; ++e) {
+                const int g = blist[e];
+                const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
+                int m = 0;
+                for (int s = s0; s < s1; ++s) {
+                    const int c = (int)cnt[s];
+                    const float* src = vals + pl.seg_base[s];
+                    for (int i = tid; i < c; i += OVO_THREADS) gA[m + i] = f2key(src[i]);
+                    m += c;
+                }
+                __syncthreads();
+                const uint32_t* gk = block_radix_sort(gA, gB, m, hist, aux);
+                unsigned long long u2 = 0, tie = 0;
+                double sum = 0.0;
+                for (int i = tid; i < m; i += OVO_THREADS) {
+                    uint32_t key = gk[i];
+                    sum += fc_value(key2f(key), P.flags.is_log1p);
+                    if (i == 0 || gk[i - 1] != key) {
+                        long long b = upper_bound_u32(gk, m, key) - i;
+                        rank_value(R, key, b, u2, tie);
+                    }
+                }
+                u2 = block_sum<unsigned long long>(u2, redu);
+                tie = block_sum<unsigned long long>(tie, redu);
+                sum = block_sum<double>(sum, redd);
+                if (tid == 0) finalize_group(P, R, j, g, m, u2, tie, sum);
+                __syncthreads();
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+size_t ovo_workspace_bytes(const illico_plan_t* plan, int n_ctas) {
+    return (size_t)n_ctas * 4 * (size_t)plan->max_group_size * sizeof(uint32_t);
+}
+
+int launch_ovo(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const illico_plan_t* plan,
+               const illico_flags_t* flags, double* results, long long gstride, void* workspace,
+               size_t workspace_bytes, const illico_debug_t* dbg, cudaStream_t stream) {
+    if (n_genes <= 0) return 0;
+    int dev = 0, sms = 0, max_smem = 0;
+    ILLICO_CUDA_OK(cudaGetDevice(&dev));
+    ILLICO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ILLICO_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+
+    OvoParams P;
+    P.ir_vals = ir_vals; P.ir_cnt = ir_cnt; P.n_genes = n_genes; P.plan = *plan; P.flags = *flags;
+    P.results = results; P.gstride = gstride;
+    P.dbg_u2 = dbg ? (long long*)dbg->u2 : nullptr; P.dbg_tie = dbg ? dbg->tie_sum : nullptr;
+    P.dbg_tie_exact = dbg ? (long long*)dbg->tie_exact : nullptr;
+
+    // shared memory: fixed part + control buffer + scratch, sized so that two CTAs fit on one SM.
+    // Genes whose control has more non-zeros than ref_cap keep the control in the CTA's global slab.
+    const size_t fixed = (size_t)(OVO_NW * 256 + RADIX_AUX_WORDS + 2 * GROUP_CHUNK + 4) * 4 + 32 * 8 * 2 + 64;
+    const int small_cap = 22;
+    const int scratch_words = small_cap * OVO_THREADS;  // 11264 words: 22 keys per thread / 11 warp buffers
+    int ref_cap = (plan->ref_group_size + 3) & ~3;
+    if (ref_cap < 4) ref_cap = 4;
+    if (ref_cap > scratch_words) ref_cap = scratch_words;  // the ping-pong partner is the scratch area
+    const size_t need = fixed + (size_t)(ref_cap + scratch_words) * 4;
+    if (need > (size_t)max_smem) { set_error("ovo_kernel needs %zu bytes of shared memory", need); return 1; }
+    P.ref_cap = ref_cap; P.small_cap = small_cap; P.scratch_words = scratch_words;
+
+    ILLICO_CUDA_OK(cudaFuncSetAttribute(ovo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    int occ = 0;
+    ILLICO_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ovo_kernel, OVO_THREADS, need));
+    if (occ < 1) { set_error("ovo_kernel does not fit: %zu bytes of shared memory", need); return 1; }
+    int grid = sms * occ;
+    if (grid > n_genes) grid = n_genes;
+    const size_t slab_words = 4 * (size_t)plan->max_group_size;
+    if ((size_t)grid * slab_words * 4 > workspace_bytes) {
+        grid = (int)(workspace_bytes / (slab_words * 4));
+        if (grid < 1) { set_error("rank workspace too small: %zu bytes", workspace_bytes); return 1; }
+    }
+    P.slab = (uint32_t*)workspace; P.slab_words = (long long)slab_words;
+    ovo_kernel<<<grid, OVO_THREADS, need, stream>>>(P);
+    count_launch();
+    ILLICO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace illico

@@ -1,0 +1,358 @@
+// rank_ovr.cu -- one-versus-rest Mann-Whitney U on group-segmented non-zero lists (sm_100a).
+//
+// Replaces illico/ovr/dense_ovr.py:15-80, illico/ovr/sparse_ovr.py:23-97 and
+// illico/utils/ranking.py:7-49.  The reference argsorts every gene column and scatters mid-ranks into
+// per-group sums.  Here labels never move: per gene the kernel builds a RANK ORACLE over the column's
+// non-zero values and every group looks its values up in it:
+//
+//   path H (few distinct values, e.g. raw counts): shared-memory hash table value -> multiplicity, its
+//           <= 2048 distinct values sorted and prefix-summed; lookup = one hash probe.
+//   path S (continuous data): keys-only block radix sort (shared memory when the column fits, else the
+//           CTA's global slab); lookup = lower/upper bound.
+//
+// A run of equal values at sorted positions [lo, hi) has doubled mid-rank r2 = lo + hi + 1 (an integer,
+// SURVEY.md appendix A.1).  Zeros are not stored: with n0 zeros and n_neg negative values, positives
+// are shifted by n0 and the zero block has r2 = 2 n_neg + n0 + 1 (appendix A.3, extended to negatives).
+// 2R_g, 2U_g and the tie terms are exact integers; the tie sum is accumulated in the reference's order
+// when it exceeds 2^53 (appendix A.4).
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "sort.cuh"
+
+namespace illico {
+
+constexpr int OVR_THREADS = 512;
+constexpr int OVR_NW = OVR_THREADS / 32;
+constexpr int HASH_CAP = 4096;
+constexpr int MAX_DISTINCT = 2048;
+constexpr uint32_t HASH_EMPTY = 0u;
+
+struct OvrParams {
+    const float* ir_vals;
+    const uint32_t* ir_cnt;
+    int n_genes;
+    illico_plan_t plan;
+    illico_flags_t flags;
+    double* results;
+    long long gstride;
+    unsigned long long* slab;  // global scratch, slab_qwords (8-byte words) per CTA
+    long long slab_qwords;
+    int sort_cap;              // keys per shared-memory sort buffer (path S)
+    long long* dbg_u2;
+    double* dbg_tie;
+    long long* dbg_tie_exact;
+};
+
+__device__ __forceinline__ uint32_t hash_slot(uint32_t key) { return (key * 2654435761u) >> 20; }  // 12 bits
+
+__device__ __forceinline__ void hash_insert(uint32_t* hkeys, uint32_t* hvals, int* ndist, int* overflow, uint32_t key,
+                                            uint32_t c) {
+    if (*(volatile int*)ndist >= MAX_DISTINCT) { *overflow = 1; return; }
+    uint32_t h = hash_slot(key);
+    for (;;) {
+        uint32_t prev = atomicCAS(&hkeys[h], HASH_EMPTY, key);
+        if (prev == HASH_EMPTY) atomicAdd(ndist, 1);
+        if (prev == HASH_EMPTY || prev == key) { atomicAdd(&hvals[h], c); return; }
+        h = (h + 1) & (HASH_CAP - 1);
+    }
+}
+__device__ __forceinline__ uint32_t hash_find(const uint32_t* hkeys, uint32_t key) {
+    uint32_t h = hash_slot(key);
+    while (hkeys[h] != key) h = (h + 1) & (HASH_CAP - 1);
+    return h;
+}
+
+// n0^3 - n0 the way the sparse reference kernel forms it: n0 is a float64 (ovr/sparse_ovr.py:49,83)
+__device__ __forceinline__ double zero_block_term_f64(long long n0) {
+    double x = (double)n0;
+    double c = __dmul_rn(__dmul_rn(x, x), x);
+    return __dsub_rn(c, x);
+}
+
+__global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const illico_plan_t& pl = P.plan;
+    const int S = pl.n_segments, G = pl.n_groups;
+    const long long n = pl.n_cells;
+
+    // ---- shared carve-up: region0 = hash table (path H) or sort ping-pong (path S)
+    const int region0_words = max(2 * HASH_CAP, 2 * P.sort_cap);
+    uint32_t* hkeys = smem;
+    uint32_t* hvals = smem + HASH_CAP;
+    uint32_t* sortA = smem;
+    uint32_t* sortB = smem + P.sort_cap;
+    uint32_t* hist = smem + region0_words;        // [OVR_NW*256] path S;  path H: dkeys | dcnt
+    uint32_t* dkeys = hist;                       // [MAX_DISTINCT]
+    uint32_t* dcnt = hist + MAX_DISTINCT;         // [MAX_DISTINCT]
+    uint32_t* aux = hist + OVR_NW * 256;          // [RADIX_AUX_WORDS]
+    int* sc = (int*)(aux + RADIX_AUX_WORDS);      // [8] scalars
+    double* redd = (double*)(sc + 8);             // [32]
+    unsigned long long* redu = (unsigned long long*)(redd + 32);  // [32]
+    double* tie_slot = (double*)(redu + 32);      // [1]
+
+    unsigned long long* slab = P.slab + (long long)blockIdx.x * P.slab_qwords;
+    unsigned long long* seg_r2 = slab;                       // [S]
+    double* seg_sum = (double*)(slab + S);                   // [S]
+    uint32_t* gsortA = (uint32_t*)(slab + 2ll * S);          // [n_cells]
+    uint32_t* gsortB = gsortA + ((n + 1) & ~1ll);            // [n_cells]
+
+    const double cc = P.flags.use_continuity ? 0.5 : 0.0;
+
+    for (int j = blockIdx.x; j < P.n_genes; j += gridDim.x) {
+        const uint32_t* cnt = P.ir_cnt + (long long)j * S;
+        const float* vals = P.ir_vals + (long long)j * pl.slot_cap;
+
+        // ================= phase A: value -> multiplicity hash (path H attempt) =================
+        for (int i = tid; i < 2 * HASH_CAP; i += OVR_THREADS) smem[i] = 0;
+        if (tid < 8) sc[tid] = 0;  // [0] ndist [1] overflow [2] cursor [3] dn
+        __syncthreads();
+        unsigned long long my_nnz = 0;
+        for (int s0 = 0; s0 < S; s0 += OVR_THREADS) {
+            const int s = s0 + tid;
+            const int c = (s < S) ? (int)cnt[s] : 0;
+            my_nnz += c;
+            const float* src = vals + ((s < S) ? pl.seg_base[s] : 0);
+            int maxc = c;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(FULL, maxc, o));
+            for (int i = 0; i < maxc; ++i) {
+                const bool act = i < c;
+                uint32_t key = act ? f2key(src[i]) : HASH_EMPTY;
+                if (act && key == HASH_EMPTY) key = 1u;  // only a NaN payload maps here
+                const unsigned peers = __match_any_sync(FULL, key);
+                if (act && lane == __ffs(peers) - 1 && !*(volatile int*)&sc[1])
+                    hash_insert(hkeys, hvals, &sc[0], &sc[1], key, __popc(peers));
+            }
+        }
+        const long long nnz = (long long)block_sum<unsigned long long>(my_nnz, redu);  // syncs
+        const long long n0 = n - nnz;
+        const bool path_s = sc[1] != 0 || sc[0] > MAX_DISTINCT;
+        long long n_neg = 0;
+        unsigned long long tie_nz_exact = 0;
+        const uint32_t* sk = nullptr;  // sorted keys (path S)
+        __syncthreads();
+
+        if (!path_s) {
+            // ---- distinct values: compact, sort, prefix
+            for (int t = tid; t < HASH_CAP; t += OVR_THREADS)
+                if (hkeys[t] != HASH_EMPTY) {
+                    int idx = atomicAdd(&sc[3], 1);
+                    dkeys[idx] = hkeys[t];
+                    dcnt[idx] = hvals[t];
+                }
+            __syncthreads();
+            const int D = sc[3];
+            const int Pd = max(2, next_pow2(D));
+            for (int i = D + tid; i < Pd; i += OVR_THREADS) { dkeys[i] = 0xffffffffu; dcnt[i] = 0; }
+            __syncthreads();
+            block_bitonic_sort_pairs(dkeys, dcnt, Pd);
+            // exclusive prefix of dcnt: 4 consecutive entries per thread (MAX_DISTINCT = 4 * OVR_THREADS)
+            uint32_t c4[4], loc = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int i = tid * 4 + q;
+                c4[q] = (i < D) ? dcnt[i] : 0;
+                loc += c4[q];
+            }
+            uint32_t incl = warp_incl_scan(loc, lane);
+            if (lane == 31) aux[tid >> 5] = incl;
+            __syncthreads();
+            uint32_t base = incl - loc;
+            for (int ww = 0; ww < (tid >> 5); ++ww) base += aux[ww];
+            unsigned long long t_exact = 0, negs = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int i = tid * 4 + q;
+                if (i < D) {
+                    const uint32_t key = dkeys[i];
+                    const uint32_t lo = base, hi = base + c4[q];
+                    unsigned long long r2 = (unsigned long long)lo + hi + 1;
+                    if (key > KEY_ZERO) r2 += 2ull * (unsigned long long)n0;
+                    hvals[hash_find(hkeys, key)] = (uint32_t)r2;  // table now maps value -> doubled mid-rank
+                    t_exact += (unsigned long long)cube_minus((long long)c4[q]);
+                    if (key < KEY_ZERO) negs += c4[q];
+                }
+                base += c4[q];
+            }
+            tie_nz_exact = block_sum<unsigned long long>(t_exact, redu);
+            n_neg = (long long)block_sum<unsigned long long>(negs, redu);
+            // ---- ordered f64 accumulation when the exact sum may not be representable
+            const unsigned long long zterm = (unsigned long long)cube_minus(n0);
+            const bool sparse_order = P.flags.tie_order == ILLICO_TIES_SPARSE;
+            const bool need_walk = sparse_order ? ((double)tie_nz_exact >= TWO53)
+                                                : ((double)tie_nz_exact + (double)zterm >= TWO53);
+            if (tid == 0) {
+                double acc;
+                if (!need_walk) {
+                    acc = sparse_order ? (double)tie_nz_exact : (double)(tie_nz_exact + zterm);
+                } else {
+                    acc = 0.0;
+                    bool zero_done = sparse_order || n0 == 0;
+                    for (int i = 0; i < D; ++i) {
+                        if (!zero_done && dkeys[i] > KEY_ZERO) { acc += (double)(long long)zterm; zero_done = true; }
+                        acc += (double)cube_minus((long long)dcnt[i]);
+                    }
+                    if (!zero_done) acc += (double)(long long)zterm;
+                }
+                if (sparse_order) acc = __dadd_rn(acc, zero_block_term_f64(n0));
+                *tie_slot = acc;
+            }
+            __syncthreads();
+        } else {
+            // ---- path S: gather keys, sort, scan runs
+            const bool in_smem = nnz <= P.sort_cap;
+            uint32_t* A = in_smem ? sortA : gsortA;
+            uint32_t* B = in_smem ? sortB : gsortB;
+            for (int s = tid; s < S; s += OVR_THREADS) {
+                const int c = (int)cnt[s];
+                if (c == 0) continue;
+                const float* src = vals + pl.seg_base[s];
+                const int at = atomicAdd(&sc[2], c);
+                for (int i = 0; i < c; ++i) A[at + i] = f2key(src[i]);
+            }
+            __syncthreads();
+            sk = block_radix_sort(A, B, (int)nnz, hist, aux);
+            n_neg = lower_bound_u32(sk, (int)nnz, KEY_ZERO);
+            unsigned long long t_exact = 0;
+            for (int i = tid; i < (int)nnz; i += OVR_THREADS) {
+                const uint32_t k = sk[i];
+                if (i == 0 || sk[i - 1] != k) t_exact += (unsigned long long)cube_minus(upper_bound_u32(sk, (int)nnz, k) - i);
+            }
+            tie_nz_exact = block_sum<unsigned long long>(t_exact, redu);
+            const unsigned long long zterm = (unsigned long long)cube_minus(n0);
+            const bool sparse_order = P.flags.tie_order == ILLICO_TIES_SPARSE;
+            const bool need_walk = sparse_order ? ((double)tie_nz_exact >= TWO53)
+                                                : ((double)tie_nz_exact + (double)zterm >= TWO53);
+            if (tid == 0) {
+                double acc;
+                if (!need_walk) {
+                    acc = sparse_order ? (double)tie_nz_exact : (double)(tie_nz_exact + zterm);
+                } else {
+                    acc = 0.0;
+                    bool zero_done = sparse_order || n0 == 0;
+                    int i = 0;
+                    const int m = (int)nnz;
+                    while (i < m) {
+                        const uint32_t k = sk[i];
+                        int r = i + 1;
+                        while (r < m && sk[r] == k) ++r;
+                        if (!zero_done && k > KEY_ZERO) { acc += (double)(long long)zterm; zero_done = true; }
+                        if (r - i > 1) acc += (double)cube_minus((long long)(r - i));
+                        i = r;
+                    }
+                    if (!zero_done) acc += (double)(long long)zterm;
+                }
+                if (sparse_order) acc = __dadd_rn(acc, zero_block_term_f64(n0));
+                *tie_slot = acc;
+            }
+            __syncthreads();
+        }
+        const double tie = *tie_slot;
+        const unsigned long long r2_zero = 2ull * (unsigned long long)n_neg + (unsigned long long)n0 + 1ull;
+
+        // ================= phase B: per-segment doubled rank sums and expression sums =================
+        for (int s = tid; s < S; s += OVR_THREADS) {
+            const int c = (int)cnt[s];
+            const float* src = vals + pl.seg_base[s];
+            unsigned long long acc = 0;
+            double sum = 0.0;
+            for (int i = 0; i < c; ++i) {
+                const float v = src[i];
+                uint32_t key = f2key(v);
+                if (key == HASH_EMPTY) key = 1u;
+                if (!path_s) {
+                    acc += hvals[hash_find(hkeys, key)];
+                } else {
+                    const int lo = lower_bound_u32(sk, (int)nnz, key), hi = upper_bound_u32(sk, (int)nnz, key);
+                    acc += (unsigned long long)lo + hi + 1 + ((key > KEY_ZERO) ? 2ull * (unsigned long long)n0 : 0ull);
+                }
+                sum += fc_value(v, P.flags.is_log1p);
+            }
+            seg_r2[s] = acc;
+            seg_sum[s] = sum;
+        }
+        __syncthreads();
+
+        // ================= phase C: per-group U and p; expression sums parked in the fold-change slot ============
+        double my_total = 0.0;
+        for (int g = tid; g < G; g += OVR_THREADS) {
+            unsigned long long R2 = 0;
+            double sum = 0.0;
+            long long nnz_g = 0;
+            for (int s = pl.group_seg[g]; s < pl.group_seg[g + 1]; ++s) { R2 += seg_r2[s]; sum += seg_sum[s]; nnz_g += cnt[s]; }
+            const long long n_t = pl.group_size[g], n_r = n - n_t;
+            R2 += (unsigned long long)(n_t - nnz_g) * r2_zero;
+            const long long u2 = 2 * n_r * n_t + n_t * (n_t + 1) - (long long)R2;
+            const double U = (double)u2 / 2.0;
+            const double mu = (double)(n_r * n_t) / 2.0;
+            const double p = compute_pval(n_r, n_t, n, P.flags.tie_correct ? tie : 0.0, U, mu, cc, P.flags.alternative);
+            double* o = P.results + (long long)g * P.gstride + (long long)j * 3;
+            o[0] = p; o[1] = U; o[2] = sum;
+            my_total += sum;
+            if (P.dbg_u2) P.dbg_u2[(long long)g * P.n_genes + j] = u2;
+        }
+        const double total = block_sum<double>(my_total, redd);
+        // ================= phase D: fold change (illico/utils/math.py:168-193, one-versus-rest branch) ============
+        for (int g = tid; g < G; g += OVR_THREADS) {
+            double* o = P.results + (long long)g * P.gstride + (long long)j * 3;
+            const double sum = o[2];
+            const long long n_t = pl.group_size[g];
+            const double mu_t = sum / (double)n_t;
+            const double mu_r = (total - sum) / (double)(n - n_t);
+            o[2] = (mu_r == 0.0) ? INFINITY : mu_t / mu_r;
+        }
+        if (tid == 0) {
+            if (P.dbg_tie) P.dbg_tie[j] = tie;
+            if (P.dbg_tie_exact) P.dbg_tie_exact[j] = (long long)(tie_nz_exact + (unsigned long long)cube_minus(n0));
+        }
+        __syncthreads();
+    }
+}
+
+size_t ovr_slab_qwords(const illico_plan_t* plan) {
+    return 2 * (size_t)plan->n_segments + (size_t)((plan->n_cells + 1) & ~1) + 2;
+}
+
+int launch_ovr(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const illico_plan_t* plan,
+               const illico_flags_t* flags, double* results, long long gstride, void* workspace,
+               size_t workspace_bytes, const illico_debug_t* dbg, cudaStream_t stream) {
+    if (n_genes <= 0) return 0;
+    int dev = 0, sms = 0, max_smem = 0;
+    ILLICO_CUDA_OK(cudaGetDevice(&dev));
+    ILLICO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ILLICO_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+
+    OvrParams P;
+    P.ir_vals = ir_vals; P.ir_cnt = ir_cnt; P.n_genes = n_genes; P.plan = *plan; P.flags = *flags;
+    P.results = results; P.gstride = gstride;
+    P.dbg_u2 = dbg ? (long long*)dbg->u2 : nullptr; P.dbg_tie = dbg ? dbg->tie_sum : nullptr;
+    P.dbg_tie_exact = dbg ? (long long*)dbg->tie_exact : nullptr;
+
+    // two CTAs per SM: ~113 KB each.  Fixed part: histogram / distinct table 16 KB + scalars.
+    const size_t fixed = (size_t)(OVR_NW * 256 + RADIX_AUX_WORDS + 8) * 4 + 32 * 8 * 2 + 8 + 64;
+    const size_t per_cta = (size_t)(max_smem + 1024) / 2 - 1024;
+    int sort_cap = (int)((per_cta - fixed) / 8) & ~3;
+    if (sort_cap < HASH_CAP) sort_cap = HASH_CAP;
+    P.sort_cap = sort_cap;
+    const size_t need = fixed + (size_t)2 * sort_cap * 4;
+
+    ILLICO_CUDA_OK(cudaFuncSetAttribute(ovr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    int occ = 0;
+    ILLICO_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ovr_kernel, OVR_THREADS, need));
+    if (occ < 1) { set_error("ovr_kernel does not fit: %zu bytes of shared memory", need); return 1; }
+    int grid = sms * occ;
+    if (grid > n_genes) grid = n_genes;
+    const size_t slab_q = ovr_slab_qwords(plan);
+    if ((size_t)grid * slab_q * 8 > workspace_bytes) {
+        grid = (int)(workspace_bytes / (slab_q * 8));
+        if (grid < 1) { set_error("rank workspace too small: %zu bytes", workspace_bytes); return 1; }
+    }
+    P.slab = (unsigned long long*)workspace; P.slab_qwords = (long long)slab_q;
+    ovr_kernel<<<grid, OVR_THREADS, need, stream>>>(P);
+    count_launch();
+    ILLICO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace illico

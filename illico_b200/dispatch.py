@@ -1,0 +1,114 @@
+"""The six batch dispatchers behind the reference's plug-in signature.
+
+    f(X, chunk_lb, chunk_ub, grpc, is_log1p, use_continuity, tie_correct, alternative)
+        -> (pvalues, statistics, fold_change)        each C-contiguous float64 [n_groups, chunk_ub - chunk_lb]
+
+(call site ``illico/asymptotic_wilcoxon.py:59-67``; registered like ``illico/utils/registry.py:193-202``).
+``X`` is a host ``ndarray``, a ``CSRMatrix`` / ``CSCMatrix`` namedtuple ``(data, indices, indptr, shape)``
+(``illico/utils/sparse/csc.py:10-11``), a scipy matrix, or an already resident :class:`DeviceMatrix`.
+Each call stages and ranks genes ``[chunk_lb, chunk_ub)`` on the current CUDA device through the C ABI.
+These functions can be dropped into the reference's own ``dispatcher_registry`` for A/B runs.
+"""
+from __future__ import annotations
+
+import threading
+from collections import OrderedDict, namedtuple
+
+import numpy as np
+import torch
+
+from .engine import CSC, CSR, DENSE, DeviceMatrix, Engine, make_flags
+
+CSCMatrix = namedtuple("CSCMatrix", ["data", "indices", "indptr", "shape"])
+CSRMatrix = namedtuple("CSRMatrix", ["data", "indices", "indptr", "shape"])
+
+_lock = threading.RLock()
+_engines: "OrderedDict[tuple, Engine]" = OrderedDict()
+_matrices: "OrderedDict[tuple, tuple]" = OrderedDict()
+_MAX_CACHE = 4
+
+
+def engine_for(grpc, device=None) -> Engine:
+    """One engine per (GroupContainer identity, device); tiny LRU so repeated batch calls reuse the plan."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    enc = np.asarray(grpc.encoded_groups)
+    key = (enc.__array_interface__["data"][0], enc.size, int(grpc.encoded_ref_group), str(dev))
+    with _lock:
+        eng = _engines.get(key)
+        if eng is None:
+            eng = Engine(grpc, dev)
+            _engines[key] = eng
+            while len(_engines) > _MAX_CACHE:
+                _engines.popitem(last=False)
+        else:
+            _engines.move_to_end(key)
+        return eng
+
+
+def _resident(X, fmt: str, eng: Engine) -> DeviceMatrix:
+    if isinstance(X, DeviceMatrix):
+        return X
+    arr = X if fmt == DENSE else X.data
+    key = (np.asarray(arr).__array_interface__["data"][0], tuple(X.shape), fmt, str(eng.device))
+    with _lock:
+        hit = _matrices.get(key)
+        if hit is not None:
+            _matrices.move_to_end(key)
+            return hit[0]
+        M = eng.upload_dense(X) if fmt == DENSE else eng.upload_sparse(X, fmt)
+        _matrices[key] = (M, X)  # keep the host object alive so the address stays unique
+        while len(_matrices) > 2:
+            _matrices.popitem(last=False)
+        return M
+
+
+def clear_caches() -> None:
+    with _lock:
+        _engines.clear()
+        _matrices.clear()
+
+
+def _dispatch(fmt: str, X, chunk_lb, chunk_ub, grpc, is_log1p, use_continuity, tie_correct, alternative, debug=None):
+    eng = engine_for(grpc)
+    M = _resident(X, fmt, eng)
+    lb, ub = int(chunk_lb), int(chunk_ub)
+    b = ub - lb
+    flags = make_flags(is_log1p, use_continuity, tie_correct, alternative, fmt)
+    res = torch.empty((eng.n_groups, max(b, 0), 3), dtype=torch.float64, device=eng.device)
+    eng.run_batch(M, lb, ub, flags, res, 0, debug)
+    host = res.cpu().numpy()
+    return (np.ascontiguousarray(host[:, :, 0]), np.ascontiguousarray(host[:, :, 1]),
+            np.ascontiguousarray(host[:, :, 2]))
+
+
+def _make(fmt: str, test: str):
+    def dispatcher(X, chunk_lb, chunk_ub, grpc, is_log1p, use_continuity=True, tie_correct=True,
+                   alternative="two-sided", debug=None):
+        is_ovo = int(grpc.encoded_ref_group) >= 0
+        if is_ovo != (test == "ovo"):
+            raise ValueError(f"{test} dispatcher called with encoded_ref_group={grpc.encoded_ref_group}")
+        return _dispatch(fmt, X, chunk_lb, chunk_ub, grpc, is_log1p, use_continuity, tie_correct, alternative, debug)
+
+    dispatcher.__name__ = f"{fmt}_{test}_mwu_kernel_over_contiguous_col_chunk"
+    dispatcher.__qualname__ = dispatcher.__name__
+    dispatcher.__doc__ = f"B200 {test.upper()} rank-sum test over a contiguous gene chunk of a {fmt} matrix."
+    return dispatcher
+
+
+dense_ovr_mwu_kernel_over_contiguous_col_chunk = _make(DENSE, "ovr")
+dense_ovo_mwu_kernel_over_contiguous_col_chunk = _make(DENSE, "ovo")
+csc_ovr_mwu_kernel_over_contiguous_col_chunk = _make(CSC, "ovr")
+csc_ovo_mwu_kernel_over_contiguous_col_chunk = _make(CSC, "ovo")
+csr_ovr_mwu_kernel_over_contiguous_col_chunk = _make(CSR, "ovr")
+csr_ovo_mwu_kernel_over_contiguous_col_chunk = _make(CSR, "ovo")
+
+
+def _register() -> None:
+    from .registry import KernelDataFormat, Test, dispatcher_registry
+
+    for fmt, kf in ((DENSE, KernelDataFormat.DENSE), (CSC, KernelDataFormat.CSC), (CSR, KernelDataFormat.CSR)):
+        for test, tt in (("ovr", Test.OVR), ("ovo", Test.OVO)):
+            dispatcher_registry.register(tt, kf)(globals()[f"{fmt}_{test}_mwu_kernel_over_contiguous_col_chunk"])
+
+
+_register()

@@ -1,0 +1,199 @@
+"""Plug-in registries, mirroring the reference's L2 seam (``illico/utils/registry.py:15-188``).
+
+Same names and meaning: ``Test``, ``KernelDataFormat``, ``dispatcher_registry[(Test, KernelDataFormat)]``,
+``data_handler_registry[type(X)]`` with ``DataHandler.fetch(lb, ub) -> (data, (lb', ub'))``.  The numba
+specific ``to_nb`` / ``input_signature`` become ``to_device`` (host arrays -> HBM); unsupported input
+types raise the reference's ``KeyError("Support for data type ... is not implemented.")``.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from enum import Enum
+
+import numpy as np
+from scipy import sparse as py_sparse
+
+from .engine import CSC, CSR, DENSE, DeviceMatrix, Engine
+
+
+class Test(Enum):
+    OVO = "ovo"
+    OVR = "ovr"
+
+
+class KernelDataFormat(Enum):
+    DENSE = "dense"
+    CSC = "csc"
+    CSR = "csr"
+
+
+class DispatcherRegistry(dict):
+    def register(self, test: Test, data_format: KernelDataFormat):
+        test, data_format = Test(test), KernelDataFormat(data_format)
+
+        def decorator(obj):
+            self[(test, data_format)] = obj
+            return obj
+
+        return decorator
+
+    def get(self, test: Test, data_format: KernelDataFormat):
+        key = (Test(test), KernelDataFormat(data_format))
+        try:
+            return self[key]
+        except KeyError as e:
+            raise KeyError(f"No dispatcher registered for test {test} and data format {data_format}.") from e
+
+
+class DataHandlerRegistry(dict):
+    def register(self, data_format):
+        def decorator(obj):
+            self[data_format] = obj
+            return obj
+
+        return decorator
+
+    def get(self, key):
+        for klass in type(key).__mro__:
+            if klass in self:
+                return self[klass](key)
+        raise KeyError(f"Support for data type {type(key)} is not implemented.")
+
+
+data_handler_registry = DataHandlerRegistry()
+dispatcher_registry = DispatcherRegistry()
+
+
+class DataHandler(ABC):
+    """Knows how to slice gene batches out of one kind of container and put them in HBM."""
+
+    def __init__(self, data):
+        self.data = data
+
+    @abstractmethod
+    def fetch(self, lb: int, ub: int) -> tuple:
+        """Returns ``(data, (lb', ub'))``: what to hand to ``to_device`` and the bounds inside it."""
+
+    @abstractmethod
+    def to_device(self, fetched, engine: Engine) -> DeviceMatrix:
+        """Host container -> device-resident matrix (the reference's ``to_nb``)."""
+
+    @abstractmethod
+    def kernel_data_format(self) -> KernelDataFormat:
+        pass
+
+    @abstractmethod
+    def footprint(self) -> int:
+        pass
+
+    in_ram = True
+
+
+class InRAMDataHandler(DataHandler):
+    """Whole matrix is uploaded once; batches are column ranges of the resident copy
+    (reference ``InRAMDataHandler.fetch``, ``registry.py:97-100``)."""
+
+    _resident: DeviceMatrix | None = None
+
+    def fetch(self, lb: int, ub: int) -> tuple:
+        return self.data, (lb, ub)
+
+    def to_device(self, fetched, engine: Engine) -> DeviceMatrix:
+        if self._resident is None:
+            self._resident = self._upload(fetched, engine)
+        return self._resident
+
+
+@data_handler_registry.register(np.ndarray)
+class DenseDataHandler(InRAMDataHandler):
+    def _upload(self, X, engine):
+        return engine.upload_dense(X)
+
+    def kernel_data_format(self):
+        return KernelDataFormat.DENSE
+
+    def footprint(self):
+        return self.data.nbytes
+
+
+@data_handler_registry.register(py_sparse.csr_matrix)
+class CSRDataHandler(InRAMDataHandler):
+    def _upload(self, X, engine):
+        return engine.upload_sparse(X, CSR)
+
+    def kernel_data_format(self):
+        return KernelDataFormat.CSR
+
+    def footprint(self):
+        return self.data.data.nbytes + self.data.indptr.nbytes + self.data.indices.nbytes
+
+
+@data_handler_registry.register(py_sparse.csc_matrix)
+class CSCDataHandler(InRAMDataHandler):
+    def _upload(self, X, engine):
+        return engine.upload_sparse(X, CSC)
+
+    def kernel_data_format(self):
+        return KernelDataFormat.CSC
+
+    def footprint(self):
+        return self.data.data.nbytes + self.data.indptr.nbytes + self.data.indices.nbytes
+
+
+class BackedDenseDataHandler(DataHandler):
+    """Out-of-core dense container: anything supporting ``obj[:, lb:ub] -> ndarray`` (``h5py.Dataset``;
+    reference ``H5pyDatasetDataHandler``, ``registry.py:162-168``).  Bounds are rebased to the batch."""
+
+    in_ram = False
+
+    def fetch(self, lb, ub):
+        return np.asarray(self.data[:, lb:ub]), (0, ub - lb)
+
+    def to_device(self, fetched, engine):
+        return engine.upload_dense(fetched)
+
+    def kernel_data_format(self):
+        return KernelDataFormat.DENSE
+
+    def footprint(self):
+        return int(np.prod(self.data.shape)) * np.dtype(self.data.dtype).itemsize
+
+
+class BackedCSCDataHandler(DataHandler):
+    """Out-of-core CSC container: ``obj[:, lb:ub] -> scipy CSC`` (anndata ``_CSCDataset``;
+    reference ``H5pyBackedCSCDataHandler``, ``registry.py:171-188``)."""
+
+    in_ram = False
+
+    def fetch(self, lb, ub):
+        return py_sparse.csc_matrix(self.data[:, lb:ub]), (0, ub - lb)
+
+    def to_device(self, fetched, engine):
+        return engine.upload_sparse(fetched, CSC)
+
+    def kernel_data_format(self):
+        return KernelDataFormat.CSC
+
+    def footprint(self):
+        return 0
+
+
+def _register_optional_backends() -> None:
+    """h5py / anndata are optional: register their backed containers when importable."""
+    try:
+        import h5py
+
+        data_handler_registry.register(h5py.Dataset)(BackedDenseDataHandler)
+    except Exception:
+        pass
+    try:
+        from anndata._core.sparse_dataset import _CSCDataset
+
+        data_handler_registry.register(_CSCDataset)(BackedCSCDataHandler)
+    except Exception:
+        pass
+
+
+_register_optional_backends()
+
+from . import dispatch  # noqa: E402,F401  (registers the six GPU dispatchers)

@@ -1,0 +1,178 @@
+/*
+ * illico_b200.h -- C ABI of the B200-native asymptotic Wilcoxon rank-sum (Mann-Whitney U) hot path.
+ *
+ * This is the drop-in boundary for the ONE path this repository accelerates: the six batch
+ * "dispatcher" kernels of remydubois/illico and the primitives under them.
+ * Plain `extern "C"`, plain pointers and sizes, no torch / Python types.  Every buffer is owned by
+ * the caller (device pointers unless stated otherwise); the library allocates nothing persistent.
+ * All functions return 0 on success, non-zero on failure; `illico_last_error()` gives the message
+ * (thread-local).  All work is enqueued on the caller's `stream` (a `cudaStream_t` passed as void*).
+ * Re-entrant per (device, stream).
+ *
+ * Reference interface each entry point replaces (paths relative to the reference repo):
+ *
+ *   illico_stage_dense_f32   chunk_and_fortranize            illico/utils/math.py:247-278
+ *                            (+ the per-group row gathers of  illico/ovo/dense_ovo.py:111-123)
+ *   illico_stage_csr_f32     csr_get_contig_cols_into_csc     illico/utils/sparse/csr.py:199-257
+ *                            csr_get_contig_cols_into_csr     illico/utils/sparse/csr.py:144-196
+ *                            csr_get_rows_into_csc            illico/utils/sparse/csr.py:103-141
+ *   illico_stage_csc_f32     csc_get_cols                     illico/utils/sparse/csc.py:99-136
+ *                            csc_get_contig_cols_into_csr     illico/utils/sparse/csc.py:139-183
+ *   illico_rank_ovr          dense_ovr_mwu_kernel_over_contiguous_col_chunk  illico/ovr/dense_ovr.py:15-80
+ *                            sparse_ovr_mwu_kernel            illico/ovr/sparse_ovr.py:23-97
+ *                            _accumulate_group_ranksums_from_argsort         illico/utils/ranking.py:7-49
+ *   illico_rank_ovo          dense_ovo_mwu_kernel(+wrapper)   illico/ovo/dense_ovo.py:15-137
+ *                            single_/multi_group_sparse_ovo_mwu_kernel       illico/ovo/sparse_ovo.py:22-158
+ *                            rank_sum_and_ties_from_sorted    illico/utils/ranking.py:52-158
+ *   (both rank kernels)      compute_pval                     illico/utils/math.py:64-118
+ *                            dense_/csc_/csr_fold_change, fold_change_from_summed_expr
+ *                                                             illico/utils/math.py:168-221,
+ *                                                             illico/utils/sparse/csc.py:186-211, csr.py:261-286
+ *   illico_check_csr_sorted  check_indices_sorted_per_parcel  illico/utils/ranking.py:245-273
+ *   illico_{ovr,ovo}_{dense,csc,csr}_f32   the six dispatchers registered in
+ *                            illico/utils/registry.py:193-202 (call site illico/asymptotic_wilcoxon.py:59-67)
+ *
+ * Data model.  A gene batch is first STAGED into a group-segmented, gene-major list of its
+ * non-zero values (zeros are one analytic tie block, for dense input too), then RANKED:
+ *
+ *   plan      : cells permuted to group-contiguous order; each group is cut into segments of at most
+ *               `seg_max` cells; segment s owns slot [seg_base[s], seg_base[s+1]) of every gene's
+ *               slot space (capacity `slot_cap` floats per gene).
+ *   ir_vals   : float  [n_genes_batch, slot_cap]   non-zero values of (gene, segment), compacted at
+ *                                                  the start of the segment's slot
+ *   ir_cnt    : uint32 [n_genes_batch, n_segments] how many values each (gene, segment) slot holds
+ *   results   : double [n_groups, result_gene_stride/3 .., 3] = (p_value, statistic, fold_change),
+ *               the layout of the reference's `results[G, N, 3]` (asymptotic_wilcoxon.py:210, 241-244).
+ */
+#ifndef ILLICO_B200_H
+#define ILLICO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ILLICO_ABI_VERSION 1
+
+enum illico_alternative { ILLICO_TWO_SIDED = 0, ILLICO_LESS = 1, ILLICO_GREATER = 2 };
+
+/* tie-sum accumulation order of the reference kernels */
+enum illico_tie_order {
+    ILLICO_TIES_DENSE = 0, /* zero block at its sorted position (dense kernels, utils/ranking.py:31-47) */
+    ILLICO_TIES_SPARSE = 1 /* non-zero runs first, zero block last (ovr/sparse_ovr.py:83, ovo/sparse_ovo.py:85) */
+};
+
+/* Group plan: the device-side form of the reference's GroupContainer (illico/utils/groups.py:6-15). */
+typedef struct illico_plan {
+    int32_t n_cells;
+    int32_t n_groups;
+    int32_t n_segments;
+    int32_t ref_group;          /* -1 = one-versus-rest (groups.py:55-57) */
+    int32_t max_group_size;
+    int32_t ref_group_size;     /* cells of the reference group (0 for one-versus-rest) */
+    int32_t slot_cap;           /* floats per gene in ir_vals (= seg_base[n_segments]) */
+    const int32_t* perm;        /* [n_cells]     perm[pos] = cell (row) index, groups contiguous, stable */
+    const int32_t* cell_seg;    /* [n_cells]     segment of each cell (row -> segment) */
+    const int32_t* seg_pos;     /* [n_segments+1] positions (into perm) covered by each segment */
+    const int32_t* seg_base;    /* [n_segments+1] slot offset of each segment inside a gene's slot space */
+    const int32_t* seg_group;   /* [n_segments]  owning group */
+    const int32_t* group_seg;   /* [n_groups+1]  segments of each group */
+    const int32_t* group_size;  /* [n_groups]    cells per group (GroupContainer.counts) */
+} illico_plan_t;
+
+typedef struct illico_flags {
+    int32_t is_log1p;       /* fold change on expm1(x) (utils/math.py:212) */
+    int32_t use_continuity; /* 0.5 continuity correction (utils/math.py:100-114) */
+    int32_t tie_correct;    /* 0 -> tie sum := 0 in the p-value (ovr/dense_ovr.py:70) */
+    int32_t alternative;    /* enum illico_alternative */
+    int32_t tie_order;      /* enum illico_tie_order */
+} illico_flags_t;
+
+/* Optional per-test debug outputs for bit-exact parity checks (any pointer may be NULL). */
+typedef struct illico_debug {
+    int64_t* u2;       /* [n_groups, n_genes_batch]  2*U as an exact integer */
+    double* tie_sum;   /* OVR: [n_genes_batch]; OVO: [n_groups, n_genes_batch]  f64 tie sum fed to the p-value */
+    int64_t* tie_exact;/* same shape as tie_sum: exact integer sum of t^3 - t */
+} illico_debug_t;
+
+int illico_abi_version(void);
+const char* illico_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t illico_launch_count(void);
+
+/* ---- staging: input formats -> group-segmented non-zero lists ------------------------------- */
+
+/* X: row-major [n_cells, ld] float32 on the device; genes [gene_lb, gene_lb + n_genes_batch). */
+int illico_stage_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t n_genes_batch,
+                           const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, void* stream);
+
+/* CSR (rows = cells): data/indices [nnz], indptr [n_cells+1] (int64).  Row indices must be sorted
+ * (illico/asymptotic_wilcoxon.py:185-193).  ir_cnt must be zeroed by the caller (illico_zero_counts). */
+int illico_stage_csr_f32(const float* data, const int32_t* indices, const int64_t* indptr,
+                         int32_t gene_lb, int32_t n_genes_batch, const illico_plan_t* plan,
+                         float* ir_vals, uint32_t* ir_cnt, void* stream);
+
+/* CSC (columns = genes): data/indices [nnz], indptr [n_genes+1] (int64); columns gene_lb.. */
+int illico_stage_csc_f32(const float* data, const int32_t* indices, const int64_t* indptr,
+                         int32_t gene_lb, int32_t n_genes_batch, const illico_plan_t* plan,
+                         float* ir_vals, uint32_t* ir_cnt, void* stream);
+
+int illico_zero_counts(uint32_t* ir_cnt, int32_t n_genes_batch, const illico_plan_t* plan, void* stream);
+
+/* returns 1 if every row's indices ascend, 0 if not, <0 on error; result read back synchronously */
+int illico_check_csr_sorted(const int32_t* indices, const int64_t* indptr, int64_t n_rows, int32_t* d_flag,
+                            void* stream);
+
+/* ---- ranking + fused epilogue ------------------------------------------------------------- */
+
+/* bytes of device scratch the rank kernels need for this plan (pass >= this many to illico_rank_*) */
+size_t illico_rank_workspace_bytes(const illico_plan_t* plan, int32_t n_genes_batch);
+
+/* results: pointer to element [group 0, first gene of the batch, 0]; result_group_stride in doubles
+ * between consecutive groups (= 3 * total genes of the final array). */
+int illico_rank_ovr(const float* ir_vals, const uint32_t* ir_cnt, int32_t n_genes_batch, const illico_plan_t* plan,
+                    const illico_flags_t* flags, double* results, int64_t result_group_stride,
+                    void* workspace, size_t workspace_bytes, const illico_debug_t* dbg, void* stream);
+
+int illico_rank_ovo(const float* ir_vals, const uint32_t* ir_cnt, int32_t n_genes_batch, const illico_plan_t* plan,
+                    const illico_flags_t* flags, double* results, int64_t result_group_stride,
+                    void* workspace, size_t workspace_bytes, const illico_debug_t* dbg, void* stream);
+
+/* ---- the six dispatchers (stage + rank in one call), reference registry.py:193-202 ---------- */
+
+typedef struct illico_batch_buffers {
+    float* ir_vals;          /* [n_genes_batch * plan->slot_cap] */
+    uint32_t* ir_cnt;        /* [n_genes_batch * plan->n_segments] */
+    void* workspace;         /* illico_rank_workspace_bytes() */
+    size_t workspace_bytes;
+} illico_batch_buffers_t;
+
+int illico_ovr_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t n_genes_batch,
+                         const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf,
+                         double* results, int64_t result_group_stride, const illico_debug_t* dbg, void* stream);
+int illico_ovo_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t n_genes_batch,
+                         const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf,
+                         double* results, int64_t result_group_stride, const illico_debug_t* dbg, void* stream);
+int illico_ovr_csr_f32(const float* data, const int32_t* indices, const int64_t* indptr, int32_t gene_lb,
+                       int32_t n_genes_batch, const illico_plan_t* plan, const illico_flags_t* flags,
+                       const illico_batch_buffers_t* buf, double* results, int64_t result_group_stride,
+                       const illico_debug_t* dbg, void* stream);
+int illico_ovo_csr_f32(const float* data, const int32_t* indices, const int64_t* indptr, int32_t gene_lb,
+                       int32_t n_genes_batch, const illico_plan_t* plan, const illico_flags_t* flags,
+                       const illico_batch_buffers_t* buf, double* results, int64_t result_group_stride,
+                       const illico_debug_t* dbg, void* stream);
+int illico_ovr_csc_f32(const float* data, const int32_t* indices, const int64_t* indptr, int32_t gene_lb,
+                       int32_t n_genes_batch, const illico_plan_t* plan, const illico_flags_t* flags,
+                       const illico_batch_buffers_t* buf, double* results, int64_t result_group_stride,
+                       const illico_debug_t* dbg, void* stream);
+int illico_ovo_csc_f32(const float* data, const int32_t* indices, const int64_t* indptr, int32_t gene_lb,
+                       int32_t n_genes_batch, const illico_plan_t* plan, const illico_flags_t* flags,
+                       const illico_batch_buffers_t* buf, double* results, int64_t result_group_stride,
+                       const illico_debug_t* dbg, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ILLICO_B200_H */
