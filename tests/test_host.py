@@ -1,0 +1,181 @@
+"""CPU tests of the host logic, the oracle wiring and the C-ABI surface (no compute calls without a GPU)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_build_and_exported_symbols():
+    """The CUDA library builds for sm_100a here (no GPU needed) and exports every symbol the header declares."""
+    from illico_b200 import _lib, build
+
+    path = build.build()
+    assert os.path.exists(path)
+    header = open(os.path.join(ROOT, "include", "illico_b200.h")).read()
+    declared = set(re.findall(r"\b(illico_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    out = subprocess.check_output(["nm", "-D", "--defined-only", path], text=True)
+    exported = set(re.findall(r" T (illico_[a-z0-9_]+)", out))
+    assert declared <= exported, declared - exported
+    lib = _lib.load()
+    assert lib.illico_abi_version() == _lib.ABI_VERSION
+    assert lib.illico_launch_count() == 0
+    sass = subprocess.run(["cuobjdump", "-lelf", path], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "illico_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), f
+                assert "liboracle" not in src, f
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from illico_b200 import _lib, asymptotic_wilcoxon
+    from tests.util import FakeAnnData
+
+    X = np.ones((8, 3), dtype=np.float32)
+    with pytest.raises(_lib.IllicoCudaError):
+        asymptotic_wilcoxon(FakeAnnData(X, list("aabbccdd")), is_log1p=False, group_keys="pert")
+
+
+def test_encode_and_count_groups_matches_reference_semantics():
+    import oracle
+    from illico_b200.groups import encode_and_count_groups
+
+    rng = np.random.RandomState(0)
+    labels = [f"pert_{v}" for v in rng.randint(0, 12, size=500)] + ["non-targeting"] * 7
+    uniq, g = encode_and_count_groups(labels, "non-targeting")
+    o_uniq, o_enc, o_counts, o_idx, o_ptr, o_ref = oracle.encode_groups(labels, "non-targeting")
+    assert list(uniq) == list(o_uniq) == sorted(set(labels))
+    np.testing.assert_array_equal(g.encoded_groups, o_enc)
+    np.testing.assert_array_equal(g.counts, o_counts)
+    np.testing.assert_array_equal(g.indptr, o_ptr)
+    assert g.encoded_ref_group == o_ref == list(uniq).index("non-targeting")
+    # indices: cells sorted by group (reference utils/groups.py:47)
+    assert sorted(g.indices.tolist()) == list(range(len(labels)))
+    assert all(g.encoded_groups[g.indices[g.indptr[k]:g.indptr[k + 1]]].tolist() == [k] * g.counts[k] for k in range(len(uniq)))
+    _, g2 = encode_and_count_groups(labels, None)
+    assert g2.encoded_ref_group == -1
+    with pytest.raises(ValueError, match="is not present in the group labels"):
+        encode_and_count_groups(labels, "missing")
+    # numeric labels sort numerically like np.unique
+    uniq, g3 = encode_and_count_groups([10, 2, 2, 33, 10], 2)
+    assert list(uniq) == [2, 10, 33] and g3.encoded_ref_group == 0
+
+
+@pytest.mark.parametrize("seg_max", [1, 7, 512])
+def test_plan_invariants(seg_max):
+    from illico_b200.groups import build_plan, encode_and_count_groups
+
+    rng = np.random.RandomState(1)
+    labels = rng.randint(0, 9, size=1000).tolist() + [99]
+    _, g = encode_and_count_groups(labels, 3)
+    p = build_plan(g, seg_max)
+    n = len(labels)
+    assert sorted(p.perm.tolist()) == list(range(n))
+    assert np.all(np.diff(g.encoded_groups[p.perm]) >= 0)  # groups contiguous
+    for k in range(p.n_groups):  # stable inside a group
+        rows = p.perm[g.indptr[k]:g.indptr[k + 1]]
+        assert np.all(np.diff(rows) > 0)
+    assert p.seg_pos[0] == 0 and p.seg_pos[-1] == n and np.all(np.diff(p.seg_pos) >= 1)
+    assert np.all(np.diff(p.seg_pos) <= seg_max)
+    assert np.all(p.seg_base % 4 == 0) and p.slot_cap == p.seg_base[-1]
+    assert np.all(np.diff(p.seg_base) >= np.diff(p.seg_pos))
+    assert p.group_seg[0] == 0 and p.group_seg[-1] == p.n_segments
+    for s in range(p.n_segments):
+        cells = p.perm[p.seg_pos[s]:p.seg_pos[s + 1]]
+        assert np.all(p.cell_seg[cells] == s)
+        assert np.all(g.encoded_groups[cells] == p.seg_group[s])
+        assert p.group_seg[p.seg_group[s]] <= s < p.group_seg[p.seg_group[s] + 1]
+    assert p.max_group_size == g.counts.max() and p.ref_group_size == g.counts[g.encoded_ref_group]
+
+
+def test_registries_mirror_the_reference():
+    from scipy import sparse
+
+    from illico_b200.registry import (KernelDataFormat, Test, data_handler_registry, dispatcher_registry)
+
+    assert {k for k in dispatcher_registry} == {(t, f) for t in Test for f in KernelDataFormat}
+    X = np.zeros((4, 3), dtype=np.float32)
+    assert data_handler_registry.get(X).kernel_data_format() is KernelDataFormat.DENSE
+    assert data_handler_registry.get(sparse.csr_matrix(X)).kernel_data_format() is KernelDataFormat.CSR
+    assert data_handler_registry.get(sparse.csc_matrix(X)).kernel_data_format() is KernelDataFormat.CSC
+    h = data_handler_registry.get(X)
+    assert h.fetch(1, 2) == (X, (1, 2)) or h.fetch(1, 2)[1] == (1, 2)
+
+    class Backed:  # e.g. an anndata _CSRDataset: not supported, same KeyError text as the reference
+        shape = (4, 3)
+
+    with pytest.raises(KeyError, match="Support for data type .* is not implemented."):
+        data_handler_registry.get(Backed())
+    with pytest.raises(KeyError, match="No dispatcher registered"):
+        dispatcher_registry.get("ovo", "dense") if False else dispatcher_registry.__class__().get("ovo", "dense")
+
+
+def test_gene_shards_cover_all_genes():
+    from illico_b200.parallel import gene_shard
+
+    for n, w in ((8000, 8), (15, 4), (3, 8), (20000, 3)):
+        shards = [gene_shard(n, r, w) for r in range(w)]
+        assert shards[0][0] == 0 and shards[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(shards, shards[1:]))
+        assert max(u - l for l, u in shards) - min(u - l for l, u in shards) <= 1
+    wts = np.r_[np.full(100, 10.0), np.full(900, 1.0)]
+    shards = [gene_shard(1000, r, 2, wts) for r in range(2)]
+    assert shards[0][0] == 0 and shards[1][1] == 1000 and shards[0][1] == shards[1][0]
+    assert abs(wts[: shards[0][1]].sum() - wts[shards[0][1]:].sum()) <= 20.0
+
+
+def _gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from illico_b200.parallel import gather_results, gene_shard
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    G, N = 5, 11
+    full = torch.arange(G * N * 3, dtype=torch.float64).reshape(G, N, 3)
+    lb, ub = gene_shard(N, rank, world)
+    out = gather_results(full[:, lb:ub].contiguous(), N)
+    q.put((rank, bool(torch.equal(out, full))))
+    dist.destroy_process_group()
+
+
+def test_gather_results_world_size_2_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert got == [(0, True), (1, True)]
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` times the oracle port on the host cores and prints one JSON line."""
+    import json
+
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cells", "3000",
+                                   "--genes", "32", "--perts", "10", "--steps", "1", "--warmup", "0"], text=True, cwd=ROOT)
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
