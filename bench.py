@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--sorted-cells", action="store_true", help="experiment: cells already in group order")
     return ap.parse_args()
 
 
@@ -175,6 +176,8 @@ def main():
 
     # ---- synthetic K562-shape shard of this rank (weak scaling: every rank owns a full-size gene shard)
     labels, reference = make_labels(a.seed, a.cells, a.perts, test)
+    if a.sorted_cells:
+        labels = sorted(labels)
     Xdev = synth.k562_like_torch(a.seed + 1000 * rank, a.cells, a.genes, device=dev)
     uniq, grpc = encode_and_count_groups(labels, reference)
     G = grpc.counts.size

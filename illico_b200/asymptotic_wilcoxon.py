@@ -90,8 +90,8 @@ def asymptotic_wilcoxon(
         X = sparse.csr_matrix(X) if isinstance(X, sparse.csr_array) else sparse.csc_matrix(X)
     data_handler = data_handler_registry.get(X)  # KeyError for unsupported containers, like the reference
 
-    raw_groups = adata.obs[group_keys].tolist()
-    unique_raw_groups, grpc = encode_and_count_groups(groups=raw_groups, ref_group=reference)
+    # the reference goes through `.tolist()` + a dict loop (utils/groups.py:42-45); same encoding, vectorised
+    unique_raw_groups, grpc = encode_and_count_groups(groups=adata.obs[group_keys], ref_group=reference)
     n_cells, n_genes = X.shape
     if grpc.encoded_groups.size != n_cells:
         raise ValueError(f"{grpc.encoded_groups.size} group labels for {n_cells} cells")

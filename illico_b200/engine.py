@@ -82,7 +82,8 @@ class Engine:
         budget = min(_env_int("ILLICO_B200_IR_BYTES", 16 << 30), int(free * 0.35))
         per_gene = self.host_plan.slot_cap * 4 + self.host_plan.n_segments * 4
         b = max(1, budget // max(per_gene, 1))
-        return int(min(n_genes, b, _env_int("ILLICO_B200_BATCH_GENES", 1 << 30)))
+        b = int(min(n_genes, b, _env_int("ILLICO_B200_BATCH_GENES", 1 << 30)))
+        return b if b < 8 or b == n_genes else (b // 4) * 4  # multiples of 4 keep the 128-bit staging path
 
     def _ensure_buffers(self, b: int) -> None:
         if b <= self._buf_genes:

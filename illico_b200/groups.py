@@ -25,19 +25,32 @@ GroupContainer = namedtuple(
 SEG_MAX_DEFAULT = 512
 
 
-def encode_and_count_groups(groups, ref_group: Any):
-    """Returns ``(unique_groups, GroupContainer)`` exactly like the reference."""
-    arr = np.asarray(groups)
+def _factorize_sorted(groups):
+    """``(unique_sorted, inverse)`` with ``np.unique``'s ordering.  Strings go through a hash-based
+    factorisation (12 ms instead of 170 ms at 300k labels); the sorted uniques are the same."""
+    import pandas as pd
+
+    if isinstance(groups, (pd.Series, pd.Index)):
+        arr = groups.to_numpy()
+    else:
+        arr = np.asarray(groups)
     if arr.ndim != 1:
         raise ValueError("group labels must be one-dimensional")
-    if arr.dtype == object:
-        # mixed / str objects: np.unique on an object array compares Python objects; convert the common
-        # all-str case to a unicode array first (what the reference gets from a list of str)
-        try:
-            arr = arr.astype(str) if all(isinstance(x, str) for x in arr[: min(arr.size, 1000)]) else arr
-        except Exception:  # pragma: no cover
-            pass
-    unique_groups, inverse, counts = np.unique(arr, return_inverse=True, return_counts=True)
+    if arr.dtype.kind in "OUS":
+        codes, uniq = pd.factorize(arr, sort=True)
+        if (codes < 0).any():
+            raise ValueError("group labels contain missing values")
+        uniq = np.asarray(uniq)
+        if uniq.dtype == object and all(isinstance(x, str) for x in uniq):
+            uniq = uniq.astype(str)  # what np.unique returns for a list of str
+        return uniq, codes
+    uniq, inverse = np.unique(arr, return_inverse=True)
+    return uniq, inverse.reshape(-1)
+
+
+def encode_and_count_groups(groups, ref_group: Any):
+    """Returns ``(unique_groups, GroupContainer)`` exactly like the reference."""
+    unique_groups, inverse = _factorize_sorted(groups)
     if ref_group is not None:
         hit = np.nonzero(unique_groups == ref_group)[0]
         if hit.size == 0:
@@ -45,11 +58,21 @@ def encode_and_count_groups(groups, ref_group: Any):
         encoded_ref = int(hit[0])
     else:
         encoded_ref = -1
-    encoded = np.ascontiguousarray(inverse.reshape(-1), dtype=np.int64)
-    counts = np.ascontiguousarray(counts, dtype=np.int64)
-    indices = np.argsort(encoded, kind="stable").astype(np.int64)
+    G = len(unique_groups)
+    encoded = np.ascontiguousarray(inverse, dtype=np.int64)
+    counts = np.bincount(encoded, minlength=G).astype(np.int64)
+    small = encoded.astype(np.int16) if G < 2**15 else encoded  # 16-bit keys take numpy's radix sort
+    indices = np.argsort(small, kind="stable").astype(np.int64)
     indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     return unique_groups, GroupContainer(encoded, counts, indices, indptr, encoded_ref)
+
+
+def _is_stable_group_order(enc, perm) -> bool:
+    e = enc[perm]
+    if np.any(np.diff(e) < 0):
+        return False
+    same = np.diff(e) == 0
+    return bool(np.all(np.diff(perm)[same] > 0))
 
 
 class HostPlan:
@@ -68,7 +91,10 @@ class HostPlan:
         self.n_cells, self.n_groups = int(n), int(G)
         self.ref_group = int(grpc.encoded_ref_group)
         self.seg_max = int(seg_max)
-        perm = np.argsort(enc, kind="stable")  # stable: ascending cell index inside a group
+        perm = np.asarray(grpc.indices)  # stable argsort of the codes: ascending cell index inside a group
+        if perm.size != n or not _is_stable_group_order(enc, perm):
+            small = enc.astype(np.int16) if G < 2**15 else enc
+            perm = np.argsort(small, kind="stable")
         group_off = np.concatenate([[0], np.cumsum(counts)])
         nseg = np.maximum(1, -(-counts // seg_max))
         group_seg = np.concatenate([[0], np.cumsum(nseg)])
