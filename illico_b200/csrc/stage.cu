@@ -15,122 +15,98 @@
 namespace illico {
 
 constexpr int STAGE_WARPS = 8;
+constexpr int STAGE_GENES = STAGE_WARPS * 32;
+constexpr int STAGE_MAX_SEGS = 16;
 
-// One warp = 32 adjacent genes (one coalesced 128-byte row segment per cell); the CTA's 8 warps cover 256
-// adjacent genes, i.e. 1 KB of every row they touch.  Each lane owns one (gene, segment) slot at a time and
-// appends the non-zeros of the segment's cells in order (deterministic layout, no atomics).
+// Appends v to the lane's slot when it is non-zero: one predicate, one predicated store, one predicated
+// pointer bump (no divergent branch).
+// Appends v to the lane's slot when it is non-zero.  Non-zeros are collected eight at a time in a lane-private
+// shared-memory column and leave as ONE full, aligned 32-byte sector (slots are 32-byte aligned and padded), so
+// L2 never sees a partial-sector write that it would have to merge with a DRAM fill.
+__device__ __forceinline__ void flush8(float* out0, uint32_t first, const float (*wbuf)[STAGE_WARPS * 32], int t) {
+    float4 a = make_float4(wbuf[0][t], wbuf[1][t], wbuf[2][t], wbuf[3][t]);
+    float4 b = make_float4(wbuf[4][t], wbuf[5][t], wbuf[6][t], wbuf[7][t]);
+    float4* dst = reinterpret_cast<float4*>(out0 + first);
+    __stcs(dst, a);
+    __stcs(dst + 1, b);
+}
+__device__ __forceinline__ void append_nonzero(float* out0, uint32_t& cnt, float v, float (*wbuf)[STAGE_WARPS * 32],
+                                               uint32_t wbuf_t_addr, int t) {
+    uint32_t nz;
+    const uint32_t addr = wbuf_t_addr + ((cnt & 7u) << 10);  // &wbuf[cnt & 7][t]  (row pitch 256 floats = 1 KB)
+    asm volatile("{ .reg .pred p; setp.neu.f32 p, %3, 0f00000000; @p st.shared.f32 [%2], %3; @p add.u32 %0, %0, 1; "
+                 "selp.u32 %1, 1, 0, p; }" : "+r"(cnt), "=r"(nz) : "r"(addr), "f"(v) : "memory");
+    if (nz && (cnt & 7u) == 0u) flush8(out0, cnt - 8u, wbuf, t);
+}
+// row * ld in one wide multiply-add (row < 2^31, ld * 4 < 2^32: checked by the host)
+__device__ __forceinline__ const float* row_ptr(const float* col, int row, uint32_t ld_bytes) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(col) +
+                                          (unsigned long long)(uint32_t)row * (unsigned long long)ld_bytes);
+}
+
+// One warp = 32 adjacent genes: lane = gene, so every cell row is one coalesced 128-byte request per warp and
+// the CTA's 8 warps cover 1 KB of the row.  Each lane owns one (gene, segment) slot at a time and appends the
+// non-zeros of the segment's cells in plan order: deterministic layout, no atomics, no shared-memory
+// transposition, 32 registers (full occupancy keeps ~64 KB of loads in flight per SM).  The per-(gene, segment)
+// counts go through a shared tile so that each gene's counts leave as one contiguous run.
+template <bool TILE_COUNTS>
 __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const float* __restrict__ X, long long ld,
                                                                        int gene_lb, int b, const illico_plan_t pl,
                                                                        float* __restrict__ ir_vals,
                                                                        uint32_t* __restrict__ ir_cnt,
                                                                        int segs_per_cta) {
+    __shared__ uint32_t cnt_tile[TILE_COUNTS ? STAGE_MAX_SEGS : 1][TILE_COUNTS ? STAGE_GENES : 1];
+    __shared__ float wbuf[8][STAGE_WARPS * 32];
+    static_assert(STAGE_WARPS * 32 * 4 == 1024, "append_nonzero assumes a 1 KB row pitch");
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int jb = (blockIdx.x * STAGE_WARPS + w) * 32 + lane;
+    const int jt = w * 32 + lane;
+    const uint32_t wbuf_t = (uint32_t)__cvta_generic_to_shared(&wbuf[0][threadIdx.x]);
+    const int jb = blockIdx.x * STAGE_GENES + jt;
     const bool active = jb < b;
-    const float* col = X + gene_lb + (active ? jb : 0);
+    const int jj = active ? jb : b - 1;                  // inactive lanes shadow the last gene and never store
+    const float* col = X + gene_lb + jj;
+    const uint32_t ldb = (uint32_t)(ld * 4);
     const int S = pl.n_segments;
     const int s_begin = blockIdx.y * segs_per_cta, s_end = min(S, s_begin + segs_per_cta);
     for (int s = s_begin; s < s_end; ++s) {
         const int p0 = pl.seg_pos[s], p1 = pl.seg_pos[s + 1];
-        float* out = ir_vals + (long long)(active ? jb : 0) * pl.slot_cap + pl.seg_base[s];
+        float* const out0 = ir_vals + (long long)jj * pl.slot_cap + pl.seg_base[s];
         uint32_t cnt = 0;
         for (int p = p0; p < p1; p += 32) {
-            const int myrow = (p + lane < p1) ? pl.perm[p + lane] : 0;
             const int nrows = min(32, p1 - p);
-            for (int k0 = 0; k0 < nrows; k0 += 8) {
-                float v[8];
+            const int myrow = pl.perm[p + min(lane, nrows - 1)];   // tail lanes repeat the last cell (never stored)
+            if (nrows == 32 && active) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int k = k0 + u;
-                    const int row = __shfl_sync(FULL, myrow, k & 31);
-                    v[u] = (active && k < nrows) ? __ldcs(col + (long long)row * ld) : 0.0f;
+                for (int k0 = 0; k0 < 32; k0 += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = __ldcs(row_ptr(col, __shfl_sync(FULL, myrow, k0 + u), ldb));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) append_nonzero(out0, cnt, v[u], wbuf, wbuf_t, jt);
                 }
+            } else {
+                for (int k0 = 0; k0 < nrows; k0 += 8) {
+                    float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (v[u] != 0.0f) out[cnt++] = v[u];
-            }
-        }
-        if (active) ir_cnt[(long long)jb * S + s] = cnt;
-    }
-}
-
-// Vectorised variant: one lane = 4 adjacent genes (one 128-bit load per cell), one warp = 128 genes (512 B of
-// the row), one CTA = 4 warps = 512 genes (2 KB of every row it touches).  Non-zeros are buffered four at a
-// time per gene stream and written with 128-bit stores into the 16-byte aligned slots; the per-(gene, segment)
-// counts go through a shared-memory tile so that each gene's counts leave as one contiguous run.
-constexpr int SD_WARPS = 4;
-constexpr int SD_GENES = SD_WARPS * 128;
-constexpr int SD_MAX_SEGS = 16;
-
-#define ILLICO_APPEND(K, XV)                                                              \
-    if ((XV) != 0.0f) {                                                                   \
-        const uint32_t m_ = c[K] & 3u;                                                    \
-        if (m_ == 0) pend[K].x = (XV);                                                    \
-        else if (m_ == 1) pend[K].y = (XV);                                               \
-        else if (m_ == 2) pend[K].z = (XV);                                               \
-        else { pend[K].w = (XV); *reinterpret_cast<float4*>(out[K] + (c[K] & ~3u)) = pend[K]; } \
-        ++c[K];                                                                           \
-    }
-
-__global__ void __launch_bounds__(SD_WARPS * 32) stage_dense_v4_kernel(const float* __restrict__ X, long long ld,
-                                                                        int gene_lb, int b, const illico_plan_t pl,
-                                                                        float* __restrict__ ir_vals,
-                                                                        uint32_t* __restrict__ ir_cnt,
-                                                                        int segs_per_cta) {
-    __shared__ uint32_t cnt_tile[SD_MAX_SEGS][SD_GENES];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int jl = w * 128 + lane * 4;                 // first of this lane's 4 genes inside the CTA tile
-    const int jb = blockIdx.x * SD_GENES + jl;         // ... inside the batch (b is a multiple of 4)
-    const bool active = jb < b;
-    const float4* col = reinterpret_cast<const float4*>(X + gene_lb + (active ? jb : 0));
-    const long long ld4 = ld >> 2;
-    const int S = pl.n_segments;
-    const int s_begin = blockIdx.y * segs_per_cta, s_end = min(S, s_begin + segs_per_cta);
-    for (int s = s_begin; s < s_end; ++s) {
-        const int p0 = pl.seg_pos[s], p1 = pl.seg_pos[s + 1];
-        float* out[4];
-        float4 pend[4];
-        uint32_t c[4] = {0, 0, 0, 0};
+                    for (int u = 0; u < 8; ++u) v[u] = __ldcs(row_ptr(col, __shfl_sync(FULL, myrow, (k0 + u) & 31), ldb));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            out[k] = ir_vals + (long long)((active ? jb : 0) + k) * pl.slot_cap + pl.seg_base[s];
-            pend[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (int p = p0; p < p1; p += 32) {
-            const int myrow = (p + lane < p1) ? pl.perm[p + lane] : 0;
-            const int nrows = min(32, p1 - p);
-            for (int k0 = 0; k0 < nrows; k0 += 8) {
-                float4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int k = k0 + u;
-                    const int row = __shfl_sync(FULL, myrow, k & 31);
-                    v[u] = (active && k < nrows) ? __ldcs(col + (long long)row * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    ILLICO_APPEND(0, v[u].x)
-                    ILLICO_APPEND(1, v[u].y)
-                    ILLICO_APPEND(2, v[u].z)
-                    ILLICO_APPEND(3, v[u].w)
+                    for (int u = 0; u < 8; ++u)
+                        if (active && k0 + u < nrows) append_nonzero(out0, cnt, v[u], wbuf, wbuf_t, jt);
                 }
             }
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            // the slot is padded to a multiple of 4 floats: the tail leaves as one (partly unused) 128-bit store
-            if (c[k] & 3u) *reinterpret_cast<float4*>(out[k] + (c[k] & ~3u)) = pend[k];
-            cnt_tile[s - s_begin][jl + k] = c[k];
-        }
+        if (active && (cnt & 7u)) flush8(out0, cnt & ~7u, wbuf, jt);  // tail: one padded full sector
+        if (TILE_COUNTS) cnt_tile[s - s_begin][jt] = cnt;
+        else if (active) ir_cnt[(long long)jb * S + s] = cnt;
     }
-    __syncthreads();
-    // counts: thread t owns genes t, t+128, ... of the tile and writes their consecutive segments
-    const int nseg = s_end - s_begin;
-    for (int g = threadIdx.x; g < SD_GENES; g += SD_WARPS * 32) {
-        const int j = blockIdx.x * SD_GENES + g;
-        if (j >= b) break;
-        uint32_t* dst = ir_cnt + (long long)j * S + s_begin;
-        for (int ls = 0; ls < nseg; ++ls) dst[ls] = cnt_tile[ls][g];
+    if (TILE_COUNTS) {
+        __syncthreads();
+        // thread t owns gene t of the CTA's 256 and writes its consecutive segments
+        const int nseg = s_end - s_begin;
+        if (active) {
+            uint32_t* dst = ir_cnt + (long long)jb * S + s_begin;
+            for (int ls = 0; ls < nseg; ++ls) dst[ls] = cnt_tile[ls][jt];
+        }
     }
 }
 
@@ -211,25 +187,22 @@ __global__ void check_csr_sorted_kernel(const int32_t* __restrict__ indices, con
 int launch_stage_dense(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
                        uint32_t* ir_cnt, cudaStream_t stream) {
     if (b <= 0 || plan->n_segments <= 0) return 0;
+    if (ld <= 0 || ld >= (1ll << 30)) { set_error("leading dimension %lld out of range", ld); return 1; }
     const int S = plan->n_segments;
     long long avg = plan->n_cells / S;
     if (avg < 1) avg = 1;
-    const bool vec = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (ld % 4 == 0) && (gene_lb % 4 == 0) && (b % 4 == 0);
-    int segs_per_cta = (int)(1024 / avg);
+    int segs_per_cta = (int)(2048 / avg);
     if (segs_per_cta < 1) segs_per_cta = 1;
-    const int cap = vec ? SD_MAX_SEGS : 64;
-    if (segs_per_cta > cap) segs_per_cta = cap;
+    if (segs_per_cta > STAGE_MAX_SEGS) segs_per_cta = STAGE_MAX_SEGS;
     long long gy = (S + segs_per_cta - 1) / segs_per_cta;
-    if (gy > 65535) {
-        if (vec) { set_error("too many segments (%d) for one staging launch", S); return 1; }
+    const unsigned gx = (unsigned)((b + STAGE_GENES - 1) / STAGE_GENES);
+    if (gy <= 65535) {
+        stage_dense_kernel<true><<<dim3(gx, (unsigned)gy), STAGE_WARPS * 32, 0, stream>>>(X, ld, gene_lb, b, *plan, ir_vals,
+                                                                                        ir_cnt, segs_per_cta);
+    } else {  // more than a million segments: any number of segments per CTA, counts written directly
         while (gy > 65535) { segs_per_cta *= 2; gy = (S + segs_per_cta - 1) / segs_per_cta; }
-    }
-    if (vec) {
-        dim3 grid((b + SD_GENES - 1) / SD_GENES, (unsigned)gy);
-        stage_dense_v4_kernel<<<grid, SD_WARPS * 32, 0, stream>>>(X, ld, gene_lb, b, *plan, ir_vals, ir_cnt, segs_per_cta);
-    } else {
-        dim3 grid((b + STAGE_WARPS * 32 - 1) / (STAGE_WARPS * 32), (unsigned)gy);
-        stage_dense_kernel<<<grid, STAGE_WARPS * 32, 0, stream>>>(X, ld, gene_lb, b, *plan, ir_vals, ir_cnt, segs_per_cta);
+        stage_dense_kernel<false><<<dim3(gx, (unsigned)gy), STAGE_WARPS * 32, 0, stream>>>(X, ld, gene_lb, b, *plan, ir_vals,
+                                                                                         ir_cnt, segs_per_cta);
     }
     count_launch();
     ILLICO_CUDA_OK(cudaGetLastError());

@@ -104,7 +104,7 @@ class HostPlan:
         seg_start = group_off[seg_group] + k * seg_max
         seg_len = np.minimum(seg_max, counts[seg_group] - k * seg_max)
         seg_pos = np.concatenate([seg_start, [n]])
-        seg_base = np.concatenate([[0], np.cumsum((seg_len + 3) // 4 * 4)])
+        seg_base = np.concatenate([[0], np.cumsum((seg_len + 7) // 8 * 8)])  # slots: whole 32-byte sectors
         if seg_base[-1] >= 2**31 - 1:
             raise ValueError("slot space exceeds 2^31")
         pos_seg = np.repeat(np.arange(S), seg_len)  # segment of each position

@@ -93,7 +93,7 @@ def test_plan_invariants(seg_max):
         assert np.all(np.diff(rows) > 0)
     assert p.seg_pos[0] == 0 and p.seg_pos[-1] == n and np.all(np.diff(p.seg_pos) >= 1)
     assert np.all(np.diff(p.seg_pos) <= seg_max)
-    assert np.all(p.seg_base % 4 == 0) and p.slot_cap == p.seg_base[-1]
+    assert np.all(p.seg_base % 8 == 0) and p.slot_cap == p.seg_base[-1]
     assert np.all(np.diff(p.seg_base) >= np.diff(p.seg_pos))
     assert p.group_seg[0] == 0 and p.group_seg[-1] == p.n_segments
     for s in range(p.n_segments):
