@@ -26,6 +26,8 @@ constexpr int OVO_THREADS = 512;
 constexpr int OVO_NW = OVO_THREADS / 32;
 constexpr int WARP_CAP = 1024;   // keys per warp buffer in the warp tier
 constexpr int GROUP_CHUNK = 1024;  // groups handled per sweep (bounds the deferred lists)
+constexpr int DT_CAP = 22;         // distinct control values for the table fast path (<= small_cap)
+constexpr int FAST_MAX = 96;       // largest group (non-zeros) a single thread streams through the table path
 
 struct OvoParams {
     const float* ir_vals;
@@ -110,6 +112,9 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
     int* counters = blist + GROUP_CHUNK;                    // [4]
     double* redd = (double*)(counters + 4);                 // [32]
     unsigned long long* redu = (unsigned long long*)(redd + 32);  // [32]
+    double* dval = (double*)(redu + 32);                    // [DT_CAP]   f(x) of each distinct control value
+    uint32_t* dkey = (uint32_t*)(dval + DT_CAP);            // [DT_CAP]   distinct control keys, ascending
+    int* dlo = (int*)(dkey + DT_CAP);                       // [DT_CAP+1] first position of each in the sorted control
 
     uint32_t* slab = P.slab + (long long)blockIdx.x * P.slab_words;
     const int maxg = pl.max_group_size;
@@ -172,6 +177,32 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
             }
             R.tie = block_sum<unsigned long long>(t, redu);
         }
+        // ---- distinct-value table of the control (raw counts have a handful of distinct values): groups whose
+        // values all occur in it are ranked by a private histogram over the table, without sorting or searching
+        if (tid == 0) counters[2] = 0;
+        __syncthreads();
+        for (int i = tid; i < nref_nz; i += OVO_THREADS) {
+            const uint32_t k = rA[i];
+            if (i == 0 || rA[i - 1] != k) {
+                const int slot = atomicAdd(&counters[2], 1);
+                if (slot < DT_CAP) { dkey[slot] = k; dlo[slot] = i; }
+            }
+        }
+        __syncthreads();
+        const int D = counters[2];
+        const bool table = D <= DT_CAP;
+        if (table && tid == 0) {
+            for (int a = 1; a < D; ++a) {  // order the <= 22 entries by position (= by key)
+                const uint32_t k = dkey[a];
+                const int l = dlo[a];
+                int q = a - 1;
+                while (q >= 0 && dlo[q] > l) { dlo[q + 1] = dlo[q]; dkey[q + 1] = dkey[q]; --q; }
+                dlo[q + 1] = l; dkey[q + 1] = k;
+            }
+            dlo[D] = nref_nz;
+            for (int a = 0; a < D; ++a) dval[a] = fc_value(key2f(dkey[a]), P.flags.is_log1p);
+        }
+        __syncthreads();
 
         // ================= phase 2: perturbations, in chunks of GROUP_CHUNK groups =================
         for (int g0 = 0; g0 < G; g0 += GROUP_CHUNK) {
@@ -195,11 +226,54 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
                 const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
                 int m = 0;
                 for (int s = s0; s < s1; ++s) m += (int)cnt[s];
+                uint32_t* col = scratch + tid;  // private column: element k at col[k * OVO_THREADS]
+                if (table && m <= FAST_MAX) {
+                    // ---- table path: private histogram over the control's distinct values
+                    for (int t = 0; t < D; ++t) col[t * OVO_THREADS] = 0;
+                    bool ok = true;
+                    for (int s = s0; s < s1 && ok; ++s) {
+                        const int c = (int)cnt[s];
+                        const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);  // 32-byte aligned slot
+                        for (int i = 0; i < c; i += 4) {
+                            const float4 q4 = src4[i >> 2];
+                            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                if (i + e < c) {
+                                    const uint32_t key = f2key(q[e]);
+                                    int lo = 0, hi = D;
+                                    while (lo < hi) {
+                                        const int mid = (lo + hi) >> 1;
+                                        if (dkey[mid] < key) lo = mid + 1; else hi = mid;
+                                    }
+                                    if (lo < D && dkey[lo] == key) col[lo * OVO_THREADS] += 1;
+                                    else ok = false;
+                                }
+                            }
+                        }
+                    }
+                    if (ok) {
+                        unsigned long long u2 = 0, tie = 0;
+                        double sum = 0.0;
+                        for (int t = 0; t < D; ++t) {
+                            const long long bq = col[t * OVO_THREADS];
+                            if (bq) {
+                                const long long a = dlo[t + 1] - dlo[t];
+                                const long long gt = (long long)(nref_nz - dlo[t + 1]) + ((dkey[t] < KEY_ZERO) ? R.zeros : 0);
+                                u2 += (unsigned long long)(bq * (2 * gt + a));
+                                tie += (unsigned long long)(cube_minus(a + bq) - cube_minus(a));
+                                sum += (double)bq * dval[t];
+                            }
+                        }
+                        finalize_group(P, R, j, g, m, u2, tie, sum);
+                        continue;
+                    }
+                    // a value the control does not have: fall through to the general paths
+                }
                 if (m > P.small_cap) {
                     mlist[atomicAdd(&counters[0], 1)] = g;
                     continue;
                 }
-                uint32_t* col = scratch + tid;  // private column: element k at col[k * OVO_THREADS]
                 double sum = 0.0;
                 int k = 0;
                 for (int s = s0; s < s1; ++s) {
@@ -325,7 +399,8 @@ int launch_ovo(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const 
 
     // shared memory: fixed part + control buffer + scratch, sized so that two CTAs fit on one SM.
     // Genes whose control has more non-zeros than ref_cap keep the control in the CTA's global slab.
-    const size_t fixed = (size_t)(OVO_NW * 256 + RADIX_AUX_WORDS + 2 * GROUP_CHUNK + 4) * 4 + 32 * 8 * 2 + 64;
+    const size_t fixed = (size_t)(OVO_NW * 256 + RADIX_AUX_WORDS + 2 * GROUP_CHUNK + 4) * 4 + 32 * 8 * 2 +
+                         DT_CAP * 8 + (2 * DT_CAP + 1) * 4 + 64;
     const int small_cap = 22;
     const int scratch_words = small_cap * OVO_THREADS;  // 11264 words: 22 keys per thread / 11 warp buffers
     int ref_cap = (plan->ref_group_size + 3) & ~3;

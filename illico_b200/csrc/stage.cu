@@ -17,6 +17,7 @@ namespace illico {
 constexpr int STAGE_WARPS = 8;
 constexpr int STAGE_GENES = STAGE_WARPS * 32;
 constexpr int STAGE_MAX_SEGS = 16;
+constexpr int STAGE_INFLIGHT = 16;  // cell rows in flight per warp (16 x 128 B)
 
 // Appends v to the lane's slot when it is non-zero: one predicate, one predicated store, one predicated
 // pointer bump (no divergent branch).
@@ -77,12 +78,13 @@ __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const flo
             const int myrow = pl.perm[p + min(lane, nrows - 1)];   // tail lanes repeat the last cell (never stored)
             if (nrows == 32 && active) {
 #pragma unroll
-                for (int k0 = 0; k0 < 32; k0 += 8) {
-                    float v[8];
+                for (int k0 = 0; k0 < 32; k0 += STAGE_INFLIGHT) {
+                    float v[STAGE_INFLIGHT];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = __ldcs(row_ptr(col, __shfl_sync(FULL, myrow, k0 + u), ldb));
+                    for (int u = 0; u < STAGE_INFLIGHT; ++u)
+                        v[u] = __ldcs(row_ptr(col, __shfl_sync(FULL, myrow, k0 + u), ldb));
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) append_nonzero(out0, cnt, v[u], wbuf, wbuf_t, jt);
+                    for (int u = 0; u < STAGE_INFLIGHT; ++u) append_nonzero(out0, cnt, v[u], wbuf, wbuf_t, jt);
                 }
             } else {
                 for (int k0 = 0; k0 < nrows; k0 += 8) {
