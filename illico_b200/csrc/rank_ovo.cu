@@ -27,6 +27,7 @@ constexpr int OVO_NW = OVO_THREADS / 32;
 constexpr int WARP_CAP = 1024;   // keys per warp buffer in the warp tier
 constexpr int GROUP_CHUNK = 1024;  // groups handled per sweep (bounds the deferred lists)
 constexpr int DT_CAP = 22;         // distinct control values for the table fast path (<= small_cap)
+constexpr int DT_HASH = 64;        // slots of the key -> table-index hash (load factor <= 1/3)
 constexpr int FAST_MAX = 96;       // largest group (non-zeros) a single thread streams through the table path
 
 struct OvoParams {
@@ -115,6 +116,8 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
     double* dval = (double*)(redu + 32);                    // [DT_CAP]   f(x) of each distinct control value
     uint32_t* dkey = (uint32_t*)(dval + DT_CAP);            // [DT_CAP]   distinct control keys, ascending
     int* dlo = (int*)(dkey + DT_CAP);                       // [DT_CAP+1] first position of each in the sorted control
+    uint32_t* hkey = (uint32_t*)(dlo + DT_CAP + 1);         // [DT_HASH]  open-addressed key -> table index
+    int* hidx = (int*)(hkey + DT_HASH);                     // [DT_HASH]
 
     uint32_t* slab = P.slab + (long long)blockIdx.x * P.slab_words;
     const int maxg = pl.max_group_size;
@@ -200,7 +203,14 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
                 dlo[q + 1] = l; dkey[q + 1] = k;
             }
             dlo[D] = nref_nz;
-            for (int a = 0; a < D; ++a) dval[a] = fc_value(key2f(dkey[a]), P.flags.is_log1p);
+            for (int a = 0; a < DT_HASH; ++a) hkey[a] = 0u;  // 0 is never a key of a finite value
+            for (int a = 0; a < D; ++a) {
+                dval[a] = fc_value(key2f(dkey[a]), P.flags.is_log1p);
+                uint32_t h = (dkey[a] * 2654435761u) >> 26;
+                while (hkey[h] != 0u) h = (h + 1) & (DT_HASH - 1);
+                hkey[h] = dkey[a];
+                hidx[h] = a;
+            }
         }
         __syncthreads();
 
@@ -234,19 +244,19 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
                     for (int s = s0; s < s1 && ok; ++s) {
                         const int c = (int)cnt[s];
                         const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);  // 32-byte aligned slot
+                        float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
                         for (int i = 0; i < c; i += 4) {
-                            const float4 q4 = src4[i >> 2];
+                            const float4 q4 = nxt;
+                            if (i + 4 < c) nxt = src4[(i >> 2) + 1];  // next 16 bytes are in flight while these are ranked
                             const float q[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 if (i + e < c) {
                                     const uint32_t key = f2key(q[e]);
-                                    int lo = 0, hi = D;
-                                    while (lo < hi) {
-                                        const int mid = (lo + hi) >> 1;
-                                        if (dkey[mid] < key) lo = mid + 1; else hi = mid;
-                                    }
-                                    if (lo < D && dkey[lo] == key) col[lo * OVO_THREADS] += 1;
+                                    uint32_t h = (key * 2654435761u) >> 26;
+                                    uint32_t hk = hkey[h];
+                                    while (hk != key && hk != 0u) { h = (h + 1) & (DT_HASH - 1); hk = hkey[h]; }
+                                    if (hk == key) col[hidx[h] * OVO_THREADS] += 1;
                                     else ok = false;
                                 }
                             }
@@ -268,7 +278,9 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
                         finalize_group(P, R, j, g, m, u2, tie, sum);
                         continue;
                     }
-                    // a value the control does not have: fall through to the general paths
+                    // a value the control does not have: a whole warp ranks this group (general path)
+                    mlist[atomicAdd(&counters[0], 1)] = g;
+                    continue;
                 }
                 if (m > P.small_cap) {
                     mlist[atomicAdd(&counters[0], 1)] = g;
@@ -400,7 +412,7 @@ int launch_ovo(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const 
     // shared memory: fixed part + control buffer + scratch, sized so that two CTAs fit on one SM.
     // Genes whose control has more non-zeros than ref_cap keep the control in the CTA's global slab.
     const size_t fixed = (size_t)(OVO_NW * 256 + RADIX_AUX_WORDS + 2 * GROUP_CHUNK + 4) * 4 + 32 * 8 * 2 +
-                         DT_CAP * 8 + (2 * DT_CAP + 1) * 4 + 64;
+                         DT_CAP * 8 + (2 * DT_CAP + 1) * 4 + 2 * DT_HASH * 4 + 64;
     const int small_cap = 22;
     const int scratch_words = small_cap * OVO_THREADS;  // 11264 words: 22 keys per thread / 11 warp buffers
     int ref_cap = (plan->ref_group_size + 3) & ~3;
