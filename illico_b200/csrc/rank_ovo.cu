@@ -25,7 +25,7 @@ namespace illico {
 constexpr int OVO_THREADS = 512;
 constexpr int OVO_NW = OVO_THREADS / 32;
 constexpr int WARP_CAP = 1024;   // keys per warp buffer in the warp tier
-constexpr int GROUP_CHUNK = 1024;  // groups handled per sweep (bounds the deferred lists)
+constexpr int GROUP_CHUNK = 2048;  // groups handled per sweep (bounds the deferred lists)
 constexpr int DT_CAP = 22;         // distinct control values for the table fast path (<= small_cap)
 constexpr int DT_HASH = 64;        // slots of the key -> table-index hash (load factor <= 1/3)
 constexpr int FAST_MAX = 96;       // largest group (non-zeros) a single thread streams through the table path
@@ -108,10 +108,10 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
     uint32_t* scratch = refA + P.ref_cap;                   // [scratch_words] (>= ref_cap)
     uint32_t* hist = scratch + P.scratch_words;             // [OVO_NW * 256]
     uint32_t* aux = hist + OVO_NW * 256;                    // [RADIX_AUX_WORDS]
-    int* mlist = (int*)(aux + RADIX_AUX_WORDS);             // [GROUP_CHUNK]
-    int* blist = mlist + GROUP_CHUNK;                       // [GROUP_CHUNK]
-    int* counters = blist + GROUP_CHUNK;                    // [4]
-    double* redd = (double*)(counters + 4);                 // [32]
+    uint16_t* mlist = (uint16_t*)(aux + RADIX_AUX_WORDS);   // [GROUP_CHUNK] group index inside the chunk
+    uint16_t* blist = mlist + GROUP_CHUNK;                  // [GROUP_CHUNK]
+    int* counters = (int*)(blist + GROUP_CHUNK);            // [8] three rotating {medium, big} list counters + table counter
+    double* redd = (double*)(counters + 8);                 // [32]
     unsigned long long* redu = (unsigned long long*)(redd + 32);  // [32]
     double* dval = (double*)(redu + 32);                    // [DT_CAP]   f(x) of each distinct control value
     uint32_t* dkey = (uint32_t*)(dval + DT_CAP);            // [DT_CAP]   distinct control keys, ascending
@@ -126,6 +126,9 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
     const int nwb = min(OVO_NW, P.scratch_words / WARP_CAP);  // warps that own a warp-tier buffer
 
     const int ref_s0 = pl.group_seg[ref], ref_s1 = pl.group_seg[ref + 1];
+    if (tid < 8) counters[tid] = 0;
+    int cc = 0;  // chunk counter: chunk c uses counter set c % 3 and clears set (c + 1) % 3 for the next chunk
+    __syncthreads();
 
     for (int j = blockIdx.x; j < P.n_genes; j += gridDim.x) {
         const uint32_t* cnt = P.ir_cnt + (long long)j * S;
@@ -182,17 +185,17 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
         }
         // ---- distinct-value table of the control (raw counts have a handful of distinct values): groups whose
         // values all occur in it are ranked by a private histogram over the table, without sorting or searching
-        if (tid == 0) counters[2] = 0;
+        if (tid == 0) counters[6] = 0;
         __syncthreads();
         for (int i = tid; i < nref_nz; i += OVO_THREADS) {
             const uint32_t k = rA[i];
             if (i == 0 || rA[i - 1] != k) {
-                const int slot = atomicAdd(&counters[2], 1);
+                const int slot = atomicAdd(&counters[6], 1);
                 if (slot < DT_CAP) { dkey[slot] = k; dlo[slot] = i; }
             }
         }
         __syncthreads();
-        const int D = counters[2];
+        const int D = counters[6];
         const bool table = D <= DT_CAP;
         if (table && tid == 0) {
             for (int a = 1; a < D; ++a) {  // order the <= 22 entries by position (= by key)
@@ -217,8 +220,9 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
         // ================= phase 2: perturbations, in chunks of GROUP_CHUNK groups =================
         for (int g0 = 0; g0 < G; g0 += GROUP_CHUNK) {
             const int g1 = min(G, g0 + GROUP_CHUNK);
-            if (tid == 0) { counters[0] = 0; counters[1] = 0; }
-            __syncthreads();
+            int* cnt_m = counters + 2 * (cc % 3);      // [0] medium list length, [1] big list length
+            if (tid == 0) { const int nx = 2 * ((cc + 1) % 3); counters[nx] = 0; counters[nx + 1] = 0; }
+            ++cc;
             // ---- thread tier
             for (int g = g0 + tid; g < g1; g += OVO_THREADS) {
                 if (g == ref) {
@@ -241,6 +245,8 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
                     // ---- table path: private histogram over the control's distinct values
                     for (int t = 0; t < D; ++t) col[t * OVO_THREADS] = 0;
                     bool ok = true;
+                    int ne = 0;                                   // values the control does not have: (key, count)
+                    const int ne_cap = (P.small_cap - D) >> 1;    // pairs kept after the D histogram bins
                     for (int s = s0; s < s1 && ok; ++s) {
                         const int c = (int)cnt[s];
                         const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);  // 32-byte aligned slot
@@ -256,8 +262,18 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
                                     uint32_t h = (key * 2654435761u) >> 26;
                                     uint32_t hk = hkey[h];
                                     while (hk != key && hk != 0u) { h = (h + 1) & (DT_HASH - 1); hk = hkey[h]; }
-                                    if (hk == key) col[hidx[h] * OVO_THREADS] += 1;
-                                    else ok = false;
+                                    if (hk == key) {
+                                        col[hidx[h] * OVO_THREADS] += 1;  // private bin (shared atomics are slower here)
+                                    } else {
+                                        int x = 0;
+                                        while (x < ne && col[(D + 2 * x) * OVO_THREADS] != key) ++x;
+                                        if (x < ne) col[(D + 2 * x + 1) * OVO_THREADS] += 1;
+                                        else if (ne < ne_cap) {
+                                            col[(D + 2 * ne) * OVO_THREADS] = key;
+                                            col[(D + 2 * ne + 1) * OVO_THREADS] = 1;
+                                            ++ne;
+                                        } else ok = false;
+                                    }
                                 }
                             }
                         }
@@ -275,15 +291,24 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
                                 sum += (double)bq * dval[t];
                             }
                         }
+                        for (int x = 0; x < ne; ++x) {  // absent from the control: a = 0, position by binary search
+                            const uint32_t key = col[(D + 2 * x) * OVO_THREADS];
+                            const long long bq = col[(D + 2 * x + 1) * OVO_THREADS];
+                            const long long gt = (long long)(nref_nz - lower_bound_u32(rA, nref_nz, key)) +
+                                                 ((key < KEY_ZERO) ? R.zeros : 0);
+                            u2 += (unsigned long long)(bq * 2 * gt);
+                            tie += (unsigned long long)cube_minus(bq);
+                            sum += (double)bq * fc_value(key2f(key), P.flags.is_log1p);
+                        }
                         finalize_group(P, R, j, g, m, u2, tie, sum);
                         continue;
                     }
-                    // a value the control does not have: a whole warp ranks this group (general path)
-                    mlist[atomicAdd(&counters[0], 1)] = g;
+                    // too many values the control does not have: a whole warp ranks this group (general path)
+                    mlist[atomicAdd(&cnt_m[0], 1)] = (uint16_t)(g - g0);
                     continue;
                 }
                 if (m > P.small_cap) {
-                    mlist[atomicAdd(&counters[0], 1)] = g;
+                    mlist[atomicAdd(&cnt_m[0], 1)] = (uint16_t)(g - g0);
                     continue;
                 }
                 double sum = 0.0;
@@ -314,15 +339,16 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
                 finalize_group(P, R, j, g, m, u2, tie, sum);
             }
             __syncthreads();
-            // ---- warp tier
-            const int nm = counters[0];
+            // ---- warp tier (usually empty: then this barrier is the only one of the chunk)
+            const int nm = cnt_m[0];
+            if (nm == 0) continue;
             for (int e = w; e < nm && w < nwb; e += nwb) {
-                const int g = mlist[e];
+                const int g = g0 + mlist[e];
                 const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
                 int m = 0;
                 for (int s = s0; s < s1; ++s) m += (int)cnt[s];
                 if (m > WARP_CAP) {
-                    if (lane == 0) blist[atomicAdd(&counters[1], 1)] = g;
+                    if (lane == 0) blist[atomicAdd(&cnt_m[1], 1)] = (uint16_t)(g - g0);
                     continue;
                 }
                 uint32_t* buf = scratch + w * WARP_CAP;
@@ -355,9 +381,9 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
             }
             __syncthreads();
             // ---- block tier: one group at a time, sorted in the CTA's global slab
-            const int nb = counters[1];
+            const int nb = cnt_m[1];
             for (int e = 0; e < nb; ++e) {
-                const int g = blist[e];
+                const int g = g0 + blist[e];
                 const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
                 int m = 0;
                 for (int s = s0; s < s1; ++s) {
@@ -411,7 +437,7 @@ int launch_ovo(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const 
 
     // shared memory: fixed part + control buffer + scratch, sized so that two CTAs fit on one SM.
     // Genes whose control has more non-zeros than ref_cap keep the control in the CTA's global slab.
-    const size_t fixed = (size_t)(OVO_NW * 256 + RADIX_AUX_WORDS + 2 * GROUP_CHUNK + 4) * 4 + 32 * 8 * 2 +
+    const size_t fixed = (size_t)(OVO_NW * 256 + RADIX_AUX_WORDS + GROUP_CHUNK + 8) * 4 + 32 * 8 * 2 +
                          DT_CAP * 8 + (2 * DT_CAP + 1) * 4 + 2 * DT_HASH * 4 + 64;
     const int small_cap = 22;
     const int scratch_words = small_cap * OVO_THREADS;  // 11264 words: 22 keys per thread / 11 warp buffers
