@@ -22,7 +22,8 @@ class Plan(C.Structure):
 
     _fields_ = [
         ("n_cells", _i32), ("n_groups", _i32), ("n_segments", _i32), ("ref_group", _i32),
-        ("max_group_size", _i32), ("ref_group_size", _i32), ("slot_cap", _i32),
+        ("max_group_size", _i32), ("ref_group_size", _i32), ("ref_seg_begin", _i32), ("ref_seg_end", _i32),
+        ("slot_cap", _i32),
         ("perm", _vp), ("cell_seg", _vp), ("seg_pos", _vp), ("seg_base", _vp), ("seg_group", _vp),
         ("group_seg", _vp), ("group_size", _vp),
     ]

@@ -40,13 +40,17 @@ static int check_plan(const illico_plan_t* p) {
         return 1;
     }
     if (p->ref_group >= p->n_groups) { set_error("plan.ref_group out of range"); return 1; }
+    if (p->ref_group >= 0 && (p->ref_seg_begin < 0 || p->ref_seg_end > p->n_segments || p->ref_seg_begin >= p->ref_seg_end)) {
+        set_error("plan.ref_seg_* out of range");
+        return 1;
+    }
     return 0;
 }
 
 static int max_resident_ctas() {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms * 2;
+    return sms * 4;
 }
 
 }  // namespace illico

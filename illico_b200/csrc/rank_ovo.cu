@@ -20,10 +20,10 @@
 #include "epilogue.cuh"
 #include "sort.cuh"
 
+#include <stdlib.h>
+
 namespace illico {
 
-constexpr int OVO_THREADS = 512;
-constexpr int OVO_NW = OVO_THREADS / 32;
 constexpr int WARP_CAP = 1024;   // keys per warp buffer in the warp tier
 constexpr int GROUP_CHUNK = 2048;  // groups handled per sweep (bounds the deferred lists)
 constexpr int DT_CAP = 22;         // distinct control values for the table fast path (<= small_cap)
@@ -97,7 +97,9 @@ __device__ __forceinline__ void finalize_group(const OvoParams& P, const RefInfo
     if (P.dbg_tie_exact) P.dbg_tie_exact[di] = (long long)tie_exact;
 }
 
-__global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) {
+template <int OVO_THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoParams P) {
+    constexpr int OVO_NW = OVO_THREADS / 32;
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const illico_plan_t& pl = P.plan;
@@ -415,9 +417,67 @@ __global__ void __launch_bounds__(OVO_THREADS, 2) ovo_kernel(const OvoParams P) 
     }
 }
 
+// max over the batch's genes of the control group's non-zero count: sizes the shared control buffer
+__global__ void max_ref_nnz_kernel(const uint32_t* __restrict__ ir_cnt, int n_genes, int S, int s0, int s1, int* out) {
+    int m = 0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_genes; j += gridDim.x * blockDim.x) {
+        int c = 0;
+        for (int s = s0; s < s1; ++s) c += (int)ir_cnt[(long long)j * S + s];
+        m = max(m, c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
 // ------------------------------------------------------------------------------------------------------
 size_t ovo_workspace_bytes(const illico_plan_t* plan, int n_ctas) {
     return (size_t)n_ctas * 4 * (size_t)plan->max_group_size * sizeof(uint32_t);
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int NT, int MIN_CTAS>
+static int launch_ovo_t(OvoParams& P, const illico_plan_t* plan, void* workspace, size_t workspace_bytes, int sms,
+                        int max_smem, cudaStream_t stream) {
+    constexpr int NW = NT / 32;
+    // shared memory: fixed part + control buffer + scratch.  Genes whose control has more non-zeros than ref_cap
+    // keep the control in the CTA's global slab.
+    const size_t fixed = (size_t)(NW * 256 + RADIX_AUX_WORDS + GROUP_CHUNK + 8) * 4 + 32 * 8 * 2 + DT_CAP * 8 +
+                         (2 * DT_CAP + 1) * 4 + 2 * DT_HASH * 4 + 64;
+    const int small_cap = DT_CAP;
+    int scratch_words = small_cap * NT;               // thread tier: small_cap keys per thread
+    if (scratch_words < 2 * WARP_CAP) scratch_words = 2 * WARP_CAP;  // at least two warp-tier buffers
+    // The control buffer is sized to what this batch needs (P.ref_cap holds the measured maximum): shared memory
+    // that is not carved out stays L1 cache for the scattered reads of the group slots.
+    int ref_cap = (P.ref_cap + 3) & ~3;
+    if (ref_cap < 4) ref_cap = 4;
+    const int ref_cap_max = env_int("ILLICO_OVO_REF_CAP", scratch_words);
+    if (ref_cap > ref_cap_max) ref_cap = ref_cap_max;
+    if (ref_cap > scratch_words) ref_cap = scratch_words;  // the ping-pong partner is the scratch area
+    const size_t need = fixed + (size_t)(ref_cap + scratch_words) * 4;
+    if (need > (size_t)max_smem) { set_error("ovo_kernel needs %zu bytes of shared memory", need); return 1; }
+    P.ref_cap = ref_cap; P.small_cap = small_cap; P.scratch_words = scratch_words;
+    auto kern = ovo_kernel<NT, MIN_CTAS>;
+    ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    int occ = 0;
+    ILLICO_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, need));
+    if (occ < 1) { set_error("ovo_kernel does not fit: %zu bytes of shared memory", need); return 1; }
+    int grid = sms * occ;
+    if (grid > P.n_genes) grid = P.n_genes;
+    const size_t slab_words = 4 * (size_t)plan->max_group_size;
+    if ((size_t)grid * slab_words * 4 > workspace_bytes) {
+        grid = (int)(workspace_bytes / (slab_words * 4));
+        if (grid < 1) { set_error("rank workspace too small: %zu bytes", workspace_bytes); return 1; }
+    }
+    P.slab = (uint32_t*)workspace; P.slab_words = (long long)slab_words;
+    kern<<<grid, NT, need, stream>>>(P);
+    count_launch();
+    ILLICO_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 int launch_ovo(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const illico_plan_t* plan,
@@ -434,36 +494,23 @@ int launch_ovo(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const 
     P.results = results; P.gstride = gstride;
     P.dbg_u2 = dbg ? (long long*)dbg->u2 : nullptr; P.dbg_tie = dbg ? dbg->tie_sum : nullptr;
     P.dbg_tie_exact = dbg ? (long long*)dbg->tie_exact : nullptr;
-
-    // shared memory: fixed part + control buffer + scratch, sized so that two CTAs fit on one SM.
-    // Genes whose control has more non-zeros than ref_cap keep the control in the CTA's global slab.
-    const size_t fixed = (size_t)(OVO_NW * 256 + RADIX_AUX_WORDS + GROUP_CHUNK + 8) * 4 + 32 * 8 * 2 +
-                         DT_CAP * 8 + (2 * DT_CAP + 1) * 4 + 2 * DT_HASH * 4 + 64;
-    const int small_cap = 22;
-    const int scratch_words = small_cap * OVO_THREADS;  // 11264 words: 22 keys per thread / 11 warp buffers
-    int ref_cap = (plan->ref_group_size + 3) & ~3;
-    if (ref_cap < 4) ref_cap = 4;
-    if (ref_cap > scratch_words) ref_cap = scratch_words;  // the ping-pong partner is the scratch area
-    const size_t need = fixed + (size_t)(ref_cap + scratch_words) * 4;
-    if (need > (size_t)max_smem) { set_error("ovo_kernel needs %zu bytes of shared memory", need); return 1; }
-    P.ref_cap = ref_cap; P.small_cap = small_cap; P.scratch_words = scratch_words;
-
-    ILLICO_CUDA_OK(cudaFuncSetAttribute(ovo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    int occ = 0;
-    ILLICO_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ovo_kernel, OVO_THREADS, need));
-    if (occ < 1) { set_error("ovo_kernel does not fit: %zu bytes of shared memory", need); return 1; }
-    int grid = sms * occ;
-    if (grid > n_genes) grid = n_genes;
-    const size_t slab_words = 4 * (size_t)plan->max_group_size;
-    if ((size_t)grid * slab_words * 4 > workspace_bytes) {
-        grid = (int)(workspace_bytes / (slab_words * 4));
-        if (grid < 1) { set_error("rank workspace too small: %zu bytes", workspace_bytes); return 1; }
+    // measured control size (one tiny kernel + a 4-byte read-back; the staging kernel is already in flight)
+    {
+        int* d_max = reinterpret_cast<int*>(workspace);
+        int h_max = 0;
+        ILLICO_CUDA_OK(cudaMemsetAsync(d_max, 0, sizeof(int), stream));
+        max_ref_nnz_kernel<<<(n_genes + 255) / 256, 256, 0, stream>>>(ir_cnt, n_genes, plan->n_segments, plan->ref_seg_begin,
+                                                                      plan->ref_seg_end, d_max);
+        count_launch();
+        ILLICO_CUDA_OK(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
+        P.ref_cap = h_max;
+        workspace = reinterpret_cast<char*>(workspace) + 256;
+        workspace_bytes -= 256;
     }
-    P.slab = (uint32_t*)workspace; P.slab_words = (long long)slab_words;
-    ovo_kernel<<<grid, OVO_THREADS, need, stream>>>(P);
-    count_launch();
-    ILLICO_CUDA_OK(cudaGetLastError());
-    return 0;
+    if (env_int("ILLICO_OVO_THREADS", 256) == 256)
+        return launch_ovo_t<256, 4>(P, plan, workspace, workspace_bytes, sms, max_smem, stream);
+    return launch_ovo_t<512, 2>(P, plan, workspace, workspace_bytes, sms, max_smem, stream);
 }
 
 }  // namespace illico

@@ -19,6 +19,8 @@
 #include "epilogue.cuh"
 #include "sort.cuh"
 
+#include <stdlib.h>
+
 namespace illico {
 
 constexpr int OVR_THREADS = 512;
@@ -116,13 +118,21 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
             int maxc = c;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(FULL, maxc, o));
-            for (int i = 0; i < maxc; ++i) {
-                const bool act = i < c;
-                uint32_t key = act ? f2key(src[i]) : HASH_EMPTY;
-                if (act && key == HASH_EMPTY) key = 1u;  // only a NaN payload maps here
-                const unsigned peers = __match_any_sync(FULL, key);
-                if (act && lane == __ffs(peers) - 1 && !*(volatile int*)&sc[1])
-                    hash_insert(hkeys, hvals, &sc[0], &sc[1], key, __popc(peers));
+            const float4* src4 = reinterpret_cast<const float4*>(src);  // slots are 32-byte aligned and padded
+            float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < maxc; i += 4) {
+                const float4 q4 = nxt;
+                if (i + 4 < c) nxt = src4[(i >> 2) + 1];
+                const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool act = i + e < c;
+                    uint32_t key = act ? f2key(q[e]) : HASH_EMPTY;
+                    if (act && key == HASH_EMPTY) key = 1u;  // only a NaN payload maps here
+                    const unsigned peers = __match_any_sync(FULL, key);
+                    if (act && lane == __ffs(peers) - 1 && !*(volatile int*)&sc[1])
+                        hash_insert(hkeys, hvals, &sc[0], &sc[1], key, __popc(peers));
+                }
             }
         }
         const long long nnz = (long long)block_sum<unsigned long long>(my_nnz, redu);  // syncs
@@ -257,17 +267,27 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
             const float* src = vals + pl.seg_base[s];
             unsigned long long acc = 0;
             double sum = 0.0;
-            for (int i = 0; i < c; ++i) {
-                const float v = src[i];
-                uint32_t key = f2key(v);
-                if (key == HASH_EMPTY) key = 1u;
-                if (!path_s) {
-                    acc += hvals[hash_find(hkeys, key)];
-                } else {
-                    const int lo = lower_bound_u32(sk, (int)nnz, key), hi = upper_bound_u32(sk, (int)nnz, key);
-                    acc += (unsigned long long)lo + hi + 1 + ((key > KEY_ZERO) ? 2ull * (unsigned long long)n0 : 0ull);
+            const float4* src4 = reinterpret_cast<const float4*>(src);
+            float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < c; i += 4) {
+                const float4 q4 = nxt;
+                if (i + 4 < c) nxt = src4[(i >> 2) + 1];
+                const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (i + e < c) {
+                        const float v = q[e];
+                        uint32_t key = f2key(v);
+                        if (key == HASH_EMPTY) key = 1u;
+                        if (!path_s) {
+                            acc += hvals[hash_find(hkeys, key)];
+                        } else {
+                            const int lo = lower_bound_u32(sk, (int)nnz, key), hi = upper_bound_u32(sk, (int)nnz, key);
+                            acc += (unsigned long long)lo + hi + 1 + ((key > KEY_ZERO) ? 2ull * (unsigned long long)n0 : 0ull);
+                        }
+                        sum += fc_value(v, P.flags.is_log1p);
+                    }
                 }
-                sum += fc_value(v, P.flags.is_log1p);
             }
             seg_r2[s] = acc;
             seg_sum[s] = sum;
@@ -332,7 +352,12 @@ int launch_ovr(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const 
     // two CTAs per SM: ~113 KB each.  Fixed part: histogram / distinct table 16 KB + scalars.
     const size_t fixed = (size_t)(OVR_NW * 256 + RADIX_AUX_WORDS + 8) * 4 + 32 * 8 * 2 + 8 + 64;
     const size_t per_cta = (size_t)(max_smem + 1024) / 2 - 1024;
+    // Path S sorts in shared memory only up to sort_cap keys (default: the hash table's footprint); what is not
+    // carved out stays L1 cache for the scattered reads of the group slots.
     int sort_cap = (int)((per_cta - fixed) / 8) & ~3;
+    const char* sc_env = getenv("ILLICO_OVR_SORT_CAP");
+    const int want = sc_env ? atoi(sc_env) : HASH_CAP;
+    if (sort_cap > want) sort_cap = want;
     if (sort_cap < HASH_CAP) sort_cap = HASH_CAP;
     P.sort_cap = sort_cap;
     const size_t need = fixed + (size_t)2 * sort_cap * 4;

@@ -115,6 +115,8 @@ class HostPlan:
         self.max_group_size = int(counts.max())
         self.ref_group_size = int(counts[self.ref_group]) if self.ref_group >= 0 else 0
         self.slot_cap = int(seg_base[-1])
+        self.ref_seg_begin = int(group_seg[self.ref_group]) if self.ref_group >= 0 else 0
+        self.ref_seg_end = int(group_seg[self.ref_group + 1]) if self.ref_group >= 0 else 0
         self.perm, self.cell_seg = i32(perm), i32(cell_seg)
         self.seg_pos, self.seg_base, self.seg_group = i32(seg_pos), i32(seg_base), i32(seg_group)
         self.group_seg, self.group_size = i32(group_seg), i32(counts)

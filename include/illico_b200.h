@@ -72,6 +72,8 @@ typedef struct illico_plan {
     int32_t ref_group;          /* -1 = one-versus-rest (groups.py:55-57) */
     int32_t max_group_size;
     int32_t ref_group_size;     /* cells of the reference group (0 for one-versus-rest) */
+    int32_t ref_seg_begin;      /* segments [ref_seg_begin, ref_seg_end) belong to the reference group */
+    int32_t ref_seg_end;
     int32_t slot_cap;           /* floats per gene in ir_vals (= seg_base[n_segments]) */
     const int32_t* perm;        /* [n_cells]     perm[pos] = cell (row) index, groups contiguous, stable */
     const int32_t* cell_seg;    /* [n_cells]     segment of each cell (row -> segment) */
