@@ -344,7 +344,7 @@ def main():
         import oracle
 
         threads = oracle.max_threads()
-        sample = a.cpu_sample_genes or min(a.genes, max(threads, 64))
+        sample = a.cpu_sample_genes or min(a.genes, 32 * threads)  # ~10 s of CPU work on the K562 shape
         Xs = host_sample(Xdev, fmt, sample)
         cpu_run(fmt, test, Xs[:, : min(sample, 4)] if fmt == "dense" else Xs[:, : min(sample, 4)], labels, reference, a.genes,
                 min(sample, 4), threads)  # warm the page cache / thread pool
@@ -384,7 +384,7 @@ def reference_arm(a, fmt, test, rank, world):
     from illico_b200 import synth
 
     threads = oracle.max_threads()
-    sample = a.cpu_sample_genes or min(a.genes, max(threads, 64))
+    sample = a.cpu_sample_genes or min(a.genes, 32 * threads)
     labels, reference = make_labels(a.seed, a.cells, a.perts, test)
     try:
         import torch

@@ -12,15 +12,14 @@
 // element exactly once with warp-coalesced row segments and writes only the ~10 % that are non-zero.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace illico {
 
 constexpr int STAGE_WARPS = 8;
-constexpr int STAGE_GENES = STAGE_WARPS * 32;
 constexpr int STAGE_MAX_SEGS = 16;
 constexpr int STAGE_INFLIGHT = 16;  // cell rows in flight per warp (16 x 128 B)
 
-// Appends v to the lane's slot when it is non-zero: one predicate, one predicated store, one predicated
-// pointer bump (no divergent branch).
 // Appends v to the lane's slot when it is non-zero.  Non-zeros are collected eight at a time in a lane-private
 // shared-memory column and leave as ONE full, aligned 32-byte sector (slots are 32-byte aligned and padded), so
 // L2 never sees a partial-sector write that it would have to merge with a DRAM fill.
@@ -45,69 +44,86 @@ __device__ __forceinline__ const float* row_ptr(const float* col, int row, uint3
                                           (unsigned long long)(uint32_t)row * (unsigned long long)ld_bytes);
 }
 
-// One warp = 32 adjacent genes: lane = gene, so every cell row is one coalesced 128-byte request per warp and
-// the CTA's 8 warps cover 1 KB of the row.  Each lane owns one (gene, segment) slot at a time and appends the
-// non-zeros of the segment's cells in plan order: deterministic layout, no atomics, no shared-memory
-// transposition, 32 registers (full occupancy keeps ~64 KB of loads in flight per SM).  The per-(gene, segment)
-// counts go through a shared tile so that each gene's counts leave as one contiguous run.
-template <bool TILE_COUNTS>
+// One warp = 32 * VEC adjacent genes: lane = VEC adjacent genes, so every cell row is one coalesced 128 * VEC
+// byte request per warp and the CTA's 8 warps cover 1 KB * VEC of the row.  Each lane owns VEC (gene, segment)
+// slots at a time and appends the non-zeros of the segment's cells in plan order: deterministic layout, no
+// atomics, no shared-memory transposition.  The per-(gene, segment) counts go through a shared tile so that
+// each gene's counts leave as one contiguous run.
+template <bool TILE_COUNTS, int VEC>
 __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const float* __restrict__ X, long long ld,
                                                                        int gene_lb, int b, const illico_plan_t pl,
                                                                        float* __restrict__ ir_vals,
                                                                        uint32_t* __restrict__ ir_cnt,
                                                                        int segs_per_cta) {
-    __shared__ uint32_t cnt_tile[TILE_COUNTS ? STAGE_MAX_SEGS : 1][TILE_COUNTS ? STAGE_GENES : 1];
-    __shared__ float wbuf[8][STAGE_WARPS * 32];
-    static_assert(STAGE_WARPS * 32 * 4 == 1024, "append_nonzero assumes a 1 KB row pitch");
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int jt = w * 32 + lane;
-    const uint32_t wbuf_t = (uint32_t)__cvta_generic_to_shared(&wbuf[0][threadIdx.x]);
-    const int jb = blockIdx.x * STAGE_GENES + jt;
-    const bool active = jb < b;
-    const int jj = active ? jb : b - 1;                  // inactive lanes shadow the last gene and never store
+    constexpr int NT = STAGE_WARPS * 32;
+    __shared__ uint16_t cnt_tile[TILE_COUNTS ? STAGE_MAX_SEGS : 1][TILE_COUNTS ? NT * VEC : 1];
+    __shared__ float wbuf[VEC][8][NT];
+    static_assert(NT * 4 == 1024, "append_nonzero assumes a 1 KB row pitch");
+    const int lane = threadIdx.x & 31;
+    const int t = threadIdx.x;
+    const int jb = (blockIdx.x * NT + t) * VEC;          // first of this lane's VEC genes inside the batch
+    const bool active = jb < b;                          // b is a multiple of VEC (host)
+    const int jj = active ? jb : 0;                      // inactive lanes shadow gene 0 and never store
     const float* col = X + gene_lb + jj;
     const uint32_t ldb = (uint32_t)(ld * 4);
+    const uint32_t wbuf_t = (uint32_t)__cvta_generic_to_shared(&wbuf[0][0][t]);
     const int S = pl.n_segments;
     const int s_begin = blockIdx.y * segs_per_cta, s_end = min(S, s_begin + segs_per_cta);
     for (int s = s_begin; s < s_end; ++s) {
         const int p0 = pl.seg_pos[s], p1 = pl.seg_pos[s + 1];
-        float* const out0 = ir_vals + (long long)jj * pl.slot_cap + pl.seg_base[s];
-        uint32_t cnt = 0;
+        float* out0[VEC];
+        uint32_t cnt[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            out0[e] = ir_vals + (long long)(jj + e) * pl.slot_cap + pl.seg_base[s];
+            cnt[e] = 0;
+        }
         for (int p = p0; p < p1; p += 32) {
             const int nrows = min(32, p1 - p);
             const int myrow = pl.perm[p + min(lane, nrows - 1)];   // tail lanes repeat the last cell (never stored)
-            if (nrows == 32 && active) {
+            const bool full = nrows == 32;
+#pragma unroll 1
+            for (int k0 = 0; k0 < nrows; k0 += STAGE_INFLIGHT) {
+                float v[STAGE_INFLIGHT][VEC];
 #pragma unroll
-                for (int k0 = 0; k0 < 32; k0 += STAGE_INFLIGHT) {
-                    float v[STAGE_INFLIGHT];
-#pragma unroll
-                    for (int u = 0; u < STAGE_INFLIGHT; ++u)
-                        v[u] = __ldcs(row_ptr(col, __shfl_sync(FULL, myrow, k0 + u), ldb));
-#pragma unroll
-                    for (int u = 0; u < STAGE_INFLIGHT; ++u) append_nonzero(out0, cnt, v[u], wbuf, wbuf_t, jt);
+                for (int u = 0; u < STAGE_INFLIGHT; ++u) {
+                    const float* src = row_ptr(col, __shfl_sync(FULL, myrow, (k0 + u) & 31), ldb);
+                    if (VEC == 2) {
+                        const float2 q = __ldcs(reinterpret_cast<const float2*>(src));
+                        v[u][0] = q.x; v[u][VEC - 1] = q.y;
+                    } else {
+                        v[u][0] = __ldcs(src);
+                    }
                 }
-            } else {
-                for (int k0 = 0; k0 < nrows; k0 += 8) {
-                    float v[8];
+                if (active) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = __ldcs(row_ptr(col, __shfl_sync(FULL, myrow, (k0 + u) & 31), ldb));
+                    for (int u = 0; u < STAGE_INFLIGHT; ++u) {
+                        if (full || k0 + u < nrows) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (active && k0 + u < nrows) append_nonzero(out0, cnt, v[u], wbuf, wbuf_t, jt);
+                            for (int e = 0; e < VEC; ++e)
+                                append_nonzero(out0[e], cnt[e], v[u][e], wbuf[e], wbuf_t + e * 8 * NT * 4, t);
+                        }
+                    }
                 }
             }
         }
-        if (active && (cnt & 7u)) flush8(out0, cnt & ~7u, wbuf, jt);  // tail: one padded full sector
-        if (TILE_COUNTS) cnt_tile[s - s_begin][jt] = cnt;
-        else if (active) ir_cnt[(long long)jb * S + s] = cnt;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            if (active && (cnt[e] & 7u)) flush8(out0[e], cnt[e] & ~7u, wbuf[e], t);  // tail: one padded full sector
+            if (TILE_COUNTS) cnt_tile[s - s_begin][t * VEC + e] = (uint16_t)cnt[e];
+            else if (active) ir_cnt[(long long)(jb + e) * S + s] = cnt[e];
+        }
     }
     if (TILE_COUNTS) {
         __syncthreads();
-        // thread t owns gene t of the CTA's 256 and writes its consecutive segments
+        // thread t writes the consecutive segments of genes t, t + NT, ... of the CTA's NT * VEC genes
         const int nseg = s_end - s_begin;
-        if (active) {
-            uint32_t* dst = ir_cnt + (long long)jb * S + s_begin;
-            for (int ls = 0; ls < nseg; ++ls) dst[ls] = cnt_tile[ls][jt];
+        for (int g = t; g < NT * VEC; g += NT) {
+            const int j = blockIdx.x * NT * VEC + g;
+            if (j < b) {
+                uint32_t* dst = ir_cnt + (long long)j * S + s_begin;
+                for (int ls = 0; ls < nseg; ++ls) dst[ls] = cnt_tile[ls][g];
+            }
         }
     }
 }
@@ -186,6 +202,12 @@ __global__ void check_csr_sorted_kernel(const int32_t* __restrict__ indices, con
 }
 
 // ------------------------------------------------------------------------------------------------------
+template <bool TILE, int VEC>
+static void launch_stage_dense_t(dim3 grid, cudaStream_t stream, const float* X, long long ld, int gene_lb, int b,
+                                 const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, int segs_per_cta) {
+    stage_dense_kernel<TILE, VEC><<<grid, STAGE_WARPS * 32, 0, stream>>>(X, ld, gene_lb, b, *plan, ir_vals, ir_cnt, segs_per_cta);
+}
+
 int launch_stage_dense(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
                        uint32_t* ir_cnt, cudaStream_t stream) {
     if (b <= 0 || plan->n_segments <= 0) return 0;
@@ -197,15 +219,21 @@ int launch_stage_dense(const float* X, long long ld, int gene_lb, int b, const i
     if (segs_per_cta < 1) segs_per_cta = 1;
     if (segs_per_cta > STAGE_MAX_SEGS) segs_per_cta = STAGE_MAX_SEGS;
     long long gy = (S + segs_per_cta - 1) / segs_per_cta;
-    const unsigned gx = (unsigned)((b + STAGE_GENES - 1) / STAGE_GENES);
-    if (gy <= 65535) {
-        stage_dense_kernel<true><<<dim3(gx, (unsigned)gy), STAGE_WARPS * 32, 0, stream>>>(X, ld, gene_lb, b, *plan, ir_vals,
-                                                                                        ir_cnt, segs_per_cta);
-    } else {  // more than a million segments: any number of segments per CTA, counts written directly
+    // two genes per lane (64-bit loads) when the batch is 8-byte aligned
+    const char* v2 = getenv("ILLICO_STAGE_VEC");
+    const bool vec2 = (!v2 || atoi(v2) == 2) && ((reinterpret_cast<uintptr_t>(X) & 7) == 0) && (ld % 2 == 0) &&
+                      (gene_lb % 2 == 0) && (b % 2 == 0);
+    const int gpc = STAGE_WARPS * 32 * (vec2 ? 2 : 1);
+    const unsigned gx = (unsigned)((b + gpc - 1) / gpc);
+    const bool tile = gy <= 65535 && plan->max_group_size < 65536;
+    if (!tile) {  // more than a million segments: any number of segments per CTA, counts written directly
         while (gy > 65535) { segs_per_cta *= 2; gy = (S + segs_per_cta - 1) / segs_per_cta; }
-        stage_dense_kernel<false><<<dim3(gx, (unsigned)gy), STAGE_WARPS * 32, 0, stream>>>(X, ld, gene_lb, b, *plan, ir_vals,
-                                                                                         ir_cnt, segs_per_cta);
     }
+    const dim3 grid(gx, (unsigned)gy);
+    if (tile && vec2) launch_stage_dense_t<true, 2>(grid, stream, X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta);
+    else if (tile) launch_stage_dense_t<true, 1>(grid, stream, X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta);
+    else if (vec2) launch_stage_dense_t<false, 2>(grid, stream, X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta);
+    else launch_stage_dense_t<false, 1>(grid, stream, X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta);
     count_launch();
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
