@@ -284,8 +284,15 @@ def main():
         dom, dom_bytes, dom_ms = f"{test}_kernel", rank_bytes, t_rank
     n_launch_dom = len(batches)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None  # dram bytes per launch from the committed ncu --set full capture (same shape only)
+    try:
+        if (a.cells, a.genes, a.perts) == (300_000, 8_000, 2_000) and n_launch_dom == 1:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                traffic = json.load(f)["bytes_per_launch"].get(dom.replace("stage_dense", "stage_dense").replace("_kernel", "_kernel"))
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "launches_per_step": n_launch_dom, "ms_per_launch": round(dom_ms / n_launch_dom, 4),
                 "algorithmic_bytes_per_launch": int(dom_bytes / n_launch_dom),
                 "stage_ms": round(t_stage, 3), "rank_ms": round(t_rank, 3),

@@ -23,7 +23,7 @@ import pandas as pd
 import torch
 from scipy import sparse
 
-from .engine import CSR, Engine, make_flags
+from .engine import CSR, Engine, make_flags, require_cuda
 from .groups import GroupContainer, encode_and_count_groups
 from .registry import DataHandler, Test, data_handler_registry, dispatcher_registry  # noqa: F401
 
@@ -90,13 +90,20 @@ def asymptotic_wilcoxon(
         X = sparse.csr_matrix(X) if isinstance(X, sparse.csr_array) else sparse.csc_matrix(X)
     data_handler = data_handler_registry.get(X)  # KeyError for unsupported containers, like the reference
 
+    # In-RAM input: start the host->device copy first; it runs (asynchronously for pinned memory) while the
+    # host encodes the groups and builds the plan.
+    dev = require_cuda(device)
+    if data_handler.in_ram:
+        with torch.cuda.device(dev):
+            data_handler.to_device(X, dev)
+
     # the reference goes through `.tolist()` + a dict loop (utils/groups.py:42-45); same encoding, vectorised
     unique_raw_groups, grpc = encode_and_count_groups(groups=adata.obs[group_keys], ref_group=reference)
     n_cells, n_genes = X.shape
     if grpc.encoded_groups.size != n_cells:
         raise ValueError(f"{grpc.encoded_groups.size} group labels for {n_cells} cells")
 
-    engine = Engine(grpc, device)
+    engine = Engine(grpc, dev)
     fmt = data_handler.kernel_data_format().value
     flags = make_flags(is_log1p, use_continuity, tie_correct, alternative, fmt)
     iterator = _batches(n_genes, batch_size, engine, data_handler.in_ram)

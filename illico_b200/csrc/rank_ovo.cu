@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 uint32_t h = (dkey[a] * 2654435761u) >> 26;
                 while (hkey[h] != 0u) h = (h + 1) & (DT_HASH - 1);
                 hkey[h] = dkey[a];
-                hidx[h] = a;
+                hidx[h] = a * OVO_THREADS;
             }
         }
         __syncthreads();
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                                     uint32_t hk = hkey[h];
                                     while (hk != key && hk != 0u) { h = (h + 1) & (DT_HASH - 1); hk = hkey[h]; }
                                     if (hk == key) {
-                                        col[hidx[h] * OVO_THREADS] += 1;  // private bin (shared atomics are slower here)
+                                        col[hidx[h]] += 1;  // hidx holds bin * OVO_THREADS (private bin; shared atomics are slower)
                                     } else {
                                         int x = 0;
                                         while (x < ne && col[(D + 2 * x) * OVO_THREADS] != key) ++x;

@@ -30,13 +30,18 @@ __device__ __forceinline__ void flush8(float* out0, uint32_t first, const float 
     __stcs(dst, a);
     __stcs(dst + 1, b);
 }
-__device__ __forceinline__ void append_nonzero(float* out0, uint32_t& cnt, float v, float (*wbuf)[STAGE_WARPS * 32],
-                                               uint32_t wbuf_t_addr, int t) {
-    uint32_t nz;
-    const uint32_t addr = wbuf_t_addr + ((cnt & 7u) << 10);  // &wbuf[cnt & 7][t]  (row pitch 256 floats = 1 KB)
-    asm volatile("{ .reg .pred p; setp.neu.f32 p, %3, 0f00000000; @p st.shared.f32 [%2], %3; @p add.u32 %0, %0, 1; "
-                 "selp.u32 %1, 1, 0, p; }" : "+r"(cnt), "=r"(nz) : "r"(addr), "f"(v) : "memory");
-    if (nz && (cnt & 7u) == 0u) flush8(out0, cnt - 8u, wbuf, t);
+// `off` = byte offset of the next free entry in the lane's shared column (1 KB per entry, 8 entries);
+// `done` = values already written to the slot.  Six instructions per element, no divergent branch except the
+// flush every eighth non-zero.
+__device__ __forceinline__ void append_nonzero(float* out0, uint32_t& done, uint32_t& off, float v,
+                                               float (*wbuf)[STAGE_WARPS * 32], uint32_t wbuf_t_addr, int t) {
+    asm volatile("{ .reg .pred p; setp.neu.f32 p, %2, 0f00000000; @p st.shared.f32 [%1], %2; @p add.u32 %0, %0, 1024; }"
+                 : "+r"(off) : "r"(wbuf_t_addr + off), "f"(v) : "memory");
+    if (off == 8192u) {
+        flush8(out0, done, wbuf, t);
+        done += 8u;
+        off = 0u;
+    }
 }
 // row * ld in one wide multiply-add (row < 2^31, ld * 4 < 2^32: checked by the host)
 __device__ __forceinline__ const float* row_ptr(const float* col, int row, uint32_t ld_bytes) {
@@ -72,11 +77,12 @@ __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const flo
     for (int s = s_begin; s < s_end; ++s) {
         const int p0 = pl.seg_pos[s], p1 = pl.seg_pos[s + 1];
         float* out0[VEC];
-        uint32_t cnt[VEC];
+        uint32_t done[VEC], off[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             out0[e] = ir_vals + (long long)(jj + e) * pl.slot_cap + pl.seg_base[s];
-            cnt[e] = 0;
+            done[e] = 0;
+            off[e] = 0;
         }
         for (int p = p0; p < p1; p += 32) {
             const int nrows = min(32, p1 - p);
@@ -101,7 +107,7 @@ __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const flo
                         if (full || k0 + u < nrows) {
 #pragma unroll
                             for (int e = 0; e < VEC; ++e)
-                                append_nonzero(out0[e], cnt[e], v[u][e], wbuf[e], wbuf_t + e * 8 * NT * 4, t);
+                                append_nonzero(out0[e], done[e], off[e], v[u][e], wbuf[e], wbuf_t + e * 8 * NT * 4, t);
                         }
                     }
                 }
@@ -109,9 +115,10 @@ __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const flo
         }
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            if (active && (cnt[e] & 7u)) flush8(out0[e], cnt[e] & ~7u, wbuf[e], t);  // tail: one padded full sector
-            if (TILE_COUNTS) cnt_tile[s - s_begin][t * VEC + e] = (uint16_t)cnt[e];
-            else if (active) ir_cnt[(long long)(jb + e) * S + s] = cnt[e];
+            if (active && off[e]) flush8(out0[e], done[e], wbuf[e], t);  // tail: one padded full sector
+            const uint32_t cnt = done[e] + (off[e] >> 10);
+            if (TILE_COUNTS) cnt_tile[s - s_begin][t * VEC + e] = (uint16_t)cnt;
+            else if (active) ir_cnt[(long long)(jb + e) * S + s] = cnt;
         }
     }
     if (TILE_COUNTS) {

@@ -102,27 +102,10 @@ class Engine:
 
     # ---- uploads (plumbing) -----------------------------------------------------------------------------
     def upload_dense(self, X: np.ndarray, gene_lb: int = 0, gene_ub: int | None = None) -> DeviceMatrix:
-        """Copies ``X[:, gene_lb:gene_ub]`` (any real dtype) into a float32 device matrix."""
-        n, N = X.shape
-        gene_ub = N if gene_ub is None else gene_ub
-        view = X[:, gene_lb:gene_ub]
-        with torch.cuda.device(self.device):
-            t = torch.from_numpy(view) if isinstance(view, np.ndarray) else view
-            if t.dtype == torch.float32:
-                d = torch.empty((n, gene_ub - gene_lb), dtype=torch.float32, device=self.device)
-                d.copy_(t, non_blocking=True)
-            else:
-                d = _to_f32_exact(t.to(self.device))
-        return DeviceMatrix(DENSE, (n, gene_ub - gene_lb), d, gene_offset=gene_lb)
+        return upload_dense(X, self.device, gene_lb, gene_ub)
 
     def upload_sparse(self, X, fmt: str) -> DeviceMatrix:
-        with torch.cuda.device(self.device):
-            data = torch.from_numpy(np.ascontiguousarray(X.data))
-            data = data.to(self.device, non_blocking=True)
-            data = data if data.dtype == torch.float32 else _to_f32_exact(data)
-            indices = torch.from_numpy(np.ascontiguousarray(X.indices, dtype=np.int32)).to(self.device, non_blocking=True)
-            indptr = torch.from_numpy(np.ascontiguousarray(X.indptr, dtype=np.int64)).to(self.device, non_blocking=True)
-        return DeviceMatrix(fmt, tuple(X.shape), data, indices, indptr)
+        return upload_sparse(X, fmt, self.device)
 
     def check_csr_sorted(self, M: DeviceMatrix) -> bool:
         st = torch.cuda.current_stream(self.device).cuda_stream
@@ -172,6 +155,34 @@ class Engine:
                 rc = fn(M.data.data_ptr(), M.indices.data_ptr(), M.indptr.data_ptr(), lb, b, C.byref(self.plan),
                         C.byref(flags), C.byref(buf), out_ptr, gstride, dbg_ref, st)
         _lib.check(rc, f"illico_{test}_{M.fmt}_f32")
+
+
+def upload_dense(X: np.ndarray, device, gene_lb: int = 0, gene_ub: int | None = None) -> DeviceMatrix:
+    """Enqueues the copy of ``X[:, gene_lb:gene_ub]`` (any real dtype) into a float32 device matrix.
+    Asynchronous when ``X`` lives in pinned memory: the caller can keep working on the host meanwhile."""
+    device = require_cuda(device)
+    n, N = X.shape
+    gene_ub = N if gene_ub is None else gene_ub
+    view = X[:, gene_lb:gene_ub]
+    with torch.cuda.device(device):
+        t = torch.from_numpy(view) if isinstance(view, np.ndarray) else view
+        if t.dtype == torch.float32:
+            d = torch.empty((n, gene_ub - gene_lb), dtype=torch.float32, device=device)
+            d.copy_(t, non_blocking=True)
+        else:
+            d = _to_f32_exact(t.to(device))
+    return DeviceMatrix(DENSE, (n, gene_ub - gene_lb), d, gene_offset=gene_lb)
+
+
+def upload_sparse(X, fmt: str, device) -> DeviceMatrix:
+    device = require_cuda(device)
+    with torch.cuda.device(device):
+        data = torch.from_numpy(np.ascontiguousarray(X.data))
+        data = data.to(device, non_blocking=True)
+        data = data if data.dtype == torch.float32 else _to_f32_exact(data)
+        indices = torch.from_numpy(np.ascontiguousarray(X.indices, dtype=np.int32)).to(device, non_blocking=True)
+        indptr = torch.from_numpy(np.ascontiguousarray(X.indptr, dtype=np.int64)).to(device, non_blocking=True)
+    return DeviceMatrix(fmt, tuple(X.shape), data, indices, indptr)
 
 
 def _to_f32_exact(t: torch.Tensor) -> torch.Tensor:

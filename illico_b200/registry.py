@@ -13,7 +13,7 @@ from enum import Enum
 import numpy as np
 from scipy import sparse as py_sparse
 
-from .engine import CSC, CSR, DENSE, DeviceMatrix, Engine
+from .engine import CSC, CSR, DENSE, DeviceMatrix, Engine, upload_dense, upload_sparse
 
 
 class Test(Enum):
@@ -98,16 +98,18 @@ class InRAMDataHandler(DataHandler):
     def fetch(self, lb: int, ub: int) -> tuple:
         return self.data, (lb, ub)
 
-    def to_device(self, fetched, engine: Engine) -> DeviceMatrix:
+    def to_device(self, fetched, engine) -> DeviceMatrix:
+        """``engine`` may be an :class:`Engine` or just a device (the upload does not need the group plan,
+        so it can be started before the groups are encoded)."""
         if self._resident is None:
-            self._resident = self._upload(fetched, engine)
+            self._resident = self._upload(fetched, getattr(engine, "device", engine))
         return self._resident
 
 
 @data_handler_registry.register(np.ndarray)
 class DenseDataHandler(InRAMDataHandler):
-    def _upload(self, X, engine):
-        return engine.upload_dense(X)
+    def _upload(self, X, device):
+        return upload_dense(X, device)
 
     def kernel_data_format(self):
         return KernelDataFormat.DENSE
@@ -118,8 +120,8 @@ class DenseDataHandler(InRAMDataHandler):
 
 @data_handler_registry.register(py_sparse.csr_matrix)
 class CSRDataHandler(InRAMDataHandler):
-    def _upload(self, X, engine):
-        return engine.upload_sparse(X, CSR)
+    def _upload(self, X, device):
+        return upload_sparse(X, CSR, device)
 
     def kernel_data_format(self):
         return KernelDataFormat.CSR
@@ -130,8 +132,8 @@ class CSRDataHandler(InRAMDataHandler):
 
 @data_handler_registry.register(py_sparse.csc_matrix)
 class CSCDataHandler(InRAMDataHandler):
-    def _upload(self, X, engine):
-        return engine.upload_sparse(X, CSC)
+    def _upload(self, X, device):
+        return upload_sparse(X, CSC, device)
 
     def kernel_data_format(self):
         return KernelDataFormat.CSC
@@ -150,7 +152,7 @@ class BackedDenseDataHandler(DataHandler):
         return np.asarray(self.data[:, lb:ub]), (0, ub - lb)
 
     def to_device(self, fetched, engine):
-        return engine.upload_dense(fetched)
+        return upload_dense(fetched, getattr(engine, "device", engine))
 
     def kernel_data_format(self):
         return KernelDataFormat.DENSE
@@ -169,7 +171,7 @@ class BackedCSCDataHandler(DataHandler):
         return py_sparse.csc_matrix(self.data[:, lb:ub]), (0, ub - lb)
 
     def to_device(self, fetched, engine):
-        return engine.upload_sparse(fetched, CSC)
+        return upload_sparse(fetched, CSC, getattr(engine, "device", engine))
 
     def kernel_data_format(self):
         return KernelDataFormat.CSC
