@@ -239,3 +239,26 @@ def test_k562_shape_properties_and_oracle_sample():
         ref_row = int(np.searchsorted(groups, ref)) if ref is not None else None
         assert_parity((got[:, :, 0], got[:, :, 1], got[:, :, 2]), (p, Uo, fc), ref_row=ref_row, what=f"k562 ref={ref}")
     assert G == perts + 1
+
+
+def test_two_million_cells_csr_against_oracle():
+    """BASELINE config-5 column length (2 M cells, control + 1000 perturbations) on a handful of genes:
+    int64-sized tie terms (n0^3 ~ 6e18), ordered tie sums, multi-segment control."""
+    from scipy import sparse
+
+    from illico_b200 import asymptotic_wilcoxon, synth
+
+    n, N, perts = 2_000_000, 6, 1_000
+    rng = np.random.RandomState(31)
+    labels, _ = synth.perturbation_labels(rng, n, perts)
+    X = rng.poisson(1.0, size=(n, N)).astype(np.float32)
+    X[rng.rand(n, N) < 0.9] = 0
+    X[:, 5] = (rng.rand(n) < 0.1) * rng.gamma(2.0, 2.0, n).astype(np.float32)  # continuous non-zeros: path S
+    csr = sparse.csr_matrix(X)
+    groups = np.unique(np.asarray(labels))
+    for ref in (synth.CONTROL, None):
+        _, _, got = asymptotic_wilcoxon(FakeAnnData(csr, labels), is_log1p=False, group_keys="pert", reference=ref,
+                                        return_array=True)
+        g, p, U, fc = oracle.run(csr, labels, ref, n_threads=6, batch_size=1)
+        ref_row = int(np.searchsorted(groups, ref)) if ref is not None else None
+        assert_parity((got[:, :, 0], got[:, :, 1], got[:, :, 2]), (p, U, fc), ref_row=ref_row, what=f"2M cells ref={ref}")
