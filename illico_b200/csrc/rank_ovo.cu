@@ -75,6 +75,7 @@ __device__ __forceinline__ void finalize_group(const OvoParams& P, const RefInfo
                                                unsigned long long u2, unsigned long long tie_nz, double sum) {
     const long long n_t = P.plan.group_size[g];
     const long long z_t = n_t - m;
+    if (P.flags.group_sums) sum = P.flags.group_sums[(long long)g * P.n_genes + j];
     const long long Z = R.zeros + z_t;
     u2 += (unsigned long long)(z_t * (2ll * R.npos + R.zeros));
     const unsigned long long tie_exact = R.tie + tie_nz + (unsigned long long)cube_minus(Z);
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
         R.n_ref = pl.group_size[ref];
         R.zeros = R.n_ref - nref_nz;
         R.npos = nref_nz - upper_bound_u32(rA, nref_nz, KEY_ZERO);
-        R.sum = rsum;
+        R.sum = P.flags.group_sums ? P.flags.group_sums[(long long)ref * P.n_genes + j] : rsum;
         {
             unsigned long long t = 0;
             for (int i = tid; i < nref_nz; i += OVO_THREADS) {

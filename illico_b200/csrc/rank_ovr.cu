@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
             double sum = 0.0;
             long long nnz_g = 0;
             for (int s = pl.group_seg[g]; s < pl.group_seg[g + 1]; ++s) { R2 += seg_r2[s]; sum += seg_sum[s]; nnz_g += cnt[s]; }
+            if (P.flags.group_sums) sum = P.flags.group_sums[(long long)g * P.n_genes + j];
             const long long n_t = pl.group_size[g], n_r = n - n_t;
             R2 += (unsigned long long)(n_t - nnz_g) * r2_zero;
             const long long u2 = 2 * n_r * n_t + n_t * (n_t + 1) - (long long)R2;

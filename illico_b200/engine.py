@@ -35,6 +35,8 @@ class DeviceMatrix:
     indices: torch.Tensor | None = None   # int32 [nnz]
     indptr: torch.Tensor | None = None    # int64
     gene_offset: int = 0          # genes [gene_offset, gene_offset + shape[1]) of the caller's matrix
+    raw: torch.Tensor | None = None  # values float32 cannot hold exactly (float64 / big integers), as float64:
+    #                                  `data` is then unused and every batch is recoded (Engine._run_batch_wide)
 
     @property
     def ld(self) -> int:
@@ -129,6 +131,8 @@ class Engine:
             raise ValueError(f"matrix has {M.shape[0]} cells, groups describe {self.host_plan.n_cells}")
         if lb < 0 or ub > M.shape[1]:
             raise ValueError(f"Invalid chunk bounds: {(lb, ub)} for data with {M.shape[1]} columns.")
+        if M.raw is not None:
+            return self._run_batch_wide(M, lb, ub, flags, results, result_gene0, debug)
         self._ensure_buffers(b)
         G, Ntot = results.shape[0], results.shape[1]
         assert results.dtype == torch.float64 and results.is_contiguous() and G == self.n_groups
@@ -156,6 +160,34 @@ class Engine:
                         C.byref(flags), C.byref(buf), out_ptr, gstride, dbg_ref, st)
         _lib.check(rc, f"illico_{test}_{M.fmt}_f32")
 
+    def _run_batch_wide(self, M: DeviceMatrix, lb: int, ub: int, flags: _lib.Flags, results, result_gene0, debug):
+        """float64 / big-integer input: every sub-batch is recoded to order-preserving float32 codes (exact ranks,
+        U, ties, p) and the fold change uses float64 group sums computed from the original values."""
+        n = self.host_plan.n_cells
+        step = max(1, min(ub - lb, (1 << 28) // max(n, 1)))  # ~2 GB of float64 per sub-batch
+        enc = getattr(self, "_enc_dev", None)
+        if enc is None:
+            enc = self._enc_dev = torch.from_numpy(np.ascontiguousarray(self.grpc.encoded_groups)).to(self.device)
+        for a in range(lb, ub, step):
+            z = min(ub, a + step)
+            with torch.cuda.device(self.device):
+                Xb = _dense_block_f64(M, a, z)
+                fx = torch.expm1(Xb) if flags.is_log1p else Xb
+                sums = torch.zeros((self.n_groups, z - a), dtype=torch.float64, device=self.device).index_add_(0, enc, fx)
+                codes = recode_order_preserving(Xb)
+            sub = DeviceMatrix(DENSE, (n, z - a), codes)
+            f2 = _lib.Flags(flags.is_log1p, flags.use_continuity, flags.tie_correct, flags.alternative, flags.tie_order,
+                            0, sums.data_ptr())
+            dbg = {} if debug is not None else None
+            self.run_batch(sub, 0, z - a, f2, results, result_gene0 + (a - lb), dbg)
+            if debug is not None:
+                for k, v in dbg.items():
+                    debug.setdefault("_parts", {}).setdefault(k, []).append(v)
+            torch.cuda.current_stream(self.device).synchronize()  # sums/codes must outlive the kernels
+        if debug is not None and "_parts" in debug:
+            for k, parts in debug.pop("_parts").items():
+                debug[k] = torch.cat(parts, dim=-1)
+
 
 def upload_dense(X: np.ndarray, device, gene_lb: int = 0, gene_ub: int | None = None) -> DeviceMatrix:
     """Enqueues the copy of ``X[:, gene_lb:gene_ub]`` (any real dtype) into a float32 device matrix.
@@ -166,12 +198,13 @@ def upload_dense(X: np.ndarray, device, gene_lb: int = 0, gene_ub: int | None = 
     view = X[:, gene_lb:gene_ub]
     with torch.cuda.device(device):
         t = torch.from_numpy(view) if isinstance(view, np.ndarray) else view
+        raw = None
         if t.dtype == torch.float32:
             d = torch.empty((n, gene_ub - gene_lb), dtype=torch.float32, device=device)
             d.copy_(t, non_blocking=True)
         else:
-            d = _to_f32_exact(t.to(device))
-    return DeviceMatrix(DENSE, (n, gene_ub - gene_lb), d, gene_offset=gene_lb)
+            d, raw = _to_f32_or_wide(t.to(device))
+    return DeviceMatrix(DENSE, (n, gene_ub - gene_lb), d, gene_offset=gene_lb, raw=raw)
 
 
 def upload_sparse(X, fmt: str, device) -> DeviceMatrix:
@@ -179,20 +212,60 @@ def upload_sparse(X, fmt: str, device) -> DeviceMatrix:
     with torch.cuda.device(device):
         data = torch.from_numpy(np.ascontiguousarray(X.data))
         data = data.to(device, non_blocking=True)
-        data = data if data.dtype == torch.float32 else _to_f32_exact(data)
+        raw = None
+        if data.dtype != torch.float32:
+            data, raw = _to_f32_or_wide(data)
         indices = torch.from_numpy(np.ascontiguousarray(X.indices, dtype=np.int32)).to(device, non_blocking=True)
         indptr = torch.from_numpy(np.ascontiguousarray(X.indptr, dtype=np.int64)).to(device, non_blocking=True)
-    return DeviceMatrix(fmt, tuple(X.shape), data, indices, indptr)
+    return DeviceMatrix(fmt, tuple(X.shape), data, indices, indptr, raw=raw)
 
 
-def _to_f32_exact(t: torch.Tensor) -> torch.Tensor:
-    """Converts a device tensor to float32, refusing to create ties that are not in the data."""
+def _dense_block_f64(M: DeviceMatrix, lb: int, ub: int) -> torch.Tensor:
+    """Genes [lb, ub) of a wide matrix as a dense float64 block [n, ub - lb] on the device."""
+    if M.fmt == DENSE:
+        return M.raw[:, lb:ub].contiguous()
+    n = M.shape[0]
+    if M.fmt == CSC:
+        lo, hi = int(M.indptr[lb]), int(M.indptr[ub])
+        ptr = (M.indptr[lb:ub + 1] - lo)
+        t = torch.sparse_csc_tensor(ptr, M.indices[lo:hi].to(torch.int64), M.raw[lo:hi], size=(n, ub - lb))
+        return t.to_dense()
+    # CSR: rows x all genes -> dense columns of the batch
+    cols = M.indices.to(torch.int64)
+    sel = (cols >= lb) & (cols < ub)
+    rows = torch.repeat_interleave(torch.arange(n, device=cols.device), M.indptr[1:] - M.indptr[:-1])
+    out = torch.zeros((n, ub - lb), dtype=torch.float64, device=cols.device)
+    out[rows[sel], cols[sel] - lb] = M.raw[sel]
+    return out
+
+
+def _to_f32_or_wide(t: torch.Tensor):
+    """``(float32 tensor, None)`` when float32 holds every value exactly, else ``(None, float64 tensor)``.
+    Never rounds: rounding would create ties that are not in the data."""
     f = t.to(torch.float32)
-    if not bool((f.to(t.dtype) == t).all()):
-        raise NotImplementedError(
-            f"values of dtype {t.dtype} are not exactly representable in float32; the CUDA path ranks float32 keys "
-            "(64-bit keys are not implemented yet)")
-    return f
+    if bool((f.to(t.dtype) == t).all()):
+        return f, None
+    return None, t.to(torch.float64)
+
+
+def recode_order_preserving(Xb: torch.Tensor) -> torch.Tensor:
+    """Per column, replaces float64 values by small integers (as float32) with the same order, the same ties,
+    zero -> 0, negatives < 0 < positives.  Ranks, U and tie sums only depend on that, so the float32 kernels
+    stay exact for wider input types.  Plumbing (torch sort/scan), used only for such inputs."""
+    n = Xb.shape[0]
+    if n >= (1 << 24):
+        raise NotImplementedError("more than 2^24 cells with values float32 cannot hold")
+    s, idx = torch.sort(Xb, dim=0)
+    d = torch.zeros(s.shape, dtype=torch.int32, device=Xb.device)
+    d[1:] = (s[1:] != s[:-1]).to(torch.int32)
+    r = torch.cumsum(d, dim=0)
+    big = int(n) + 2
+    r0 = torch.where(s >= 0, r, torch.full_like(r, big)).min(dim=0).values
+    has_zero = (s == 0).any(dim=0)
+    code = (r - r0) + ((s > 0) & ~has_zero).to(r.dtype)
+    out = torch.empty(s.shape, dtype=torch.float32, device=Xb.device)
+    out.scatter_(0, idx, code.to(torch.float32))
+    return out
 
 
 def make_flags(is_log1p: bool, use_continuity: bool, tie_correct: bool, alternative: str, fmt: str) -> _lib.Flags:

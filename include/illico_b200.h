@@ -90,6 +90,11 @@ typedef struct illico_flags {
     int32_t tie_correct;    /* 0 -> tie sum := 0 in the p-value (ovr/dense_ovr.py:70) */
     int32_t alternative;    /* enum illico_alternative */
     int32_t tie_order;      /* enum illico_tie_order */
+    int32_t reserved;
+    /* Optional [n_groups, n_genes_batch] float64 expression sums (device).  When set, the fold change uses them
+     * instead of sums of the staged values: the host stages ORDER-PRESERVING float32 codes of values that
+     * float32 cannot hold (float64 / large integers), which keeps U, ties and p exact. */
+    const double* group_sums;
 } illico_flags_t;
 
 /* Optional per-test debug outputs for bit-exact parity checks (any pointer may be NULL). */

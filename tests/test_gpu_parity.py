@@ -37,9 +37,6 @@ def _run(X, labels, reference, **kw):
     return groups, planes(df, len(groups), X.shape[1])
 
 
-F64_CASES = {"log1p64"}
-
-
 @pytest.mark.parametrize("name", list(C.CASES))
 def test_cuda_matches_reference_golden(golden_dir, name):
     builder, grid, batch_size = C.CASES[name]
@@ -49,11 +46,6 @@ def test_cuda_matches_reference_golden(golden_dir, name):
     for fmt, test, cc, tc, alt, log1p in grid:
         ref = reference if test == "ovo" else None
         kw = dict(is_log1p=log1p, batch_size=batch_size, alternative=alt, use_continuity=cc, tie_correct=tc)
-        if name in F64_CASES:
-            # float64 values that float32 cannot hold need 64-bit keys: not implemented, must fail loudly
-            with pytest.raises(NotImplementedError):
-                _run(C.to_format(X, fmt), labels, ref, **kw)
-            continue
         g, got = _run(C.to_format(X, fmt), labels, ref, **kw)
         assert list(g) == list(groups)
         want = gold[C.combo_key(fmt, test, cc, tc, alt, log1p)]
@@ -262,3 +254,23 @@ def test_two_million_cells_csr_against_oracle():
         g, p, U, fc = oracle.run(csr, labels, ref, n_threads=6, batch_size=1)
         ref_row = int(np.searchsorted(groups, ref)) if ref is not None else None
         assert_parity((got[:, :, 0], got[:, :, 1], got[:, :, 2]), (p, U, fc), ref_row=ref_row, what=f"2M cells ref={ref}")
+
+
+@pytest.mark.parametrize("fmt", ["dense", "csr", "csc"])
+@pytest.mark.parametrize("test", ["ovr", "ovo"])
+def test_float64_and_integer_inputs(fmt, test):
+    """Values float32 cannot hold (float64 noise, large integers) are ranked exactly through order-preserving
+    recoding; dtypes that float32 holds exactly (int32 counts) take the normal path."""
+    X, labels, reference = C.CASES["conftest"][0]()
+    ref = reference if test == "ovo" else None
+    rng = np.random.RandomState(8)
+    noise = rng.rand(*X.shape) * 1e-9                      # differences far below float32 resolution
+    X64 = np.where(X > 0, X.astype(np.float64) + noise, 0.0)
+    X64[:, 3] = np.where(X[:, 3] > 0, X[:, 3].astype(np.float64) + 2.0**40, 0.0)  # big integers
+    Xi = X.astype(np.int32)
+    for arr in (X64, Xi):
+        Xf = C.to_format(arr, fmt)
+        groups, got = _run(Xf, labels, ref, is_log1p=False, batch_size=4)
+        g, p, U, fc = oracle.run(Xf, labels, ref)
+        ref_row = int(np.searchsorted(groups, ref)) if ref is not None else None
+        assert_parity(got, (p, U, fc), ref_row=ref_row, what=f"{arr.dtype}:{fmt}:{test}")
