@@ -251,9 +251,9 @@ def main():
                 rc = lib.illico_stage_dense_f32(M.data.data_ptr(), M.ld, lb, b, C.byref(eng.plan), eng._ir_vals.data_ptr(),
                                                 eng._ir_cnt.data_ptr(), st)
             else:
-                lib.illico_zero_counts(eng._ir_cnt.data_ptr(), b, C.byref(eng.plan), st)
                 rc = lib.illico_stage_csr_f32(M.data.data_ptr(), M.indices.data_ptr(), M.indptr.data_ptr(), lb, b,
-                                              C.byref(eng.plan), eng._ir_vals.data_ptr(), eng._ir_cnt.data_ptr(), st)
+                                              C.byref(eng.plan), eng._ir_vals.data_ptr(), eng._ir_cnt.data_ptr(),
+                                              eng._ws.data_ptr(), eng._ws.numel(), st)
             _lib.check(rc, "stage")
             ev[1].record()
             fn = lib.illico_rank_ovo if test == "ovo" else lib.illico_rank_ovr

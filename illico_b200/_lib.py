@@ -57,7 +57,8 @@ SIGNATURES = {
     "illico_last_error": (C.c_char_p, []),
     "illico_launch_count": (_i64, []),
     "illico_stage_dense_f32": (C.c_int, [_vp, _i64, _i32, _i32, _PP, _vp, _vp, _vp]),
-    "illico_stage_csr_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _PP, _vp, _vp, _vp]),
+    "illico_stage_csr_workspace_bytes": (_sz, [_PP, _i32]),
+    "illico_stage_csr_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _PP, _vp, _vp, _vp, _sz, _vp]),
     "illico_stage_csc_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _PP, _vp, _vp, _vp]),
     "illico_zero_counts": (C.c_int, [_vp, _i32, _PP, _vp]),
     "illico_check_csr_sorted": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),

@@ -22,7 +22,8 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // kernels' host launchers (stage.cu, rank_ovr.cu, rank_ovo.cu)
 int launch_stage_dense(const float*, long long, int, int, const illico_plan_t*, float*, uint32_t*, cudaStream_t);
 int launch_stage_csr(const float*, const int32_t*, const long long*, int, int, const illico_plan_t*, float*, uint32_t*,
-                     cudaStream_t);
+                     void*, size_t, cudaStream_t);
+size_t stage_csr_workspace_bytes(const illico_plan_t*, int);
 int launch_stage_csc(const float*, const int32_t*, const long long*, int, int, const illico_plan_t*, float*, uint32_t*,
                      cudaStream_t);
 int launch_check_csr_sorted(const int32_t*, const long long*, long long, int*, int*, cudaStream_t);
@@ -77,12 +78,18 @@ int illico_zero_counts(uint32_t* ir_cnt, int32_t n_genes_batch, const illico_pla
     return 0;
 }
 
+size_t illico_stage_csr_workspace_bytes(const illico_plan_t* plan, int32_t n_genes_batch) {
+    if (check_plan(plan)) return 0;
+    return stage_csr_workspace_bytes(plan, n_genes_batch);
+}
+
 int illico_stage_csr_f32(const float* data, const int32_t* indices, const int64_t* indptr, int32_t gene_lb,
-                         int32_t n_genes_batch, const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, void* stream) {
+                         int32_t n_genes_batch, const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt,
+                         void* workspace, size_t workspace_bytes, void* stream) {
     if (check_plan(plan)) return 1;
     if (!indptr || !ir_vals || !ir_cnt) { set_error("illico_stage_csr_f32: NULL buffer"); return 1; }
     return launch_stage_csr(data, indices, (const long long*)indptr, gene_lb, n_genes_batch, plan, ir_vals, ir_cnt,
-                            (cudaStream_t)stream);
+                            workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int illico_stage_csc_f32(const float* data, const int32_t* indices, const int64_t* indptr, int32_t gene_lb,
@@ -105,7 +112,9 @@ size_t illico_rank_workspace_bytes(const illico_plan_t* plan, int32_t n_genes_ba
     if ((size_t)n_genes_batch < ctas) ctas = (size_t)(n_genes_batch > 0 ? n_genes_batch : 1);
     size_t per_cta = plan->ref_group >= 0 ? 4 * (size_t)plan->max_group_size * sizeof(uint32_t)
                                           : ovr_slab_qwords(plan) * 8;
-    return ctas * per_cta + 256;
+    size_t rank = ctas * per_cta + 256;
+    size_t stage = stage_csr_workspace_bytes(plan, n_genes_batch);  // CSR staging reuses the same scratch
+    return rank > stage ? rank : stage;
 }
 
 int illico_rank_ovr(const float* ir_vals, const uint32_t* ir_cnt, int32_t n_genes_batch, const illico_plan_t* plan,
@@ -155,8 +164,8 @@ int illico_ovr_csr_f32(const float* data, const int32_t* indices, const int64_t*
                        const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf,
                        double* results, int64_t gstride, const illico_debug_t* dbg, void* stream) {
     ILLICO_CHECK_BUF(buf);
-    if (illico_zero_counts(buf->ir_cnt, nb, plan, stream)) return 1;
-    if (illico_stage_csr_f32(data, indices, indptr, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
+    if (illico_stage_csr_f32(data, indices, indptr, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, buf->workspace,
+                             buf->workspace_bytes, stream)) return 1;
     return illico_rank_ovr(buf->ir_vals, buf->ir_cnt, nb, plan, flags, results, gstride, buf->workspace,
                            buf->workspace_bytes, dbg, stream);
 }
@@ -164,8 +173,8 @@ int illico_ovo_csr_f32(const float* data, const int32_t* indices, const int64_t*
                        const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf,
                        double* results, int64_t gstride, const illico_debug_t* dbg, void* stream) {
     ILLICO_CHECK_BUF(buf);
-    if (illico_zero_counts(buf->ir_cnt, nb, plan, stream)) return 1;
-    if (illico_stage_csr_f32(data, indices, indptr, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
+    if (illico_stage_csr_f32(data, indices, indptr, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, buf->workspace,
+                             buf->workspace_bytes, stream)) return 1;
     return illico_rank_ovo(buf->ir_vals, buf->ir_cnt, nb, plan, flags, results, gstride, buf->workspace,
                            buf->workspace_bytes, dbg, stream);
 }

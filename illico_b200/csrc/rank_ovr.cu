@@ -28,6 +28,9 @@ constexpr int OVR_NW = OVR_THREADS / 32;
 constexpr int HASH_CAP = 4096;
 constexpr int MAX_DISTINCT = 2048;
 constexpr uint32_t HASH_EMPTY = 0u;
+constexpr int T_SLOTS = 16;   // path T: slots of the small value table (also the bins of a segment histogram)
+constexpr int T_CAP = 11;     // path T: most distinct values it takes
+constexpr int T_WORDS = T_SLOTS / 2;  // two 16-bit bins per 32-bit word
 
 struct OvrParams {
     const float* ir_vals;
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
     double* seg_sum = (double*)(slab + S);                   // [S]
     uint32_t* gsortA = (uint32_t*)(slab + 2ll * S);          // [n_cells]
     uint32_t* gsortB = gsortA + ((n + 1) & ~1ll);            // [n_cells]
+    uint16_t* seg_bins = (uint16_t*)(gsortB + ((n + 1) & ~1ll));  // [S][T_SLOTS] path T segment histograms
 
     const double cc = P.flags.use_continuity ? 0.5 : 0.0;
 
@@ -105,6 +109,145 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
         const uint32_t* cnt = P.ir_cnt + (long long)j * S;
         const float* vals = P.ir_vals + (long long)j * pl.slot_cap;
 
+        // ================= path T: a handful of distinct values (raw counts) =================
+        // ONE pass over the staged values: every thread owns a segment at a time, looks each value up in a tiny
+        // shared table (inserting unseen values) and bumps a private histogram bin; the segment histograms go to
+        // the slab.  Once the table is complete its <= 16 values are sorted, turned into doubled mid-ranks, and
+        // every segment's rank sum is a 32-term dot product -- the values are never touched again.
+        bool path_t = false;
+        long long nnz = 0, n0 = 0, n_neg = 0;
+        unsigned long long tie_nz_exact = 0;
+        bool path_s = false;
+        const uint32_t* sk = nullptr;  // sorted keys (path S)
+        {
+            uint32_t* bins = smem;                                      // [T_WORDS][OVR_THREADS] private histograms, 2 bins/word
+            uint32_t* tkey = hist;                                      // [T_SLOTS] raw float bits, 0 = empty
+            uint32_t* gcount = hist + T_SLOTS;                          // [T_SLOTS] multiplicity in the whole column
+            uint32_t* r2slot = hist + 2 * T_SLOTS;                      // [T_SLOTS] doubled mid-rank of the slot's value
+            double* fcslot = reinterpret_cast<double*>(hist + 4 * T_SLOTS);  // [T_SLOTS] f(x) of the slot's value
+            uint32_t* skey = hist + 8 * T_SLOTS;                        // [T_SLOTS] finalize scratch: sorted keys
+            uint32_t* sslot = hist + 9 * T_SLOTS;                       // [T_SLOTS] ... and their slots
+            if (tid < T_SLOTS) { tkey[tid] = 0u; gcount[tid] = 0u; }
+            if (tid < 8) sc[tid] = 0;  // [0] distinct [1] overflow
+            __syncthreads();
+            unsigned long long my_nnz = 0;
+            for (int s = tid; s < S; s += OVR_THREADS) {
+                if (*(volatile int*)&sc[1]) break;
+#pragma unroll
+                for (int q = 0; q < T_WORDS; ++q) bins[q * OVR_THREADS + tid] = 0u;
+                const int c = (int)cnt[s];
+                my_nnz += c;
+                const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);
+                float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+                bool ok = true;
+                for (int i = 0; i < c && ok; i += 4) {
+                    const float4 q4 = nxt;
+                    if (i + 4 < c) nxt = src4[(i >> 2) + 1];
+                    const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (i + e < c && ok) {
+                            const uint32_t bits = __float_as_uint(q[e]);
+                            uint32_t h = (bits * 2654435761u) >> 28;
+                            int probes = 0;
+                            for (;;) {
+                                uint32_t kk = *(volatile uint32_t*)&tkey[h];
+                                if (kk == 0u) {
+                                    kk = atomicCAS(&tkey[h], 0u, bits);
+                                    if (kk == 0u) {
+                                        if (atomicAdd(&sc[0], 1) >= T_CAP) { sc[1] = 1; ok = false; }
+                                        break;
+                                    }
+                                }
+                                if (kk == bits) break;
+                                h = (h + 1) & (T_SLOTS - 1);
+                                if (++probes > T_SLOTS) { sc[1] = 1; ok = false; break; }
+                            }
+                            if (ok) bins[(h >> 1) * OVR_THREADS + tid] += 1u << ((h & 1u) << 4);
+                        }
+                    }
+                }
+                if (!ok) break;
+                uint32_t* dst = reinterpret_cast<uint32_t*>(seg_bins + (long long)s * T_SLOTS);
+#pragma unroll 2
+                for (int q = 0; q < T_WORDS; ++q) {
+                    const uint32_t w2 = bins[q * OVR_THREADS + tid];
+                    dst[q] = w2;
+                    if (w2 & 0xffffu) atomicAdd(&gcount[2 * q], w2 & 0xffffu);
+                    if (w2 >> 16) atomicAdd(&gcount[2 * q + 1], w2 >> 16);
+                }
+            }
+            const long long nnz_t = (long long)block_sum<unsigned long long>(my_nnz, redu);  // syncs
+            path_t = sc[1] == 0;
+            __syncthreads();
+            if (path_t) {
+                nnz = nnz_t;
+                n0 = n - nnz;
+                if (tid == 0) {
+                    int D = 0;
+                    for (int q = 0; q < T_SLOTS; ++q)
+                        if (tkey[q] != 0u) {  // insertion sort by order-preserving key
+                            const uint32_t k = f2key(__uint_as_float(tkey[q]));
+                            int a = D - 1;
+                            while (a >= 0 && skey[a] > k) { skey[a + 1] = skey[a]; sslot[a + 1] = sslot[a]; --a; }
+                            skey[a + 1] = k; sslot[a + 1] = (uint32_t)q;
+                            ++D;
+                        }
+                    unsigned long long lo = 0, t_exact = 0, negs = 0;
+                    for (int a = 0; a < D; ++a) {
+                        const uint32_t q = sslot[a], cq = gcount[q];
+                        unsigned long long r2 = 2ull * lo + cq + 1ull;   // lo + hi + 1 with hi = lo + cq
+                        if (skey[a] > KEY_ZERO) r2 += 2ull * (unsigned long long)n0;
+                        r2slot[q] = (uint32_t)r2;
+                        fcslot[q] = fc_value(__uint_as_float(tkey[q]), P.flags.is_log1p);
+                        t_exact += (unsigned long long)cube_minus((long long)cq);
+                        if (skey[a] < KEY_ZERO) negs += cq;
+                        lo += cq;
+                    }
+                    for (int q = 0; q < T_SLOTS; ++q) if (tkey[q] == 0u) { r2slot[q] = 0u; fcslot[q] = 0.0; }
+                    const unsigned long long zterm = (unsigned long long)cube_minus(n0);
+                    const bool sparse_order = P.flags.tie_order == ILLICO_TIES_SPARSE;
+                    const bool need_walk = sparse_order ? ((double)t_exact >= TWO53) : ((double)t_exact + (double)zterm >= TWO53);
+                    double acc;
+                    if (!need_walk) {
+                        acc = sparse_order ? (double)t_exact : (double)(t_exact + zterm);
+                    } else {
+                        acc = 0.0;
+                        bool zero_done = sparse_order || n0 == 0;
+                        for (int a = 0; a < D; ++a) {
+                            if (!zero_done && skey[a] > KEY_ZERO) { acc += (double)(long long)zterm; zero_done = true; }
+                            acc += (double)cube_minus((long long)gcount[sslot[a]]);
+                        }
+                        if (!zero_done) acc += (double)(long long)zterm;
+                    }
+                    if (sparse_order) acc = __dadd_rn(acc, zero_block_term_f64(n0));
+                    *tie_slot = acc;
+                    redu[0] = t_exact;
+                    redu[1] = negs;
+                }
+                __syncthreads();
+                tie_nz_exact = redu[0];
+                n_neg = (long long)redu[1];
+                // ---- every segment's doubled rank sum and expression sum from its histogram
+                for (int s = tid; s < S; s += OVR_THREADS) {
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(seg_bins + (long long)s * T_SLOTS);
+                    unsigned long long acc = 0;
+                    double sum = 0.0;
+#pragma unroll 2
+                    for (int q = 0; q < T_WORDS; ++q) {
+                        const uint32_t w2 = src[q];
+                        if (w2 == 0u) continue;
+                        const uint32_t b0 = w2 & 0xffffu, b1 = w2 >> 16;
+                        acc += (unsigned long long)b0 * r2slot[2 * q] + (unsigned long long)b1 * r2slot[2 * q + 1];
+                        sum += (double)b0 * fcslot[2 * q] + (double)b1 * fcslot[2 * q + 1];
+                    }
+                    seg_r2[s] = acc;
+                    seg_sum[s] = sum;
+                }
+                __syncthreads();
+            }
+        }
+        if (!path_t) {
         // ================= phase A: value -> multiplicity hash (path H attempt) =================
         for (int i = tid; i < 2 * HASH_CAP; i += OVR_THREADS) smem[i] = 0;
         if (tid < 8) sc[tid] = 0;  // [0] ndist [1] overflow [2] cursor [3] dn
@@ -135,12 +278,9 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
                 }
             }
         }
-        const long long nnz = (long long)block_sum<unsigned long long>(my_nnz, redu);  // syncs
-        const long long n0 = n - nnz;
-        const bool path_s = sc[1] != 0 || sc[0] > MAX_DISTINCT;
-        long long n_neg = 0;
-        unsigned long long tie_nz_exact = 0;
-        const uint32_t* sk = nullptr;  // sorted keys (path S)
+        nnz = (long long)block_sum<unsigned long long>(my_nnz, redu);  // syncs
+        n0 = n - nnz;
+        path_s = sc[1] != 0 || sc[0] > MAX_DISTINCT;
         __syncthreads();
 
         if (!path_s) {
@@ -258,11 +398,12 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
             }
             __syncthreads();
         }
+        }  // !path_t
         const double tie = *tie_slot;
         const unsigned long long r2_zero = 2ull * (unsigned long long)n_neg + (unsigned long long)n0 + 1ull;
 
         // ================= phase B: per-segment doubled rank sums and expression sums =================
-        for (int s = tid; s < S; s += OVR_THREADS) {
+        for (int s = tid; s < S && !path_t; s += OVR_THREADS) {
             const int c = (int)cnt[s];
             const float* src = vals + pl.seg_base[s];
             unsigned long long acc = 0;
@@ -332,7 +473,8 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
 }
 
 size_t ovr_slab_qwords(const illico_plan_t* plan) {
-    return 2 * (size_t)plan->n_segments + (size_t)((plan->n_cells + 1) & ~1) + 2;
+    return 2 * (size_t)plan->n_segments + (size_t)((plan->n_cells + 1) & ~1) + 2 +
+           (size_t)plan->n_segments * T_SLOTS * 2 / 8 + 2;
 }
 
 int launch_ovr(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const illico_plan_t* plan,

@@ -144,35 +144,169 @@ __device__ __forceinline__ long long lower_bound_i32(const int32_t* a, long long
     return lo;
 }
 
-// CSR: one warp per cell (row).  The row's sorted gene indices are narrowed to the batch by binary search
-// (as illico/utils/sparse/csr.py:171,226 does) and every stored value claims the next free place of its
-// (gene, segment) slot with one atomic.  The order inside a slot is therefore arbitrary; ranks, U and tie
-// sums do not depend on it.
-__global__ void __launch_bounds__(256) stage_csr_kernel(const float* __restrict__ data, const int32_t* __restrict__ indices,
-                                                        const long long* __restrict__ indptr, int gene_lb, int b,
-                                                        const illico_plan_t pl, float* __restrict__ ir_vals,
-                                                        uint32_t* __restrict__ ir_cnt) {
+// ---- CSR ----------------------------------------------------------------------------------------------
+// Pass 1 (csr_split_kernel): for every cell row, the position of each gene-range boundary of the batch inside the
+// row's sorted indices (binary search, as illico/utils/sparse/csr.py:171,226 does for the batch bounds).
+// Pass 2 (stage_csr_kernel): a CTA owns (a few segments) x (one range of CSR_GC genes).  It counting-sorts the
+// tile's stored values by gene in shared memory and writes every (gene, segment) run with aligned, padded
+// 32-byte sectors -- no global atomics and no partial-sector writes (which cost one DRAM fill each).  The order
+// inside a slot is arbitrary (shared-memory cursor atomics); ranks, U and tie sums do not depend on it.
+constexpr int CSR_GC = 512;        // genes per range
+constexpr int CSR_CAP = 8192;      // values per shared tile pass
+constexpr int CSR_THREADS = 256;
+constexpr int CSR_MAX_SEGS = 16;
+
+__global__ void __launch_bounds__(256) csr_split_kernel(const int32_t* __restrict__ indices, const long long* __restrict__ indptr,
+                                                        int n_rows, int gene_lb, int b, int K, int32_t* __restrict__ split) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int S = pl.n_segments;
-    // Cells are visited in group order (perm) so that the values of one (gene, segment) slot are written
-    // close together in time and merge into full sectors in L2 instead of one DRAM read-modify-write each.
-    for (long long p = warp; p < pl.n_cells; p += nwarps) {
-        const long long r = pl.perm[p];
-        const long long start = indptr[r], end = indptr[r + 1];
-        if (end <= start) continue;
-        const int s = pl.cell_seg[r];
-        const int base = pl.seg_base[s], cap = pl.seg_base[s + 1] - base;
-        const long long lo = start + lower_bound_i32(indices + start, end - start, gene_lb);
-        const long long hi = start + lower_bound_i32(indices + start, end - start, gene_lb + b);
-        for (long long k = lo + lane; k < hi; k += 32) {
-            const float v = __ldcs(data + k);
-            if (v == 0.0f) continue;  // explicitly stored zeros are zeros
-            const int j = indices[k] - gene_lb;
-            const uint32_t slot = atomicAdd(&ir_cnt[(long long)j * S + s], 1u);
-            if (slot < (uint32_t)cap) ir_vals[(long long)j * pl.slot_cap + base + slot] = v;
+    for (long long r = warp; r < n_rows; r += nwarps) {
+        const long long start = indptr[r], len = indptr[r + 1] - start;
+        for (int k = lane; k <= K; k += 32) {
+            const int bound = gene_lb + min(k * CSR_GC, b);
+            split[r * (K + 1) + k] = (int32_t)lower_bound_i32(indices + start, len, bound);
         }
+    }
+}
+
+constexpr int CSR_MAX_ROWS = 1024;  // cells per segment this kernel accepts (the plan cuts groups at 512)
+
+__global__ void __launch_bounds__(CSR_THREADS) stage_csr_kernel(const float* __restrict__ data, const int32_t* __restrict__ indices,
+                                                                const long long* __restrict__ indptr, int gene_lb, int b, int K,
+                                                                const int32_t* __restrict__ split, const illico_plan_t pl,
+                                                                float* __restrict__ ir_vals, uint32_t* __restrict__ ir_cnt,
+                                                                int segs_per_cta) {
+    extern __shared__ __align__(16) unsigned char csr_smem[];
+    long long* row_a = reinterpret_cast<long long*>(csr_smem);             // [CSR_MAX_ROWS] first stored element of each row in the range
+    float* vals = reinterpret_cast<float*>(row_a + CSR_MAX_ROWS);          // [CSR_CAP]
+    uint32_t* hist = reinterpret_cast<uint32_t*>(vals + CSR_CAP);          // [CSR_GC] per-gene count, then scatter cursor
+    uint32_t* offs = hist + CSR_GC;                                        // [CSR_GC + 1] exclusive prefix of the counts
+    int* row_n = reinterpret_cast<int*>(offs + CSR_GC + 1);                // [CSR_MAX_ROWS] stored elements per row in the range
+    uint32_t* wsum = reinterpret_cast<uint32_t*>(row_n + CSR_MAX_ROWS);    // [8]
+    int* chunk_end_p = reinterpret_cast<int*>(wsum + 8);                   // [1]
+    uint16_t (*done)[CSR_GC] = reinterpret_cast<uint16_t (*)[CSR_GC]>(chunk_end_p + 1);  // [CSR_MAX_SEGS][CSR_GC] values written
+    int& chunk_end = *chunk_end_p;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    constexpr int NW = CSR_THREADS / 32;
+    const int k = blockIdx.x;                          // gene range
+    const int g0 = k * CSR_GC;                         // first gene of the range inside the batch
+    const int ng = min(CSR_GC, b - g0);
+    const int S = pl.n_segments;
+    const int s_begin = blockIdx.y * segs_per_cta, s_end = min(S, s_begin + segs_per_cta);
+    for (int s = s_begin; s < s_end; ++s) {
+        const int ls = s - s_begin;
+        __syncthreads();
+        for (int g = t; g < CSR_GC; g += CSR_THREADS) done[ls][g] = 0;
+      // segments longer than the row table are walked in blocks of CSR_MAX_ROWS cells (the plan cuts at 512)
+      for (int pb = pl.seg_pos[s]; pb < pl.seg_pos[s + 1]; pb += CSR_MAX_ROWS) {
+        const int p0 = pb, nrows = min(CSR_MAX_ROWS, pl.seg_pos[s + 1] - pb);
+        __syncthreads();
+        uint32_t mine = 0;
+        for (int i = t; i < nrows; i += CSR_THREADS) {
+            const long long r = pl.perm[p0 + i];
+            const int a = split[r * (K + 1) + k], z = split[r * (K + 1) + k + 1];
+            row_a[i] = indptr[r] + a;
+            row_n[i] = z - a;
+            mine += (uint32_t)(z - a);
+        }
+        // total stored values of the tile: the whole segment goes in one pass when it fits (the usual case)
+        mine = warp_sum<uint32_t>(mine);
+        if (lane == 0) wsum[w] = mine;
+        __syncthreads();
+        uint32_t tile_total = 0;
+        for (int ww = 0; ww < NW; ++ww) tile_total += wsum[ww];
+        int rc = 0;                                    // first row of the current pass
+        while (rc < nrows) {
+            __syncthreads();
+            if (t == 0) {
+                int e = nrows;
+                if (tile_total > CSR_CAP) {
+                    int tot = 0;
+                    e = rc;
+                    while (e < nrows && (tot + row_n[e] <= CSR_CAP || e == rc)) { tot += row_n[e]; ++e; }
+                }
+                chunk_end = e;
+            }
+            for (int g = t; g < CSR_GC; g += CSR_THREADS) hist[g] = 0;
+            __syncthreads();
+            const int re = chunk_end;
+            // ---- count per gene
+            for (int i = rc + w; i < re; i += NW) {
+                const long long a = row_a[i], z = a + row_n[i];
+                for (long long e = a + lane; e < z; e += 32)
+                    if (data[e] != 0.0f) atomicAdd(&hist[indices[e] - gene_lb - g0], 1u);
+            }
+            __syncthreads();
+            // ---- exclusive scan of hist[0..CSR_GC) (2 entries per thread)
+            {
+                const uint32_t c0 = hist[2 * t], c1 = hist[2 * t + 1];
+                const uint32_t incl = warp_incl_scan(c0 + c1, lane);
+                if (lane == 31) wsum[w] = incl;
+                __syncthreads();
+                uint32_t basev = incl - (c0 + c1);
+                for (int ww = 0; ww < w; ++ww) basev += wsum[ww];
+                offs[2 * t] = basev;
+                offs[2 * t + 1] = basev + c0;
+                if (t == CSR_THREADS - 1) offs[CSR_GC] = basev + c0 + c1;
+                hist[2 * t] = basev;                   // cursors start at the offsets
+                hist[2 * t + 1] = basev + c0;
+            }
+            __syncthreads();
+            if (offs[CSR_GC] <= CSR_CAP) {
+                // ---- scatter the values by gene into the shared tile
+                for (int i = rc + w; i < re; i += NW) {
+                    const long long a = row_a[i], z = a + row_n[i];
+                    for (long long e = a + lane; e < z; e += 32) {
+                        const float v = data[e];
+                        if (v != 0.0f) vals[atomicAdd(&hist[indices[e] - gene_lb - g0], 1u)] = v;
+                    }
+                }
+                __syncthreads();
+                // ---- write every gene's run: aligned padded sectors while the slot start is sector aligned
+                for (int g = t; g < ng; g += CSR_THREADS) {
+                    const uint32_t o = offs[g], c = offs[g + 1] - o;
+                    if (c == 0) continue;
+                    const uint32_t prior = done[ls][g];
+                    float* dst = ir_vals + (long long)(g0 + g) * pl.slot_cap + pl.seg_base[s] + prior;
+                    if ((prior & 7u) == 0u) {
+                        for (uint32_t i = 0; i < c; i += 8) {
+                            float q[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) q[u] = vals[min(o + i + u, (uint32_t)CSR_CAP - 1)];
+                            __stcs(reinterpret_cast<float4*>(dst + i), make_float4(q[0], q[1], q[2], q[3]));
+                            __stcs(reinterpret_cast<float4*>(dst + i) + 1, make_float4(q[4], q[5], q[6], q[7]));
+                        }
+                    } else {
+                        for (uint32_t i = 0; i < c; ++i) dst[i] = vals[o + i];
+                    }
+                    done[ls][g] = (uint16_t)(prior + c);
+                }
+            } else {
+                // one row holds more values in this range than the tile (cannot happen with CSR_GC <= CSR_CAP and
+                // unique column indices; kept as a safe path): write it directly, one warp per row
+                for (int i = rc + w; i < re; i += NW) {
+                    const long long a = row_a[i], z = a + row_n[i];
+                    for (long long e = a + lane; e < z; e += 32) {
+                        const float v = data[e];
+                        if (v == 0.0f) continue;
+                        const int g = indices[e] - gene_lb - g0;
+                        const uint32_t slot = atomicAdd(&hist[g], 1u) - offs[g] + done[ls][g];
+                        ir_vals[(long long)(g0 + g) * pl.slot_cap + pl.seg_base[s] + slot] = v;
+                    }
+                }
+                __syncthreads();
+                for (int g = t; g < ng; g += CSR_THREADS) done[ls][g] += (uint16_t)(offs[g + 1] - offs[g]);
+            }
+            rc = re;
+        }
+      }
+    }
+    __syncthreads();
+    const int nseg = s_end - s_begin;
+    for (int g = t; g < ng; g += CSR_THREADS) {
+        uint32_t* dst = ir_cnt + (long long)(g0 + g) * S + s_begin;
+        for (int ls = 0; ls < nseg; ++ls) dst[ls] = done[ls][g];
     }
 }
 
@@ -246,13 +380,43 @@ int launch_stage_dense(const float* X, long long ld, int gene_lb, int b, const i
     return 0;
 }
 
+size_t stage_csr_workspace_bytes(const illico_plan_t* plan, int b) {
+    const int K = (b + CSR_GC - 1) / CSR_GC;
+    return (size_t)plan->n_cells * (size_t)(K + 1) * sizeof(int32_t) + 256;
+}
+
 int launch_stage_csr(const float* data, const int32_t* indices, const long long* indptr, int gene_lb, int b,
-                     const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, cudaStream_t stream) {
+                     const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
     if (b <= 0 || plan->n_cells <= 0) return 0;
-    long long warps = plan->n_cells;
-    long long blocks = (warps + 7) / 8;
-    if (blocks > 148 * 64) blocks = 148 * 64;
-    stage_csr_kernel<<<(unsigned)blocks, 256, 0, stream>>>(data, indices, indptr, gene_lb, b, *plan, ir_vals, ir_cnt);
+    const int K = (b + CSR_GC - 1) / CSR_GC;
+    if (!workspace || workspace_bytes < stage_csr_workspace_bytes(plan, b)) {
+        set_error("illico_stage_csr_f32: workspace too small (%zu < %zu bytes)", workspace_bytes, stage_csr_workspace_bytes(plan, b));
+        return 1;
+    }
+    int32_t* split = reinterpret_cast<int32_t*>(workspace);
+    long long blocks = ((long long)plan->n_cells + 7) / 8;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    csr_split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indices, indptr, plan->n_cells, gene_lb, b, K, split);
+    count_launch();
+    ILLICO_CUDA_OK(cudaGetLastError());
+    const int S = plan->n_segments;
+    long long avg = plan->n_cells / S;
+    if (avg < 1) avg = 1;
+    int segs_per_cta = (int)(1024 / avg);
+    if (segs_per_cta < 1) segs_per_cta = 1;
+    if (segs_per_cta > CSR_MAX_SEGS) segs_per_cta = CSR_MAX_SEGS;
+    const long long gy = (S + segs_per_cta - 1) / segs_per_cta;
+    if (gy > 65535) { set_error("too many segments (%d) for one CSR staging launch", S); return 1; }
+    if (plan->max_group_size >= 65536 && plan->n_segments == plan->n_groups) {
+        set_error("segments of 65536 or more cells are not supported by the CSR staging kernel");
+        return 1;
+    }
+    const size_t smem = CSR_MAX_ROWS * 8 + CSR_CAP * 4 + (2 * CSR_GC + 1) * 4 + CSR_MAX_ROWS * 4 + 9 * 4 +
+                        CSR_MAX_SEGS * CSR_GC * 2 + 16;
+    ILLICO_CUDA_OK(cudaFuncSetAttribute(stage_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stage_csr_kernel<<<dim3((unsigned)K, (unsigned)gy), CSR_THREADS, smem, stream>>>(data, indices, indptr, gene_lb, b, K, split,
+                                                                                     *plan, ir_vals, ir_cnt, segs_per_cta);
     count_launch();
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;

@@ -116,12 +116,15 @@ int illico_stage_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t 
                            const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, void* stream);
 
 /* CSR (rows = cells): data/indices [nnz], indptr [n_cells+1] (int64).  Row indices must be sorted
- * (illico/asymptotic_wilcoxon.py:185-193).  ir_cnt must be zeroed by the caller (illico_zero_counts). */
+ * (illico/asymptotic_wilcoxon.py:185-193).  Needs illico_stage_csr_workspace_bytes() of device scratch (may be
+ * the rank workspace: the rank kernels run after staging on the same stream). */
+size_t illico_stage_csr_workspace_bytes(const illico_plan_t* plan, int32_t n_genes_batch);
 int illico_stage_csr_f32(const float* data, const int32_t* indices, const int64_t* indptr,
                          int32_t gene_lb, int32_t n_genes_batch, const illico_plan_t* plan,
-                         float* ir_vals, uint32_t* ir_cnt, void* stream);
+                         float* ir_vals, uint32_t* ir_cnt, void* workspace, size_t workspace_bytes, void* stream);
 
-/* CSC (columns = genes): data/indices [nnz], indptr [n_genes+1] (int64); columns gene_lb.. */
+/* CSC (columns = genes): data/indices [nnz], indptr [n_genes+1] (int64); columns gene_lb..
+ * ir_cnt must be zeroed by the caller (illico_zero_counts). */
 int illico_stage_csc_f32(const float* data, const int32_t* indices, const int64_t* indptr,
                          int32_t gene_lb, int32_t n_genes_batch, const illico_plan_t* plan,
                          float* ir_vals, uint32_t* ir_cnt, void* stream);
