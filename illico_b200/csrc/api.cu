@@ -112,7 +112,7 @@ size_t illico_rank_workspace_bytes(const illico_plan_t* plan, int32_t n_genes_ba
     if ((size_t)n_genes_batch < ctas) ctas = (size_t)(n_genes_batch > 0 ? n_genes_batch : 1);
     size_t per_cta = plan->ref_group >= 0 ? 4 * (size_t)plan->max_group_size * sizeof(uint32_t)
                                           : ovr_slab_qwords(plan) * 8;
-    size_t rank = ctas * per_cta + 256;
+    size_t rank = ctas * per_cta + 256 + (((size_t)(n_genes_batch > 0 ? n_genes_batch : 1) + 64) * sizeof(int) + 255);
     size_t stage = stage_csr_workspace_bytes(plan, n_genes_batch);  // CSR staging reuses the same scratch
     return rank > stage ? rank : stage;
 }

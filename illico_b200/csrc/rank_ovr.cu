@@ -28,9 +28,11 @@ constexpr int OVR_NW = OVR_THREADS / 32;
 constexpr int HASH_CAP = 4096;
 constexpr int MAX_DISTINCT = 2048;
 constexpr uint32_t HASH_EMPTY = 0u;
-constexpr int T_SLOTS = 16;   // path T: slots of the small value table (also the bins of a segment histogram)
-constexpr int T_CAP = 11;     // path T: most distinct values it takes
+constexpr int T_THREADS = 128;  // table kernel: threads per CTA (one gene at a time, ~8 CTAs per SM)
+constexpr int T_SLOTS = 32;     // slots of the small value table (also the bins of a segment histogram)
+constexpr int T_CAP = 20;       // most distinct values the table kernel takes
 constexpr int T_WORDS = T_SLOTS / 2;  // two 16-bit bins per 32-bit word
+constexpr int T_MULTI = 256;    // multi-segment groups handed to whole warps per gene (more are ranked inline)
 
 struct OvrParams {
     const float* ir_vals;
@@ -46,6 +48,8 @@ struct OvrParams {
     long long* dbg_u2;
     double* dbg_tie;
     long long* dbg_tie_exact;
+    int* todo;        // genes the table kernel could not take (NULL: the general kernel ranks every gene)
+    int* todo_count;
 };
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key) { return (key * 2654435761u) >> 20; }  // 12 bits
@@ -101,153 +105,20 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
     double* seg_sum = (double*)(slab + S);                   // [S]
     uint32_t* gsortA = (uint32_t*)(slab + 2ll * S);          // [n_cells]
     uint32_t* gsortB = gsortA + ((n + 1) & ~1ll);            // [n_cells]
-    uint16_t* seg_bins = (uint16_t*)(gsortB + ((n + 1) & ~1ll));  // [S][T_SLOTS] path T segment histograms
 
     const double cc = P.flags.use_continuity ? 0.5 : 0.0;
 
-    for (int j = blockIdx.x; j < P.n_genes; j += gridDim.x) {
+    const int n_work = P.todo ? *P.todo_count : P.n_genes;
+    for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const int j = P.todo ? P.todo[wi] : wi;
         const uint32_t* cnt = P.ir_cnt + (long long)j * S;
         const float* vals = P.ir_vals + (long long)j * pl.slot_cap;
 
-        // ================= path T: a handful of distinct values (raw counts) =================
-        // ONE pass over the staged values: every thread owns a segment at a time, looks each value up in a tiny
-        // shared table (inserting unseen values) and bumps a private histogram bin; the segment histograms go to
-        // the slab.  Once the table is complete its <= 16 values are sorted, turned into doubled mid-ranks, and
-        // every segment's rank sum is a 32-term dot product -- the values are never touched again.
-        bool path_t = false;
         long long nnz = 0, n0 = 0, n_neg = 0;
         unsigned long long tie_nz_exact = 0;
         bool path_s = false;
         const uint32_t* sk = nullptr;  // sorted keys (path S)
         {
-            uint32_t* bins = smem;                                      // [T_WORDS][OVR_THREADS] private histograms, 2 bins/word
-            uint32_t* tkey = hist;                                      // [T_SLOTS] raw float bits, 0 = empty
-            uint32_t* gcount = hist + T_SLOTS;                          // [T_SLOTS] multiplicity in the whole column
-            uint32_t* r2slot = hist + 2 * T_SLOTS;                      // [T_SLOTS] doubled mid-rank of the slot's value
-            double* fcslot = reinterpret_cast<double*>(hist + 4 * T_SLOTS);  // [T_SLOTS] f(x) of the slot's value
-            uint32_t* skey = hist + 8 * T_SLOTS;                        // [T_SLOTS] finalize scratch: sorted keys
-            uint32_t* sslot = hist + 9 * T_SLOTS;                       // [T_SLOTS] ... and their slots
-            if (tid < T_SLOTS) { tkey[tid] = 0u; gcount[tid] = 0u; }
-            if (tid < 8) sc[tid] = 0;  // [0] distinct [1] overflow
-            __syncthreads();
-            unsigned long long my_nnz = 0;
-            for (int s = tid; s < S; s += OVR_THREADS) {
-                if (*(volatile int*)&sc[1]) break;
-#pragma unroll
-                for (int q = 0; q < T_WORDS; ++q) bins[q * OVR_THREADS + tid] = 0u;
-                const int c = (int)cnt[s];
-                my_nnz += c;
-                const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);
-                float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-                bool ok = true;
-                for (int i = 0; i < c && ok; i += 4) {
-                    const float4 q4 = nxt;
-                    if (i + 4 < c) nxt = src4[(i >> 2) + 1];
-                    const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (i + e < c && ok) {
-                            const uint32_t bits = __float_as_uint(q[e]);
-                            uint32_t h = (bits * 2654435761u) >> 28;
-                            int probes = 0;
-                            for (;;) {
-                                uint32_t kk = *(volatile uint32_t*)&tkey[h];
-                                if (kk == 0u) {
-                                    kk = atomicCAS(&tkey[h], 0u, bits);
-                                    if (kk == 0u) {
-                                        if (atomicAdd(&sc[0], 1) >= T_CAP) { sc[1] = 1; ok = false; }
-                                        break;
-                                    }
-                                }
-                                if (kk == bits) break;
-                                h = (h + 1) & (T_SLOTS - 1);
-                                if (++probes > T_SLOTS) { sc[1] = 1; ok = false; break; }
-                            }
-                            if (ok) bins[(h >> 1) * OVR_THREADS + tid] += 1u << ((h & 1u) << 4);
-                        }
-                    }
-                }
-                if (!ok) break;
-                uint32_t* dst = reinterpret_cast<uint32_t*>(seg_bins + (long long)s * T_SLOTS);
-#pragma unroll 2
-                for (int q = 0; q < T_WORDS; ++q) {
-                    const uint32_t w2 = bins[q * OVR_THREADS + tid];
-                    dst[q] = w2;
-                    if (w2 & 0xffffu) atomicAdd(&gcount[2 * q], w2 & 0xffffu);
-                    if (w2 >> 16) atomicAdd(&gcount[2 * q + 1], w2 >> 16);
-                }
-            }
-            const long long nnz_t = (long long)block_sum<unsigned long long>(my_nnz, redu);  // syncs
-            path_t = sc[1] == 0;
-            __syncthreads();
-            if (path_t) {
-                nnz = nnz_t;
-                n0 = n - nnz;
-                if (tid == 0) {
-                    int D = 0;
-                    for (int q = 0; q < T_SLOTS; ++q)
-                        if (tkey[q] != 0u) {  // insertion sort by order-preserving key
-                            const uint32_t k = f2key(__uint_as_float(tkey[q]));
-                            int a = D - 1;
-                            while (a >= 0 && skey[a] > k) { skey[a + 1] = skey[a]; sslot[a + 1] = sslot[a]; --a; }
-                            skey[a + 1] = k; sslot[a + 1] = (uint32_t)q;
-                            ++D;
-                        }
-                    unsigned long long lo = 0, t_exact = 0, negs = 0;
-                    for (int a = 0; a < D; ++a) {
-                        const uint32_t q = sslot[a], cq = gcount[q];
-                        unsigned long long r2 = 2ull * lo + cq + 1ull;   // lo + hi + 1 with hi = lo + cq
-                        if (skey[a] > KEY_ZERO) r2 += 2ull * (unsigned long long)n0;
-                        r2slot[q] = (uint32_t)r2;
-                        fcslot[q] = fc_value(__uint_as_float(tkey[q]), P.flags.is_log1p);
-                        t_exact += (unsigned long long)cube_minus((long long)cq);
-                        if (skey[a] < KEY_ZERO) negs += cq;
-                        lo += cq;
-                    }
-                    for (int q = 0; q < T_SLOTS; ++q) if (tkey[q] == 0u) { r2slot[q] = 0u; fcslot[q] = 0.0; }
-                    const unsigned long long zterm = (unsigned long long)cube_minus(n0);
-                    const bool sparse_order = P.flags.tie_order == ILLICO_TIES_SPARSE;
-                    const bool need_walk = sparse_order ? ((double)t_exact >= TWO53) : ((double)t_exact + (double)zterm >= TWO53);
-                    double acc;
-                    if (!need_walk) {
-                        acc = sparse_order ? (double)t_exact : (double)(t_exact + zterm);
-                    } else {
-                        acc = 0.0;
-                        bool zero_done = sparse_order || n0 == 0;
-                        for (int a = 0; a < D; ++a) {
-                            if (!zero_done && skey[a] > KEY_ZERO) { acc += (double)(long long)zterm; zero_done = true; }
-                            acc += (double)cube_minus((long long)gcount[sslot[a]]);
-                        }
-                        if (!zero_done) acc += (double)(long long)zterm;
-                    }
-                    if (sparse_order) acc = __dadd_rn(acc, zero_block_term_f64(n0));
-                    *tie_slot = acc;
-                    redu[0] = t_exact;
-                    redu[1] = negs;
-                }
-                __syncthreads();
-                tie_nz_exact = redu[0];
-                n_neg = (long long)redu[1];
-                // ---- every segment's doubled rank sum and expression sum from its histogram
-                for (int s = tid; s < S; s += OVR_THREADS) {
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(seg_bins + (long long)s * T_SLOTS);
-                    unsigned long long acc = 0;
-                    double sum = 0.0;
-#pragma unroll 2
-                    for (int q = 0; q < T_WORDS; ++q) {
-                        const uint32_t w2 = src[q];
-                        if (w2 == 0u) continue;
-                        const uint32_t b0 = w2 & 0xffffu, b1 = w2 >> 16;
-                        acc += (unsigned long long)b0 * r2slot[2 * q] + (unsigned long long)b1 * r2slot[2 * q + 1];
-                        sum += (double)b0 * fcslot[2 * q] + (double)b1 * fcslot[2 * q + 1];
-                    }
-                    seg_r2[s] = acc;
-                    seg_sum[s] = sum;
-                }
-                __syncthreads();
-            }
-        }
-        if (!path_t) {
         // ================= phase A: value -> multiplicity hash (path H attempt) =================
         for (int i = tid; i < 2 * HASH_CAP; i += OVR_THREADS) smem[i] = 0;
         if (tid < 8) sc[tid] = 0;  // [0] ndist [1] overflow [2] cursor [3] dn
@@ -398,12 +269,12 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
             }
             __syncthreads();
         }
-        }  // !path_t
+        }
         const double tie = *tie_slot;
         const unsigned long long r2_zero = 2ull * (unsigned long long)n_neg + (unsigned long long)n0 + 1ull;
 
         // ================= phase B: per-segment doubled rank sums and expression sums =================
-        for (int s = tid; s < S && !path_t; s += OVR_THREADS) {
+        for (int s = tid; s < S; s += OVR_THREADS) {
             const int c = (int)cnt[s];
             const float* src = vals + pl.seg_base[s];
             unsigned long long acc = 0;
@@ -472,9 +343,225 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Table kernel: genes with a handful of distinct non-zero values (raw counts).  Small CTAs, almost no shared
+// memory, so ~8 genes are in flight per SM and the dependent global loads of one gene overlap with the work
+// of the others.  Per gene:
+//   pass 1  one thread per segment: every value is looked up in a 32-slot shared table (unseen values are
+//           inserted), a private 16-bit histogram is bumped and then added to the column's multiplicities;
+//   finish  thread 0 sorts the <= 20 values, turns multiplicities into doubled mid-ranks, tie sum, totals;
+//   pass 2  one thread per group: sum of the looked-up doubled mid-ranks and expression values -> 2U, p, fold
+//           change (the rest-of-cells total comes from the table, so there is no second sweep over groups).
+// A gene with more distinct values is appended to `todo` for the general kernel.
+__global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams P) {
+    __shared__ uint32_t tkey[T_SLOTS];      // raw float bits, 0 = empty
+    __shared__ uint32_t gcount[T_SLOTS];    // multiplicity in the whole column
+    __shared__ uint32_t r2slot[T_SLOTS];    // doubled mid-rank of the slot's value
+    __shared__ double fcslot[T_SLOTS];      // f(x) of the slot's value
+    __shared__ uint32_t bins[T_WORDS][T_THREADS];
+    __shared__ unsigned long long redu[8];
+    __shared__ double redd[4];
+    __shared__ int sc[4];
+    __shared__ int multi[T_MULTI];          // groups with several segments (e.g. the rest-of-cells sized clusters)
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const illico_plan_t& pl = P.plan;
+    const int S = pl.n_segments, G = pl.n_groups;
+    const long long n = pl.n_cells;
+    const double cc = P.flags.use_continuity ? 0.5 : 0.0;
+
+    for (int j = blockIdx.x; j < P.n_genes; j += gridDim.x) {
+        const uint32_t* cnt = P.ir_cnt + (long long)j * S;
+        const float* vals = P.ir_vals + (long long)j * pl.slot_cap;
+        __syncthreads();
+        if (tid < T_SLOTS) { tkey[tid] = 0u; gcount[tid] = 0u; }
+        if (tid < 4) sc[tid] = 0;  // [0] distinct [1] overflow
+        __syncthreads();
+        // ================= pass 1 =================
+        // The private 16-bit bins accumulate over all of the thread's segments and are added to the column's
+        // multiplicities once (or whenever a bin could overflow).
+        unsigned long long my_nnz = 0;
+        uint32_t since_flush = 0;
+        auto flush_bins = [&]() {
+#pragma unroll 4
+            for (int q = 0; q < T_WORDS; ++q) {
+                const uint32_t w2 = bins[q][tid];
+                if (w2 & 0xffffu) atomicAdd(&gcount[2 * q], w2 & 0xffffu);
+                if (w2 >> 16) atomicAdd(&gcount[2 * q + 1], w2 >> 16);
+                bins[q][tid] = 0u;
+            }
+            since_flush = 0;
+        };
+#pragma unroll
+        for (int q = 0; q < T_WORDS; ++q) bins[q][tid] = 0u;
+        bool ok = true;
+        for (int s = tid; s < S && ok; s += T_THREADS) {
+            if (*(volatile int*)&sc[1]) break;
+            const int c = (int)cnt[s];
+            if (since_flush + (uint32_t)c > 60000u) flush_bins();
+            since_flush += (uint32_t)c;
+            my_nnz += c;
+            const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);  // 32-byte aligned, padded slot
+            float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < c && ok; i += 4) {
+                const float4 q4 = nxt;
+                if (i + 4 < c) nxt = src4[(i >> 2) + 1];
+                const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (i + e < c && ok) {
+                        const uint32_t bits = __float_as_uint(q[e]);
+                        uint32_t h = (bits * 2654435761u) >> 27;
+                        int probes = 0;
+                        for (;;) {
+                            uint32_t kk = *(volatile uint32_t*)&tkey[h];
+                            if (kk == 0u) {
+                                kk = atomicCAS(&tkey[h], 0u, bits);
+                                if (kk == 0u) {
+                                    if (atomicAdd(&sc[0], 1) >= T_CAP) { sc[1] = 1; ok = false; }
+                                    break;
+                                }
+                            }
+                            if (kk == bits) break;
+                            h = (h + 1) & (T_SLOTS - 1);
+                            if (++probes > T_SLOTS) { sc[1] = 1; ok = false; break; }
+                        }
+                        if (ok) bins[h >> 1][tid] += 1u << ((h & 1u) << 4);
+                    }
+                }
+            }
+        }
+        if (ok) flush_bins();
+        // block sum of my_nnz
+        my_nnz = warp_sum_u64(my_nnz);
+        if (lane == 0) redu[w] = my_nnz;
+        __syncthreads();
+        if (sc[1]) {  // too many distinct values: leave the gene to the general kernel
+            if (tid == 0) P.todo[atomicAdd(P.todo_count, 1)] = j;
+            continue;
+        }
+        const long long nnz = (long long)(redu[0] + redu[1] + redu[2] + redu[3]);
+        const long long n0 = n - nnz;
+        // ================= finish the table (thread 0; <= 20 entries) =================
+        if (tid == 0) {
+            uint32_t skey[T_CAP + 1], sslot[T_CAP + 1];
+            int D = 0;
+            for (int q = 0; q < T_SLOTS; ++q)
+                if (tkey[q] != 0u) {  // insertion sort by order-preserving key
+                    const uint32_t k = f2key(__uint_as_float(tkey[q]));
+                    int a = D - 1;
+                    while (a >= 0 && skey[a] > k) { skey[a + 1] = skey[a]; sslot[a + 1] = sslot[a]; --a; }
+                    skey[a + 1] = k; sslot[a + 1] = (uint32_t)q;
+                    ++D;
+                }
+            unsigned long long lo = 0, t_exact = 0, negs = 0;
+            double total = 0.0;
+            for (int a = 0; a < D; ++a) {
+                const uint32_t q = sslot[a], cq = gcount[q];
+                unsigned long long r2 = 2ull * lo + cq + 1ull;   // lo + hi + 1 with hi = lo + cq
+                if (skey[a] > KEY_ZERO) r2 += 2ull * (unsigned long long)n0;
+                r2slot[q] = (uint32_t)r2;
+                const double f = fc_value(__uint_as_float(tkey[q]), P.flags.is_log1p);
+                fcslot[q] = f;
+                total += (double)cq * f;
+                t_exact += (unsigned long long)cube_minus((long long)cq);
+                if (skey[a] < KEY_ZERO) negs += cq;
+                lo += cq;
+            }
+            const unsigned long long zterm = (unsigned long long)cube_minus(n0);
+            const bool sparse_order = P.flags.tie_order == ILLICO_TIES_SPARSE;
+            const bool need_walk = sparse_order ? ((double)t_exact >= TWO53) : ((double)t_exact + (double)zterm >= TWO53);
+            double acc;
+            if (!need_walk) {
+                acc = sparse_order ? (double)t_exact : (double)(t_exact + zterm);
+            } else {  // the reference's sequential f64 accumulation, in its order
+                acc = 0.0;
+                bool zero_done = sparse_order || n0 == 0;
+                for (int a = 0; a < D; ++a) {
+                    if (!zero_done && skey[a] > KEY_ZERO) { acc += (double)(long long)zterm; zero_done = true; }
+                    acc += (double)cube_minus((long long)gcount[sslot[a]]);
+                }
+                if (!zero_done) acc += (double)(long long)zterm;
+            }
+            if (sparse_order) acc = __dadd_rn(acc, zero_block_term_f64(n0));
+            redd[0] = acc;
+            redd[1] = total;
+            redu[4] = t_exact;
+            redu[5] = negs;
+        }
+        __syncthreads();
+        const double tie = redd[0], total = redd[1];
+        const unsigned long long r2_zero = 2ull * redu[5] + (unsigned long long)n0 + 1ull;
+        // ================= pass 2: one thread per single-segment group, one warp per multi-segment group =========
+        auto rank_segment = [&](int s, unsigned long long& R2, double& sum, long long& nnz_g) {
+            const int c = (int)cnt[s];
+            nnz_g += c;
+            const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);
+            float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < c; i += 4) {
+                const float4 q4 = nxt;
+                if (i + 4 < c) nxt = src4[(i >> 2) + 1];
+                const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (i + e < c) {
+                        const uint32_t bits = __float_as_uint(q[e]);
+                        uint32_t h = (bits * 2654435761u) >> 27;
+                        while (tkey[h] != bits) h = (h + 1) & (T_SLOTS - 1);
+                        R2 += r2slot[h];
+                        sum += fcslot[h];
+                    }
+                }
+            }
+        };
+        auto finish_group = [&](int g, unsigned long long R2, double sum, long long nnz_g) {
+            const long long n_t = pl.group_size[g], n_r = n - n_t;
+            R2 += (unsigned long long)(n_t - nnz_g) * r2_zero;
+            const long long u2 = 2 * n_r * n_t + n_t * (n_t + 1) - (long long)R2;
+            const double U = (double)u2 / 2.0;
+            const double mu = (double)(n_r * n_t) / 2.0;
+            const double p = compute_pval(n_r, n_t, n, P.flags.tie_correct ? tie : 0.0, U, mu, cc, P.flags.alternative);
+            const double mu_t = sum / (double)n_t;
+            const double mu_r = (total - sum) / (double)(n - n_t);
+            double* o = P.results + (long long)g * P.gstride + (long long)j * 3;
+            o[0] = p; o[1] = U; o[2] = (mu_r == 0.0) ? INFINITY : mu_t / mu_r;
+            if (P.dbg_u2) P.dbg_u2[(long long)g * P.n_genes + j] = u2;
+        };
+        if (tid == 0) sc[2] = 0;  // multi-segment groups found so far
+        __syncthreads();
+        for (int g = tid; g < G; g += T_THREADS) {
+            const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
+            if (s1 - s0 > 1) {  // big group: leave it to a whole warp (one lane per segment)
+                const int slot = atomicAdd(&sc[2], 1);
+                if (slot < T_MULTI) { multi[slot] = g; continue; }
+            }
+            unsigned long long R2 = 0;
+            double sum = 0.0;
+            long long nnz_g = 0;
+            for (int s = s0; s < s1; ++s) rank_segment(s, R2, sum, nnz_g);
+            finish_group(g, R2, sum, nnz_g);
+        }
+        __syncthreads();
+        const int n_multi = min(sc[2], T_MULTI);
+        for (int m = w; m < n_multi; m += T_THREADS / 32) {
+            const int g = multi[m];
+            unsigned long long R2 = 0;
+            double sum = 0.0;
+            long long nnz_g = 0;
+            for (int s = pl.group_seg[g] + lane; s < pl.group_seg[g + 1]; s += 32) rank_segment(s, R2, sum, nnz_g);
+            R2 = warp_sum_u64(R2);
+            sum = warp_sum_f64(sum);
+            nnz_g = (long long)warp_sum_u64((unsigned long long)nnz_g);
+            if (lane == 0) finish_group(g, R2, sum, nnz_g);
+        }
+        if (tid == 0) {
+            if (P.dbg_tie) P.dbg_tie[j] = tie;
+            if (P.dbg_tie_exact) P.dbg_tie_exact[j] = (long long)(redu[4] + (unsigned long long)cube_minus(n0));
+        }
+    }
+}
+
 size_t ovr_slab_qwords(const illico_plan_t* plan) {
-    return 2 * (size_t)plan->n_segments + (size_t)((plan->n_cells + 1) & ~1) + 2 +
-           (size_t)plan->n_segments * T_SLOTS * 2 / 8 + 2;
+    return 2 * (size_t)plan->n_segments + (size_t)((plan->n_cells + 1) & ~1) + 2;
 }
 
 int launch_ovr(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const illico_plan_t* plan,
@@ -512,11 +599,33 @@ int launch_ovr(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const 
     int grid = sms * occ;
     if (grid > n_genes) grid = n_genes;
     const size_t slab_q = ovr_slab_qwords(plan);
+    // workspace head: the list of genes left to the general kernel
+    const size_t head = (((size_t)n_genes + 64) * sizeof(int) + 255) & ~(size_t)255;
+    if (workspace_bytes < head + slab_q * 8) { set_error("rank workspace too small: %zu bytes", workspace_bytes); return 1; }
+    int* todo_count = reinterpret_cast<int*>(workspace);
+    int* todo = todo_count + 16;
+    workspace = reinterpret_cast<char*>(workspace) + head;
+    workspace_bytes -= head;
     if ((size_t)grid * slab_q * 8 > workspace_bytes) {
         grid = (int)(workspace_bytes / (slab_q * 8));
         if (grid < 1) { set_error("rank workspace too small: %zu bytes", workspace_bytes); return 1; }
     }
     P.slab = (unsigned long long*)workspace; P.slab_qwords = (long long)slab_q;
+    const char* tenv = getenv("ILLICO_OVR_TABLE");
+    const bool use_table = flags->group_sums == nullptr && !(tenv && atoi(tenv) == 0);
+    if (use_table) {
+        P.todo = todo; P.todo_count = todo_count;
+        ILLICO_CUDA_OK(cudaMemsetAsync(todo_count, 0, sizeof(int), stream));
+        int tocc = 0;
+        ILLICO_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tocc, ovr_table_kernel, T_THREADS, 0));
+        int tgrid = sms * (tocc > 0 ? tocc : 1);
+        if (tgrid > n_genes) tgrid = n_genes;
+        ovr_table_kernel<<<tgrid, T_THREADS, 0, stream>>>(P);
+        count_launch();
+        ILLICO_CUDA_OK(cudaGetLastError());
+    } else {
+        P.todo = nullptr; P.todo_count = nullptr;
+    }
     ovr_kernel<<<grid, OVR_THREADS, need, stream>>>(P);
     count_launch();
     ILLICO_CUDA_OK(cudaGetLastError());
