@@ -21,24 +21,25 @@ constexpr int STAGE_MAX_SEGS = 16;
 constexpr int STAGE_INFLIGHT = 16;  // cell rows in flight per warp (16 x 128 B)
 
 // Appends v to the lane's slot when it is non-zero.  Non-zeros are collected eight at a time in a lane-private
-// shared-memory column and leave as ONE full, aligned 32-byte sector (slots are 32-byte aligned and padded), so
-// L2 never sees a partial-sector write that it would have to merge with a DRAM fill.
-__device__ __forceinline__ void flush8(float* out0, uint32_t first, const float (*wbuf)[STAGE_WARPS * 32], int t) {
-    float4 a = make_float4(wbuf[0][t], wbuf[1][t], wbuf[2][t], wbuf[3][t]);
-    float4 b = make_float4(wbuf[4][t], wbuf[5][t], wbuf[6][t], wbuf[7][t]);
+// 32-byte shared-memory row and leave as ONE full, aligned 32-byte sector (slots are 32-byte aligned and padded),
+// so L2 never sees a partial-sector write that it would have to merge with a DRAM fill.  The row is contiguous
+// per lane: only the ~3 lanes of a warp that hold a non-zero store at a time, so bank conflicts are rare, and
+// the flush is two 128-bit shared loads + two 128-bit global stores.
+__device__ __forceinline__ void flush8(float* out0, uint32_t first, uint32_t row_addr) {
+    float4 a, b;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(row_addr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(row_addr + 16));
     float4* dst = reinterpret_cast<float4*>(out0 + first);
     __stcs(dst, a);
     __stcs(dst + 1, b);
 }
-// `off` = byte offset of the next free entry in the lane's shared column (1 KB per entry, 8 entries);
-// `done` = values already written to the slot.  Six instructions per element, no divergent branch except the
-// flush every eighth non-zero.
-__device__ __forceinline__ void append_nonzero(float* out0, uint32_t& done, uint32_t& off, float v,
-                                               float (*wbuf)[STAGE_WARPS * 32], uint32_t wbuf_t_addr, int t) {
-    asm volatile("{ .reg .pred p; setp.neu.f32 p, %2, 0f00000000; @p st.shared.f32 [%1], %2; @p add.u32 %0, %0, 1024; }"
-                 : "+r"(off) : "r"(wbuf_t_addr + off), "f"(v) : "memory");
-    if (off == 8192u) {
-        flush8(out0, done, wbuf, t);
+// `off` = byte offset of the next free entry in the lane's 32-byte row; `done` = values already written to the
+// slot.  Six instructions per element, no divergent branch except the flush every eighth non-zero.
+__device__ __forceinline__ void append_nonzero(float* out0, uint32_t& done, uint32_t& off, float v, uint32_t row_addr) {
+    asm volatile("{ .reg .pred p; setp.neu.f32 p, %2, 0f00000000; @p st.shared.f32 [%1], %2; @p add.u32 %0, %0, 4; }"
+                 : "+r"(off) : "r"(row_addr + off), "f"(v) : "memory");
+    if (off == 32u) {
+        flush8(out0, done, row_addr);
         done += 8u;
         off = 0u;
     }
@@ -62,8 +63,7 @@ __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const flo
                                                                        int segs_per_cta) {
     constexpr int NT = STAGE_WARPS * 32;
     __shared__ uint16_t cnt_tile[TILE_COUNTS ? STAGE_MAX_SEGS : 1][TILE_COUNTS ? NT * VEC : 1];
-    __shared__ float wbuf[VEC][8][NT];
-    static_assert(NT * 4 == 1024, "append_nonzero assumes a 1 KB row pitch");
+    __shared__ __align__(16) float wbuf[VEC][NT][8];
     const int lane = threadIdx.x & 31;
     const int t = threadIdx.x;
     const int jb = (blockIdx.x * NT + t) * VEC;          // first of this lane's VEC genes inside the batch
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const flo
     const int jj = active ? jb : 0;                      // inactive lanes shadow gene 0 and never store
     const float* col = X + gene_lb + jj;
     const uint32_t ldb = (uint32_t)(ld * 4);
-    const uint32_t wbuf_t = (uint32_t)__cvta_generic_to_shared(&wbuf[0][0][t]);
+    const uint32_t wbuf_t = (uint32_t)__cvta_generic_to_shared(&wbuf[0][t][0]);
     const int S = pl.n_segments;
     const int s_begin = blockIdx.y * segs_per_cta, s_end = min(S, s_begin + segs_per_cta);
     for (int s = s_begin; s < s_end; ++s) {
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const flo
                         if (full || k0 + u < nrows) {
 #pragma unroll
                             for (int e = 0; e < VEC; ++e)
-                                append_nonzero(out0[e], done[e], off[e], v[u][e], wbuf[e], wbuf_t + e * 8 * NT * 4, t);
+                                append_nonzero(out0[e], done[e], off[e], v[u][e], wbuf_t + e * NT * 32);
                         }
                     }
                 }
@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const flo
         }
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            if (active && off[e]) flush8(out0[e], done[e], wbuf[e], t);  // tail: one padded full sector
-            const uint32_t cnt = done[e] + (off[e] >> 10);
+            if (active && off[e]) flush8(out0[e], done[e], wbuf_t + e * NT * 32);  // tail: one padded full sector
+            const uint32_t cnt = done[e] + (off[e] >> 2);
             if (TILE_COUNTS) cnt_tile[s - s_begin][t * VEC + e] = (uint16_t)cnt;
             else if (active) ir_cnt[(long long)(jb + e) * S + s] = cnt;
         }
