@@ -18,7 +18,7 @@ namespace illico {
 
 constexpr int STAGE_WARPS = 8;
 constexpr int STAGE_MAX_SEGS = 16;
-constexpr int STAGE_INFLIGHT = 16;  // cell rows in flight per warp (16 x 128 B)
+constexpr int STAGE_INFLIGHT = 8;   // cell rows per load batch (two batches in flight per warp)
 
 // Appends v to the lane's slot when it is non-zero.  Non-zeros are collected eight at a time in a lane-private
 // 32-byte shared-memory row and leave as ONE full, aligned 32-byte sector (slots are 32-byte aligned and padded),
@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const flo
             const int nrows = min(32, p1 - p);
             const int myrow = pl.perm[p + min(lane, nrows - 1)];   // tail lanes repeat the last cell (never stored)
             const bool full = nrows == 32;
-#pragma unroll 1
-            for (int k0 = 0; k0 < nrows; k0 += STAGE_INFLIGHT) {
-                float v[STAGE_INFLIGHT][VEC];
+            // software pipeline over the chunk's rows in batches of STAGE_INFLIGHT: the next batch's loads are
+            // issued before the current batch is compacted (two register buffers, manually alternated)
+            auto load_batch = [&](float (&v)[STAGE_INFLIGHT][VEC], int k0) {
 #pragma unroll
                 for (int u = 0; u < STAGE_INFLIGHT; ++u) {
                     const float* src = row_ptr(col, __shfl_sync(FULL, myrow, (k0 + u) & 31), ldb);
@@ -101,16 +101,28 @@ __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const flo
                         v[u][0] = __ldcs(src);
                     }
                 }
-                if (active) {
+            };
+            auto compact_batch = [&](const float (&v)[STAGE_INFLIGHT][VEC], int k0) {
+                if (!active) return;
 #pragma unroll
-                    for (int u = 0; u < STAGE_INFLIGHT; ++u) {
-                        if (full || k0 + u < nrows) {
+                for (int u = 0; u < STAGE_INFLIGHT; ++u) {
+                    if (full || k0 + u < nrows) {
 #pragma unroll
-                            for (int e = 0; e < VEC; ++e)
-                                append_nonzero(out0[e], done[e], off[e], v[u][e], wbuf_t + e * NT * 32);
-                        }
+                        for (int e = 0; e < VEC; ++e)
+                            append_nonzero(out0[e], done[e], off[e], v[u][e], wbuf_t + e * NT * 32);
                     }
                 }
+            };
+            float va[STAGE_INFLIGHT][VEC], vb[STAGE_INFLIGHT][VEC];
+            load_batch(va, 0);
+#pragma unroll
+            for (int k0 = 0; k0 < 32; k0 += 2 * STAGE_INFLIGHT) {
+                if (k0 >= nrows) break;
+                if (k0 + STAGE_INFLIGHT < nrows) load_batch(vb, k0 + STAGE_INFLIGHT);
+                compact_batch(va, k0);
+                if (k0 + STAGE_INFLIGHT >= nrows) break;
+                if (k0 + 2 * STAGE_INFLIGHT < nrows) load_batch(va, k0 + 2 * STAGE_INFLIGHT);
+                compact_batch(vb, k0 + STAGE_INFLIGHT);
             }
         }
 #pragma unroll
@@ -356,7 +368,9 @@ int launch_stage_dense(const float* X, long long ld, int gene_lb, int b, const i
     const int S = plan->n_segments;
     long long avg = plan->n_cells / S;
     if (avg < 1) avg = 1;
-    int segs_per_cta = (int)(2048 / avg);
+    const char* rows_env = getenv("ILLICO_STAGE_ROWS");
+    // ~512 cells per CTA: enough CTAs (tens of waves) that the last partial wave costs a few percent
+    int segs_per_cta = (int)((rows_env ? atoi(rows_env) : 512) / avg);
     if (segs_per_cta < 1) segs_per_cta = 1;
     if (segs_per_cta > STAGE_MAX_SEGS) segs_per_cta = STAGE_MAX_SEGS;
     long long gy = (S + segs_per_cta - 1) / segs_per_cta;
