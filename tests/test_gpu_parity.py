@@ -274,3 +274,60 @@ def test_float64_and_integer_inputs(fmt, test):
         g, p, U, fc = oracle.run(Xf, labels, ref)
         ref_row = int(np.searchsorted(groups, ref)) if ref is not None else None
         assert_parity(got, (p, U, fc), ref_row=ref_row, what=f"{arr.dtype}:{fmt}:{test}")
+
+
+def _random_case(seed):
+    """Random shapes, sparsity, value kinds and group structures: exercises every tier of the rank kernels."""
+    rng = np.random.RandomState(seed)
+    n = int(rng.choice([37, 300, 1500, 6000, 20000]))
+    N = int(rng.choice([1, 3, 9, 33]))
+    kind = rng.choice(["counts", "bigcounts", "continuous", "signed", "constant", "empty"])
+    dens = float(rng.choice([0.02, 0.1, 0.5, 1.0]))
+    if kind == "counts":
+        X = rng.poisson(1.5, size=(n, N)).astype(np.float32)
+    elif kind == "bigcounts":
+        X = rng.poisson(40.0, size=(n, N)).astype(np.float32)       # > 20 distinct values: general paths
+    elif kind == "continuous":
+        X = rng.gamma(2.0, 2.0, size=(n, N)).astype(np.float32)
+    elif kind == "signed":
+        X = np.round(rng.randn(n, N) * 3, 1).astype(np.float32)
+    elif kind == "constant":
+        X = np.full((n, N), 2.0, dtype=np.float32)
+    else:
+        X = np.zeros((n, N), dtype=np.float32)
+    X[rng.rand(n, N) >= dens] = 0
+    structure = rng.choice(["many_small", "few_big", "skewed", "two"])
+    if structure == "many_small":
+        codes = rng.randint(0, max(2, n // 7), size=n)
+    elif structure == "few_big":
+        codes = rng.randint(0, 4, size=n)
+    elif structure == "skewed":
+        codes = np.minimum(rng.geometric(0.3, size=n), 12)
+    else:
+        codes = (rng.rand(n) < 0.5).astype(int)
+    codes[0], codes[-1] = codes.min(), codes.max()
+    labels = [f"g{c:05d}" for c in codes]
+    return X, labels, kind, structure
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_inputs_against_oracle(seed):
+    from scipy import sparse
+
+    X, labels, kind, structure = _random_case(seed)
+    rng = np.random.RandomState(1000 + seed)
+    fmt = ["dense", "csr", "csc"][seed % 3]
+    if kind == "signed":
+        fmt = "dense"  # the sparse reference kernels assume stored values > 0
+    Xf = C.to_format(X, fmt)
+    uniq = sorted(set(labels))
+    ref = uniq[int(rng.randint(len(uniq)))] if seed % 2 == 0 else None
+    alt = C.ALTERNATIVES[seed % 3]
+    kw = dict(is_log1p=bool(seed % 5 == 0), use_continuity=bool(seed % 4 != 1), tie_correct=bool(seed % 7 != 3), alternative=alt)
+    groups, got = _run(Xf, labels, ref, batch_size=int(rng.choice([1, 4, 64])), **kw)
+    g, p, U, fc = oracle.run(Xf, labels, ref, **kw)
+    ref_row = int(np.searchsorted(groups, ref)) if ref is not None else None
+    fc_rtol = FC_RTOL_LOG1P_F32 if kw["is_log1p"] else FC_RTOL
+    # all-zero genes / groups: the oracle and the kernels both give inf or nan fold changes in the same places
+    assert_parity(got, (p, U, fc), ref_row=ref_row, fc_rtol=fc_rtol, what=f"seed {seed}: {kind}/{structure}/{fmt}/ref={ref}")
+    assert sparse is not None
