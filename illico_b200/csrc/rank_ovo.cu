@@ -71,8 +71,35 @@ __device__ __forceinline__ void rank_value(const RefInfo& R, uint32_t key, long 
     tie += (unsigned long long)(cube_minus(t) - cube_minus(a));
 }
 
+// The reference's sequential f64 tie accumulation for ONE pair (illico/utils/ranking.py:52-158 for the dense
+// kernels: merged runs ascending, only t > 1 added, the zero block at its sorted position;
+// illico/ovo/sparse_ovo.py:85 for the sparse ones: non-zero runs, then Z^3 - Z last).  Only needed when the
+// exact sum reaches 2^53 (pairs of more than 208 063 cells); one thread walks both sorted key lists.
+__device__ __noinline__ double ordered_pair_tie(const uint32_t* A, int nA, const uint32_t* B, int strideB, int nB,
+                                                long long Z, bool sparse_order) {
+    int i = 0, jx = 0;
+    double acc = 0.0;
+    bool zero_done = sparse_order || Z == 0;
+    while (i < nA || jx < nB) {
+        const uint32_t ka = (i < nA) ? A[i] : 0xffffffffu, kb = (jx < nB) ? B[(long long)jx * strideB] : 0xffffffffu;
+        const uint32_t k = min(ka, kb);
+        if (!zero_done && k > KEY_ZERO) {
+            if (Z > 1) acc += (double)cube_minus(Z);
+            zero_done = true;
+        }
+        long long t = 0;
+        while (i < nA && A[i] == k) { ++i; ++t; }
+        while (jx < nB && B[(long long)jx * strideB] == k) { ++jx; ++t; }
+        if (t > 1) acc += (double)cube_minus(t);
+    }
+    if (!zero_done && Z > 1) acc += (double)cube_minus(Z);
+    if (sparse_order) acc += (double)cube_minus(Z);
+    return acc;
+}
+
 __device__ __forceinline__ void finalize_group(const OvoParams& P, const RefInfo& R, int j, int g, long long m,
-                                               unsigned long long u2, unsigned long long tie_nz, double sum) {
+                                               unsigned long long u2, unsigned long long tie_nz, double sum,
+                                               const uint32_t* gkeys = nullptr, int gstride = 1) {
     const long long n_t = P.plan.group_size[g];
     const long long z_t = n_t - m;
     if (P.flags.group_sums) sum = P.flags.group_sums[(long long)g * P.n_genes + j];
@@ -80,8 +107,11 @@ __device__ __forceinline__ void finalize_group(const OvoParams& P, const RefInfo
     u2 += (unsigned long long)(z_t * (2ll * R.npos + R.zeros));
     const unsigned long long tie_exact = R.tie + tie_nz + (unsigned long long)cube_minus(Z);
     // Every partial sum of the reference's sequential f64 accumulation is an exact integer while the
-    // total stays below 2^53 (pairs of up to 208 063 cells), so the exact sum converts without rounding.
-    const double tie = (double)tie_exact;
+    // total stays below 2^53 (pairs of up to 208 063 cells), so the exact sum converts without rounding;
+    // above it the accumulation is replayed in the reference's order.
+    double tie = (double)tie_exact;
+    if (tie >= TWO53 && gkeys != nullptr)
+        tie = ordered_pair_tie(R.keys, R.nnz, gkeys, gstride, (int)m, Z, P.flags.tie_order == ILLICO_TIES_SPARSE);
     const double U = (double)u2 / 2.0;
     const double mu = (double)(R.n_ref * n_t) / 2.0;
     const double cc = P.flags.use_continuity ? 0.5 : 0.0;
@@ -244,7 +274,8 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 int m = 0;
                 for (int s = s0; s < s1; ++s) m += (int)cnt[s];
                 uint32_t* col = scratch + tid;  // private column: element k at col[k * OVO_THREADS]
-                if (table && m <= FAST_MAX) {
+                const bool big_pair = R.n_ref + (long long)pl.group_size[g] > 208063;  // tie sum may pass 2^53
+                if (table && m <= FAST_MAX && !big_pair) {
                     // ---- table path: private histogram over the control's distinct values
                     for (int t = 0; t < D; ++t) col[t * OVO_THREADS] = 0;
                     bool ok = true;
@@ -339,7 +370,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                     sum += (double)(r - i) * fc_value(key2f(key), P.flags.is_log1p);
                     i = r;
                 }
-                finalize_group(P, R, j, g, m, u2, tie, sum);
+                finalize_group(P, R, j, g, m, u2, tie, sum, col, OVO_THREADS);
             }
             __syncthreads();
             // ---- warp tier (usually empty: then this barrier is the only one of the chunk)
@@ -379,7 +410,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 u2 = warp_sum_u64(u2);
                 tie = warp_sum_u64(tie);
                 sum = warp_sum_f64(sum);
-                if (lane == 0) finalize_group(P, R, j, g, m, u2, tie, sum);
+                if (lane == 0) finalize_group(P, R, j, g, m, u2, tie, sum, buf, 1);
                 __syncwarp();
             }
             __syncthreads();
@@ -410,7 +441,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 u2 = block_sum<unsigned long long>(u2, redu);
                 tie = block_sum<unsigned long long>(tie, redu);
                 sum = block_sum<double>(sum, redd);
-                if (tid == 0) finalize_group(P, R, j, g, m, u2, tie, sum);
+                if (tid == 0) finalize_group(P, R, j, g, m, u2, tie, sum, gk, 1);
                 __syncthreads();
             }
             __syncthreads();
