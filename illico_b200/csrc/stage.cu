@@ -244,10 +244,23 @@ __global__ void __launch_bounds__(CSR_THREADS) stage_csr_kernel(const float* __r
             __syncthreads();
             const int re = chunk_end;
             // ---- count per gene
-            for (int i = rc + w; i < re; i += NW) {
-                const long long a = row_a[i], z = a + row_n[i];
-                for (long long e = a + lane; e < z; e += 32)
-                    if (data[e] != 0.0f) atomicAdd(&hist[indices[e] - gene_lb - g0], 1u);
+            // eight lanes per row, four elements per lane in flight: the loads of 32 rows x 4 elements overlap
+            for (int i = rc + (t >> 3); i < re; i += CSR_THREADS / 8) {
+                const long long a = row_a[i];
+                const int nrow = row_n[i];
+                for (int e0 = (t & 7); e0 < nrow; e0 += 32) {
+                    float d[4];
+                    int c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ee = e0 + 8 * u;
+                        d[u] = (ee < nrow) ? data[a + ee] : 0.0f;
+                        c[u] = (ee < nrow) ? indices[a + ee] : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (d[u] != 0.0f) atomicAdd(&hist[c[u] - gene_lb - g0], 1u);
+                }
             }
             __syncthreads();
             // ---- exclusive scan of hist[0..CSR_GC) (2 entries per thread)
@@ -267,11 +280,21 @@ __global__ void __launch_bounds__(CSR_THREADS) stage_csr_kernel(const float* __r
             __syncthreads();
             if (offs[CSR_GC] <= CSR_CAP) {
                 // ---- scatter the values by gene into the shared tile
-                for (int i = rc + w; i < re; i += NW) {
-                    const long long a = row_a[i], z = a + row_n[i];
-                    for (long long e = a + lane; e < z; e += 32) {
-                        const float v = data[e];
-                        if (v != 0.0f) vals[atomicAdd(&hist[indices[e] - gene_lb - g0], 1u)] = v;
+                for (int i = rc + (t >> 3); i < re; i += CSR_THREADS / 8) {
+                    const long long a = row_a[i];
+                    const int nrow = row_n[i];
+                    for (int e0 = (t & 7); e0 < nrow; e0 += 32) {
+                        float d[4];
+                        int c[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int ee = e0 + 8 * u;
+                            d[u] = (ee < nrow) ? data[a + ee] : 0.0f;
+                            c[u] = (ee < nrow) ? indices[a + ee] : 0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (d[u] != 0.0f) vals[atomicAdd(&hist[c[u] - gene_lb - g0], 1u)] = d[u];
                     }
                 }
                 __syncthreads();

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import warnings
 from dataclasses import dataclass
 
 import numpy as np
@@ -197,7 +198,9 @@ def upload_dense(X: np.ndarray, device, gene_lb: int = 0, gene_ub: int | None = 
     gene_ub = N if gene_ub is None else gene_ub
     view = X[:, gene_lb:gene_ub]
     with torch.cuda.device(device):
-        t = torch.from_numpy(view) if isinstance(view, np.ndarray) else view
+        with warnings.catch_warnings():  # read-only inputs (memmap, backed arrays) are only read from
+            warnings.simplefilter("ignore", UserWarning)
+            t = torch.from_numpy(view) if isinstance(view, np.ndarray) else view
         raw = None
         if t.dtype == torch.float32:
             d = torch.empty((n, gene_ub - gene_lb), dtype=torch.float32, device=device)
@@ -228,8 +231,10 @@ def _dense_block_f64(M: DeviceMatrix, lb: int, ub: int) -> torch.Tensor:
     if M.fmt == CSC:
         lo, hi = int(M.indptr[lb]), int(M.indptr[ub])
         ptr = (M.indptr[lb:ub + 1] - lo)
-        t = torch.sparse_csc_tensor(ptr, M.indices[lo:hi].to(torch.int64), M.raw[lo:hi], size=(n, ub - lb))
-        return t.to_dense()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)  # "sparse CSC support is in beta"
+            t = torch.sparse_csc_tensor(ptr, M.indices[lo:hi].to(torch.int64), M.raw[lo:hi], size=(n, ub - lb))
+            return t.to_dense()
     # CSR: rows x all genes -> dense columns of the batch
     cols = M.indices.to(torch.int64)
     sel = (cols >= lb) & (cols < ub)
