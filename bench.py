@@ -303,15 +303,22 @@ def main():
     e2e = None
     extra = {}
     if not a.no_e2e:
+        def host_buffer(shape, dtype):
+            try:
+                return torch.empty(shape, dtype=dtype, pin_memory=True)
+            except RuntimeError:  # not enough lockable memory on this host: pageable (slower H2D, still end to end)
+                extra["host_memory"] = "pageable"
+                return torch.empty(shape, dtype=dtype)
+
         if fmt == "dense":
-            hostX = torch.empty((a.cells, a.genes), dtype=torch.float32, pin_memory=True)
+            hostX = host_buffer((a.cells, a.genes), torch.float32)
             hostX.copy_(Xdev)
             Xh = hostX.numpy()
             h2d = Xh.nbytes
         else:
             from scipy import sparse
 
-            pins = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (M.data, M.indices, sp.crow_indices().to(torch.int32))]
+            pins = [host_buffer(t.shape, t.dtype) for t in (M.data, M.indices, sp.crow_indices().to(torch.int32))]
             for p_, t_ in zip(pins, (M.data, M.indices, sp.crow_indices().to(torch.int32))):
                 p_.copy_(t_)
             Xh = sparse.csr_matrix((pins[0].numpy(), pins[1].numpy(), pins[2].numpy()), shape=(a.cells, a.genes))
