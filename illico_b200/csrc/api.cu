@@ -32,6 +32,7 @@ int launch_ovr(const float*, const uint32_t*, int, const illico_plan_t*, const i
 int launch_ovo(const float*, const uint32_t*, int, const illico_plan_t*, const illico_flags_t*, double*, long long, void*,
                size_t, const illico_debug_t*, cudaStream_t);
 size_t ovr_slab_qwords(const illico_plan_t*);
+size_t ovr_table_rec_bytes(const illico_plan_t*);
 
 static int check_plan(const illico_plan_t* p) {
     if (!p) { set_error("plan is NULL"); return 1; }
@@ -113,6 +114,7 @@ size_t illico_rank_workspace_bytes(const illico_plan_t* plan, int32_t n_genes_ba
     size_t per_cta = plan->ref_group >= 0 ? 4 * (size_t)plan->max_group_size * sizeof(uint32_t)
                                           : ovr_slab_qwords(plan) * 8;
     size_t rank = ctas * per_cta + 256 + (((size_t)(n_genes_batch > 0 ? n_genes_batch : 1) + 64) * sizeof(int) + 255);
+    if (plan->ref_group < 0) rank += 2 * ctas * ovr_table_rec_bytes(plan) + 256;  // table kernel: up to 8 CTAs per SM
     size_t stage = stage_csr_workspace_bytes(plan, n_genes_batch);  // CSR staging reuses the same scratch
     return rank > stage ? rank : stage;
 }

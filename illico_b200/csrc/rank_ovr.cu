@@ -33,6 +33,7 @@ constexpr int T_SLOTS = 32;     // slots of the small value table (also the bins
 constexpr int T_CAP = 20;       // most distinct values the table kernel takes
 constexpr int T_WORDS = T_SLOTS / 2;  // two 16-bit bins per 32-bit word
 constexpr int T_MULTI = 256;    // multi-segment groups handed to whole warps per gene (more are ranked inline)
+constexpr int T_REC_WORDS = T_SLOTS / 4;  // segment record: one 8-bit bin per table slot = 32 bytes (one sector)
 
 struct OvrParams {
     const float* ir_vals;
@@ -50,6 +51,8 @@ struct OvrParams {
     long long* dbg_tie_exact;
     int* todo;        // genes the table kernel could not take (NULL: the general kernel ranks every gene)
     int* todo_count;
+    uint4* table_rec;          // table kernel: per-CTA [n_segments][2] segment records (NULL: second pass re-reads the values)
+    long long table_rec_stride;  // uint4 per CTA
 };
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key) { return (key * 2654435761u) >> 20; }  // 12 bits
@@ -344,21 +347,26 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Table kernel: genes with a handful of distinct non-zero values (raw counts).  Small CTAs, almost no shared
+// Table kernel: genes with a handful of distinct non-zero values (raw counts).  Small CTAs, little shared
 // memory, so ~8 genes are in flight per SM and the dependent global loads of one gene overlap with the work
 // of the others.  Per gene:
 //   pass 1  one thread per segment: every value is looked up in a 32-slot shared table (unseen values are
-//           inserted), a private 16-bit histogram is bumped and then added to the column's multiplicities;
+//           inserted) and bumps an 8-bit bin of the segment's histogram.  The finished histogram (32 bytes, one
+//           sector) goes to the CTA's record area in global memory -- it is re-read a moment later, normally from
+//           L2 -- and is added to the thread's 16-bit column accumulators;
 //   finish  thread 0 sorts the <= 20 values, turns multiplicities into doubled mid-ranks, tie sum, totals;
-//   pass 2  one thread per group: sum of the looked-up doubled mid-ranks and expression values -> 2U, p, fold
-//           change (the rest-of-cells total comes from the table, so there is no second sweep over groups).
-// A gene with more distinct values is appended to `todo` for the general kernel.
+//   pass 2  one thread per group: sum over the group's segment histograms of count x doubled mid-rank and
+//           count x expression value -> 2U, p, fold change.  The staged values are read ONCE.
+// A segment with more than 255 stored values could overflow an 8-bit bin: such a gene keeps 16-bit bins only
+// and its second pass re-reads the values (the round-1 two-pass scheme).  A gene with more distinct values is
+// appended to `todo` for the general kernel.
 __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams P) {
     __shared__ uint32_t tkey[T_SLOTS];      // raw float bits, 0 = empty
     __shared__ uint32_t gcount[T_SLOTS];    // multiplicity in the whole column
     __shared__ uint32_t r2slot[T_SLOTS];    // doubled mid-rank of the slot's value
     __shared__ double fcslot[T_SLOTS];      // f(x) of the slot's value
-    __shared__ uint32_t bins[T_WORDS][T_THREADS];
+    __shared__ uint32_t bins[T_WORDS][T_THREADS];      // 16-bit column accumulators: word 2q+r = slots 4q+r, 4q+r+2
+    __shared__ uint32_t seg8[T_REC_WORDS][T_THREADS];  // 8-bit bins of the segment in progress: word q = slots 4q..4q+3
     __shared__ unsigned long long redu[8];
     __shared__ double redd[4];
     __shared__ int sc[4];
@@ -368,31 +376,33 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
     const int S = pl.n_segments, G = pl.n_groups;
     const long long n = pl.n_cells;
     const double cc = P.flags.use_continuity ? 0.5 : 0.0;
+    uint4* rec = P.table_rec ? P.table_rec + (long long)blockIdx.x * P.table_rec_stride : nullptr;
 
     for (int j = blockIdx.x; j < P.n_genes; j += gridDim.x) {
         const uint32_t* cnt = P.ir_cnt + (long long)j * S;
         const float* vals = P.ir_vals + (long long)j * pl.slot_cap;
         __syncthreads();
         if (tid < T_SLOTS) { tkey[tid] = 0u; gcount[tid] = 0u; }
-        if (tid < 4) sc[tid] = 0;  // [0] distinct [1] overflow
+        if (tid < 4) sc[tid] = 0;  // [0] distinct [1] overflow [2] multi-segment groups [3] gene has a wide segment
         __syncthreads();
         // ================= pass 1 =================
-        // The private 16-bit bins accumulate over all of the thread's segments and are added to the column's
-        // multiplicities once (or whenever a bin could overflow).
         unsigned long long my_nnz = 0;
         uint32_t since_flush = 0;
         auto flush_bins = [&]() {
 #pragma unroll 4
-            for (int q = 0; q < T_WORDS; ++q) {
-                const uint32_t w2 = bins[q][tid];
-                if (w2 & 0xffffu) atomicAdd(&gcount[2 * q], w2 & 0xffffu);
-                if (w2 >> 16) atomicAdd(&gcount[2 * q + 1], w2 >> 16);
-                bins[q][tid] = 0u;
+            for (int a = 0; a < T_WORDS; ++a) {
+                const uint32_t w2 = bins[a][tid];
+                const int lo_slot = 4 * (a >> 1) + (a & 1);
+                if (w2 & 0xffffu) atomicAdd(&gcount[lo_slot], w2 & 0xffffu);
+                if (w2 >> 16) atomicAdd(&gcount[lo_slot + 2], w2 >> 16);
+                bins[a][tid] = 0u;
             }
             since_flush = 0;
         };
 #pragma unroll
-        for (int q = 0; q < T_WORDS; ++q) bins[q][tid] = 0u;
+        for (int a = 0; a < T_WORDS; ++a) bins[a][tid] = 0u;
+#pragma unroll
+        for (int q = 0; q < T_REC_WORDS; ++q) seg8[q][tid] = 0u;
         bool ok = true;
         for (int s = tid; s < S && ok; s += T_THREADS) {
             if (*(volatile int*)&sc[1]) break;
@@ -400,6 +410,8 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
             if (since_flush + (uint32_t)c > 60000u) flush_bins();
             since_flush += (uint32_t)c;
             my_nnz += c;
+            const bool narrow = rec != nullptr && c <= 255;   // 8-bit bins cannot overflow
+            if (!narrow) sc[3] = 1;
             const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);  // 32-byte aligned, padded slot
             float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
             for (int i = 0; i < c && ok; i += 4) {
@@ -425,9 +437,26 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
                             h = (h + 1) & (T_SLOTS - 1);
                             if (++probes > T_SLOTS) { sc[1] = 1; ok = false; break; }
                         }
-                        if (ok) bins[h >> 1][tid] += 1u << ((h & 1u) << 4);
+                        if (ok) {
+                            if (narrow) seg8[h >> 2][tid] += 1u << ((h & 3u) << 3);
+                            else bins[((h >> 2) << 1) | (h & 1u)][tid] += 1u << ((h & 2u) << 3);
+                        }
                     }
                 }
+            }
+            if (narrow && ok) {
+                uint32_t r[T_REC_WORDS];
+#pragma unroll
+                for (int q = 0; q < T_REC_WORDS; ++q) {
+                    r[q] = seg8[q][tid];
+                    if (r[q]) {
+                        seg8[q][tid] = 0u;
+                        bins[2 * q][tid] += r[q] & 0x00ff00ffu;
+                        bins[2 * q + 1][tid] += (r[q] >> 8) & 0x00ff00ffu;
+                    }
+                }
+                __stcg(rec + 2 * (long long)s, make_uint4(r[0], r[1], r[2], r[3]));
+                __stcg(rec + 2 * (long long)s + 1, make_uint4(r[4], r[5], r[6], r[7]));
             }
         }
         if (ok) flush_bins();
@@ -439,6 +468,7 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
             if (tid == 0) P.todo[atomicAdd(P.todo_count, 1)] = j;
             continue;
         }
+        const bool from_records = sc[3] == 0;   // every segment left a histogram record
         const long long nnz = (long long)(redu[0] + redu[1] + redu[2] + redu[3]);
         const long long n0 = n - nnz;
         // ================= finish the table (thread 0; <= 20 entries) =================
@@ -492,7 +522,7 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
         const double tie = redd[0], total = redd[1];
         const unsigned long long r2_zero = 2ull * redu[5] + (unsigned long long)n0 + 1ull;
         // ================= pass 2: one thread per single-segment group, one warp per multi-segment group =========
-        auto rank_segment = [&](int s, unsigned long long& R2, double& sum, long long& nnz_g) {
+        auto rank_values = [&](int s, unsigned long long& R2, double& sum, long long& nnz_g) {
             const int c = (int)cnt[s];
             nnz_g += c;
             const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);
@@ -513,6 +543,26 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
                 }
             }
         };
+        auto rank_record = [&](int s, unsigned long long& R2, double& sum, long long& nnz_g) {
+            const uint4 ra = __ldcg(rec + 2 * (long long)s), rb = __ldcg(rec + 2 * (long long)s + 1);
+            const uint32_t r[T_REC_WORDS] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int q = 0; q < T_REC_WORDS; ++q) {
+                uint32_t x = r[q];
+                while (x) {  // the non-empty bins of this word (a segment holds a few distinct values)
+                    const int byte = (__ffs(x) - 1) >> 3;
+                    const uint32_t bq = (x >> (byte << 3)) & 0xffu;
+                    x &= ~(0xffu << (byte << 3));
+                    const int h = 4 * q + byte;
+                    R2 += (unsigned long long)bq * r2slot[h];
+                    sum += (double)bq * fcslot[h];
+                    nnz_g += bq;
+                }
+            }
+        };
+        auto rank_segment = [&](int s, unsigned long long& R2, double& sum, long long& nnz_g) {
+            if (from_records) rank_record(s, R2, sum, nnz_g); else rank_values(s, R2, sum, nnz_g);
+        };
         auto finish_group = [&](int g, unsigned long long R2, double sum, long long nnz_g) {
             const long long n_t = pl.group_size[g], n_r = n - n_t;
             R2 += (unsigned long long)(n_t - nnz_g) * r2_zero;
@@ -526,8 +576,6 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
             o[0] = p; o[1] = U; o[2] = (mu_r == 0.0) ? INFINITY : mu_t / mu_r;
             if (P.dbg_u2) P.dbg_u2[(long long)g * P.n_genes + j] = u2;
         };
-        if (tid == 0) sc[2] = 0;  // multi-segment groups found so far
-        __syncthreads();
         for (int g = tid; g < G; g += T_THREADS) {
             const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
             if (s1 - s0 > 1) {  // big group: leave it to a whole warp (one lane per segment)
@@ -559,6 +607,9 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
         }
     }
 }
+
+size_t ovr_table_rec_bytes(const illico_plan_t* plan) { return (size_t)plan->n_segments * 32; }  // per table-kernel CTA
+constexpr int T_MAX_CTAS_PER_SM = 8;
 
 size_t ovr_slab_qwords(const illico_plan_t* plan) {
     return 2 * (size_t)plan->n_segments + (size_t)((plan->n_cells + 1) & ~1) + 2;
@@ -613,13 +664,23 @@ int launch_ovr(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const 
     P.slab = (unsigned long long*)workspace; P.slab_qwords = (long long)slab_q;
     const char* tenv = getenv("ILLICO_OVR_TABLE");
     const bool use_table = flags->group_sums == nullptr && !(tenv && atoi(tenv) == 0);
+    P.table_rec = nullptr; P.table_rec_stride = 0;
     if (use_table) {
         P.todo = todo; P.todo_count = todo_count;
         ILLICO_CUDA_OK(cudaMemsetAsync(todo_count, 0, sizeof(int), stream));
         int tocc = 0;
         ILLICO_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tocc, ovr_table_kernel, T_THREADS, 0));
+        if (tocc > T_MAX_CTAS_PER_SM) tocc = T_MAX_CTAS_PER_SM;
         int tgrid = sms * (tocc > 0 ? tocc : 1);
         if (tgrid > n_genes) tgrid = n_genes;
+        // segment-record area of the table kernel: behind the general kernel's slabs (both kernels may be resident)
+        const size_t slabs = ((size_t)grid * slab_q * 8 + 255) & ~(size_t)255;
+        const size_t rec_cta = ovr_table_rec_bytes(plan);
+        const char* renv = getenv("ILLICO_OVR_RECORDS");
+        if (!(renv && atoi(renv) == 0) && workspace_bytes >= slabs + (size_t)tgrid * rec_cta) {
+            P.table_rec = reinterpret_cast<uint4*>(reinterpret_cast<char*>(workspace) + slabs);
+            P.table_rec_stride = (long long)(rec_cta / 16);
+        }
         ovr_table_kernel<<<tgrid, T_THREADS, 0, stream>>>(P);
         count_launch();
         ILLICO_CUDA_OK(cudaGetLastError());
