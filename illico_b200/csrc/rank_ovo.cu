@@ -147,10 +147,11 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
     double* redd = (double*)(counters + 8);                 // [32]
     unsigned long long* redu = (unsigned long long*)(redd + 32);  // [32]
     double* dval = (double*)(redu + 32);                    // [DT_CAP]   f(x) of each distinct control value
-    uint32_t* dkey = (uint32_t*)(dval + DT_CAP);            // [DT_CAP]   distinct control keys, ascending
+    unsigned long long* dw = (unsigned long long*)(dval + DT_CAP);  // [DT_CAP] 2 #{ref > v} + a
+    unsigned long long* dA3 = dw + DT_CAP;                  // [DT_CAP]   3 a^2 - 1
+    uint2* hkv = (uint2*)(dA3 + DT_CAP);                    // [DT_HASH]  open-addressed {float bits, byte offset of the bin}
+    uint32_t* dkey = (uint32_t*)(hkv + DT_HASH);            // [DT_CAP]   distinct control keys, ascending
     int* dlo = (int*)(dkey + DT_CAP);                       // [DT_CAP+1] first position of each in the sorted control
-    uint32_t* hkey = (uint32_t*)(dlo + DT_CAP + 1);         // [DT_HASH]  open-addressed key -> table index
-    int* hidx = (int*)(hkey + DT_HASH);                     // [DT_HASH]
 
     uint32_t* slab = P.slab + (long long)blockIdx.x * P.slab_words;
     const int maxg = pl.max_group_size;
@@ -239,16 +240,23 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 dlo[q + 1] = l; dkey[q + 1] = k;
             }
             dlo[D] = nref_nz;
-            for (int a = 0; a < DT_HASH; ++a) hkey[a] = 0u;  // 0 is never a key of a finite value
+            for (int a = 0; a < DT_HASH; ++a) hkv[a] = make_uint2(0u, 0u);  // +0.0f is never staged
             for (int a = 0; a < D; ++a) {
-                dval[a] = fc_value(key2f(dkey[a]), P.flags.is_log1p);
-                uint32_t h = (dkey[a] * 2654435761u) >> 26;
-                while (hkey[h] != 0u) h = (h + 1) & (DT_HASH - 1);
-                hkey[h] = dkey[a];
-                hidx[h] = a * OVO_THREADS;
+                const float v = key2f(dkey[a]);
+                dval[a] = fc_value(v, P.flags.is_log1p);
+                const unsigned long long mult = (unsigned long long)(dlo[a + 1] - dlo[a]);
+                const unsigned long long gt = (unsigned long long)(nref_nz - dlo[a + 1]) +
+                                              ((dkey[a] < KEY_ZERO) ? (unsigned long long)R.zeros : 0ull);
+                dw[a] = 2ull * gt + mult;
+                dA3[a] = 3ull * mult * mult - 1ull;
+                const uint32_t bits = __float_as_uint(v);
+                uint32_t h = (bits * 2654435761u) >> 26;
+                while (hkv[h].x != 0u) h = (h + 1) & (DT_HASH - 1);
+                hkv[h] = make_uint2(bits, (uint32_t)(a * OVO_THREADS * 4));
             }
         }
         __syncthreads();
+        const uint32_t hkv_s = (uint32_t)__cvta_generic_to_shared(hkv);
 
         // ================= phase 2: perturbations, in chunks of GROUP_CHUNK groups =================
         for (int g0 = 0; g0 < G; g0 += GROUP_CHUNK) {
@@ -279,54 +287,66 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                     // ---- table path: private histogram over the control's distinct values
                     for (int t = 0; t < D; ++t) col[t * OVO_THREADS] = 0;
                     bool ok = true;
-                    int ne = 0;                                   // values the control does not have: (key, count)
+                    int ne = 0;                                   // values the control does not have: (bits, count)
                     const int ne_cap = (P.small_cap - D) >> 1;    // pairs kept after the D histogram bins
-                    for (int s = s0; s < s1 && ok; ++s) {
-                        const int c = (int)cnt[s];
-                        const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);  // 32-byte aligned slot
-                        float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int i = 0; i < c; i += 4) {
-                            const float4 q4 = nxt;
-                            if (i + 4 < c) nxt = src4[(i >> 2) + 1];  // next 16 bytes are in flight while these are ranked
-                            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                if (i + e < c) {
-                                    const uint32_t key = f2key(q[e]);
-                                    uint32_t h = (key * 2654435761u) >> 26;
-                                    uint32_t hk = hkey[h];
-                                    while (hk != key && hk != 0u) { h = (h + 1) & (DT_HASH - 1); hk = hkey[h]; }
-                                    if (hk == key) {
-                                        col[hidx[h]] += 1;  // hidx holds bin * OVO_THREADS (private bin; shared atomics are slower)
-                                    } else {
-                                        int x = 0;
-                                        while (x < ne && col[(D + 2 * x) * OVO_THREADS] != key) ++x;
-                                        if (x < ne) col[(D + 2 * x + 1) * OVO_THREADS] += 1;
-                                        else if (ne < ne_cap) {
-                                            col[(D + 2 * ne) * OVO_THREADS] = key;
-                                            col[(D + 2 * ne + 1) * OVO_THREADS] = 1;
-                                            ++ne;
-                                        } else ok = false;
-                                    }
-                                }
+                    const uint32_t col_s = (uint32_t)__cvta_generic_to_shared(col);
+                    // one stored value: hash probe (one 64-bit shared load on a hit) + bump of the private bin
+                    auto bump = [&](float v) {
+                        const uint32_t bits = __float_as_uint(v);
+                        uint32_t h = (bits * 2654435761u) >> 26;
+                        uint32_t k, off;
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(k), "=r"(off) : "r"(hkv_s + h * 8u));
+                        if (k != bits) {  // collision chain, or a value the control does not have (rare)
+                            while (k != bits && k != 0u) {
+                                h = (h + 1) & (DT_HASH - 1);
+                                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(k), "=r"(off) : "r"(hkv_s + h * 8u));
+                            }
+                            if (k == 0u) {
+                                int x = 0;
+                                while (x < ne && col[(D + 2 * x) * OVO_THREADS] != bits) ++x;
+                                if (x < ne) col[(D + 2 * x + 1) * OVO_THREADS] += 1;
+                                else if (ne < ne_cap) {
+                                    col[(D + 2 * ne) * OVO_THREADS] = bits;
+                                    col[(D + 2 * ne + 1) * OVO_THREADS] = 1;
+                                    ++ne;
+                                } else ok = false;
+                                return;
                             }
                         }
+                        uint32_t r;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(col_s + off) : "memory");
+                        asm volatile("st.shared.u32 [%0], %1;" :: "r"(col_s + off), "r"(r + 1u) : "memory");
+                    };
+                    for (int s = s0; s < s1; ++s) {
+                        const int c = (int)cnt[s];
+                        const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);  // 32-byte aligned slot
+                        const int nfull = c >> 2;
+                        float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int i4 = 0; i4 < nfull; ++i4) {
+                            const float4 q4 = nxt;
+                            if (4 * i4 + 4 < c) nxt = src4[i4 + 1];  // next 16 bytes are in flight while these are ranked
+                            bump(q4.x); bump(q4.y); bump(q4.z); bump(q4.w);
+                        }
+                        const int rem = c & 3;
+                        if (rem > 0) bump(nxt.x);
+                        if (rem > 1) bump(nxt.y);
+                        if (rem > 2) bump(nxt.z);
                     }
                     if (ok) {
                         unsigned long long u2 = 0, tie = 0;
                         double sum = 0.0;
                         for (int t = 0; t < D; ++t) {
-                            const long long bq = col[t * OVO_THREADS];
+                            const uint32_t bq = col[t * OVO_THREADS];
                             if (bq) {
-                                const long long a = dlo[t + 1] - dlo[t];
-                                const long long gt = (long long)(nref_nz - dlo[t + 1]) + ((dkey[t] < KEY_ZERO) ? R.zeros : 0);
-                                u2 += (unsigned long long)(bq * (2 * gt + a));
-                                tie += (unsigned long long)(cube_minus(a + bq) - cube_minus(a));
+                                // b (2 gt + a)  and  (a+b)^3 - (a+b) - (a^3 - a) = b (3a^2 - 1 + b (3a + b))
+                                const uint32_t a3 = 3u * (uint32_t)(dlo[t + 1] - dlo[t]);
+                                u2 += (unsigned long long)bq * dw[t];
+                                tie += (unsigned long long)bq * (dA3[t] + (unsigned long long)bq * (unsigned long long)(a3 + bq));
                                 sum += (double)bq * dval[t];
                             }
                         }
                         for (int x = 0; x < ne; ++x) {  // absent from the control: a = 0, position by binary search
-                            const uint32_t key = col[(D + 2 * x) * OVO_THREADS];
+                            const uint32_t key = f2key(__uint_as_float(col[(D + 2 * x) * OVO_THREADS]));
                             const long long bq = col[(D + 2 * x + 1) * OVO_THREADS];
                             const long long gt = (long long)(nref_nz - lower_bound_u32(rA, nref_nz, key)) +
                                                  ((key < KEY_ZERO) ? R.zeros : 0);
@@ -478,8 +498,8 @@ static int launch_ovo_t(OvoParams& P, const illico_plan_t* plan, void* workspace
     constexpr int NW = NT / 32;
     // shared memory: fixed part + control buffer + scratch.  Genes whose control has more non-zeros than ref_cap
     // keep the control in the CTA's global slab.
-    const size_t fixed = (size_t)(NW * 256 + RADIX_AUX_WORDS + GROUP_CHUNK + 8) * 4 + 32 * 8 * 2 + DT_CAP * 8 +
-                         (2 * DT_CAP + 1) * 4 + 2 * DT_HASH * 4 + 64;
+    const size_t fixed = (size_t)(NW * 256 + RADIX_AUX_WORDS + GROUP_CHUNK + 8) * 4 + 32 * 8 * 2 + 3 * DT_CAP * 8 +
+                         (2 * DT_CAP + 1) * 4 + DT_HASH * 8 + 64;
     const int small_cap = DT_CAP;
     int scratch_words = small_cap * NT;               // thread tier: small_cap keys per thread
     if (scratch_words < 2 * WARP_CAP) scratch_words = 2 * WARP_CAP;  // at least two warp-tier buffers
