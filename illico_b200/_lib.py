@@ -56,6 +56,7 @@ SIGNATURES = {
     "illico_abi_version": (C.c_int, []),
     "illico_last_error": (C.c_char_p, []),
     "illico_launch_count": (_i64, []),
+    "illico_last_fused_ms": (C.c_double, []),
     "illico_stage_dense_f32": (C.c_int, [_vp, _i64, _i32, _i32, _PP, _vp, _vp, _vp]),
     "illico_stage_csr_workspace_bytes": (_sz, [_PP, _i32]),
     "illico_stage_csr_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _PP, _vp, _vp, _vp, _sz, _vp]),

@@ -387,7 +387,7 @@ static void launch_stage_dense_t(dim3 grid, cudaStream_t stream, const float* X,
 // stage_dense_tma.cu
 bool stage_dense_tma_ok(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan);
 int launch_stage_dense_tma(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
-                           uint32_t* ir_cnt, cudaStream_t stream);
+                           uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream);
 
 int launch_stage_dense(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
                        uint32_t* ir_cnt, cudaStream_t stream) {
@@ -395,7 +395,7 @@ int launch_stage_dense(const float* X, long long ld, int gene_lb, int b, const i
     if (ld <= 0 || ld >= (1ll << 30)) { set_error("leading dimension %lld out of range", ld); return 1; }
     // 16-byte aligned batches: rows come in through the TMA engine; anything else takes the plain-load kernel below
     if (stage_dense_tma_ok(X, ld, gene_lb, b, plan)) {
-        const int rc = launch_stage_dense_tma(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, stream);
+        const int rc = launch_stage_dense_tma(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, 0, plan->n_segments, stream);
         if (rc >= 0) return rc;
     }
     const int S = plan->n_segments;

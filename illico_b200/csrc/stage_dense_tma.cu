@@ -13,6 +13,7 @@
 // 8 + ROWS entries and is inspected once per ring stage instead of once per element, which removes the divergent
 // flush branch from the per-element path (it was a third of the old kernel's instructions).
 #include "common.cuh"
+#include "tma.cuh"
 
 #include <stdlib.h>
 
@@ -24,36 +25,6 @@ constexpr int TMA_CONSUMER_WARPS = 8;
 constexpr int TMA_CONSUMERS = TMA_CONSUMER_WARPS * 32;
 constexpr int TMA_THREADS = TMA_CONSUMERS + 32;   // + one producer warp
 constexpr int TMA_MAX_SEGS = 16;
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); the input is read once,
-// so it is marked evict-first in L2
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
-        : "memory");
-}
 
 // Lane-private compaction buffer: ENTRIES floats per (thread, gene stream), contiguous per lane.
 __device__ __forceinline__ void append_nz(uint32_t& off, float v, uint32_t buf) {
@@ -97,7 +68,8 @@ template <int VEC, int ROWS, int STAGES>
 __global__ void __launch_bounds__(TMA_THREADS) stage_dense_tma_kernel(const float* __restrict__ X, long long ld, int gene_lb,
                                                                       int b, const illico_plan_t pl,
                                                                       float* __restrict__ ir_vals,
-                                                                      uint32_t* __restrict__ ir_cnt, int segs_per_cta, int no_store) {
+                                                                      uint32_t* __restrict__ ir_cnt, int segs_per_cta, int seg_lo,
+                                                                      int seg_hi, int no_store) {
     using L = TmaLayout<VEC, ROWS, STAGES>;
     static_assert(32 % ROWS == 0, "a 32-row group of the permutation holds whole stages");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -106,7 +78,7 @@ __global__ void __launch_bounds__(TMA_THREADS) stage_dense_tma_kernel(const floa
     uint16_t* cnt_tile = reinterpret_cast<uint16_t*>(smem + L::CNT_OFF);
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int S = pl.n_segments;
-    const int s_begin = blockIdx.y * segs_per_cta, s_end = min(S, s_begin + segs_per_cta);
+    const int s_begin = seg_lo + blockIdx.y * segs_per_cta, s_end = min(seg_hi, s_begin + segs_per_cta);
     const int p_begin = pl.seg_pos[s_begin], p_end = pl.seg_pos[s_end];
     const int g0 = blockIdx.x * L::GENES;                      // first gene of the CTA inside the batch
     // bytes of the row piece this CTA reads: whole 16-byte units (the host checked that the round-up stays in the row)
@@ -267,15 +239,14 @@ int env_int(const char* name, int dflt) {
 
 template <int VEC, int ROWS, int STAGES>
 int launch_t(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt,
-             int segs_per_cta, cudaStream_t stream) {
+             int segs_per_cta, int seg_lo, int seg_hi, cudaStream_t stream) {
     using L = TmaLayout<VEC, ROWS, STAGES>;
-    const int S = plan->n_segments;
     const unsigned gx = (unsigned)((b + L::GENES - 1) / L::GENES);
-    const unsigned gy = (unsigned)((S + segs_per_cta - 1) / segs_per_cta);
+    const unsigned gy = (unsigned)((seg_hi - seg_lo + segs_per_cta - 1) / segs_per_cta);
     const size_t smem = L::bytes(segs_per_cta);
     auto kern = stage_dense_tma_kernel<VEC, ROWS, STAGES>;
     ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(gx, gy), TMA_THREADS, smem, stream>>>(X, ld, gene_lb, b, *plan, ir_vals, ir_cnt, segs_per_cta,
+    kern<<<dim3(gx, gy), TMA_THREADS, smem, stream>>>(X, ld, gene_lb, b, *plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi,
                                                       env_int("ILLICO_STAGE_TMA_NOSTORE", 0));  // measurement aid: read path alone
     count_launch();
     ILLICO_CUDA_OK(cudaGetLastError());
@@ -293,9 +264,12 @@ bool stage_dense_tma_ok(const float* X, long long ld, int gene_lb, int b, const 
     return true;
 }
 
+// Stages segments [seg_lo, seg_hi) of the plan (the whole plan: 0, n_segments; the control group alone for the fused
+// one-versus-reference path).
 int launch_stage_dense_tma(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
-                           uint32_t* ir_cnt, cudaStream_t stream) {
+                           uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream) {
     const int S = plan->n_segments;
+    if (seg_lo < 0 || seg_hi > S || seg_lo >= seg_hi) { set_error("segment range [%d, %d) out of bounds", seg_lo, seg_hi); return 1; }
     long long avg = plan->n_cells / S;
     if (avg < 1) avg = 1;
     int segs_per_cta = (int)(env_int("ILLICO_STAGE_ROWS", 512) / avg);
@@ -305,10 +279,10 @@ int launch_stage_dense_tma(const float* X, long long ld, int gene_lb, int b, con
     // Ring configurations measured at the K562 shape (profiles/README.md): all within 3 % of each other; one gene
     // per lane (1 KB row pieces, 32 KB ring, 2-3 CTAs per SM) is the fastest and has the smallest footprint.
     switch (env_int("ILLICO_STAGE_TMA_CFG", 0)) {
-        case 1: return launch_t<2, 4, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, stream);
-        case 2: return launch_t<2, 8, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, stream);
-        case 3: return launch_t<4, 4, 3>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, stream);
-        default: return launch_t<1, 8, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, stream);
+        case 1: return launch_t<2, 4, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream);
+        case 2: return launch_t<2, 8, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream);
+        case 3: return launch_t<4, 4, 3>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream);
+        default: return launch_t<1, 8, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream);
     }
 }
 

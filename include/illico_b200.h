@@ -108,6 +108,9 @@ int illico_abi_version(void);
 const char* illico_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t illico_launch_count(void);
+/* with ILLICO_PROFILE=1 in the environment: duration (ms, CUDA events on the caller's stream) of the last
+ * ovo_fused_kernel launch of this thread, -1 if none (bench.py's roofline) */
+double illico_last_fused_ms(void);
 
 /* ---- staging: input formats -> group-segmented non-zero lists ------------------------------- */
 
