@@ -39,7 +39,7 @@ int launch_ovo(const float*, const uint32_t*, int, const illico_plan_t*, const i
                size_t, const illico_debug_t*, cudaStream_t);
 bool stage_dense_tma_ok(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan);
 int launch_stage_dense_tma(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
-                           uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream);
+                           uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream, int segs_per_cta = 0);
 
 namespace {
 
@@ -152,8 +152,8 @@ struct FusedLayout {
     static constexpr int BYTES = BAR_OFF + 2 * STAGES * 8;
 };
 
-template <int ROWS, int STAGES, int DCAP, int BUF>
-__global__ void __launch_bounds__(FUSED_THREADS, 3) ovo_fused_kernel(const float* __restrict__ X, long long ld, int gene_lb, int b,
+template <int ROWS, int STAGES, int DCAP, int BUF, int MINB>
+__global__ void __launch_bounds__(FUSED_THREADS, MINB) ovo_fused_kernel(const float* __restrict__ X, long long ld, int gene_lb, int b,
                                                                   const illico_plan_t pl, int groups_per_cta, int is_log1p,
                                                                   Ctab ct, int bstride, unsigned long long* __restrict__ rec,
                                                                   long long gstride) {
@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) ovo_fused_kernel(const float
             if (ref_in && p >= ref_p0) p += ref_len;
             return pl.perm[p];
         };
+        // (reading the permutation two groups ahead, or the group boundaries one group ahead, measured 5-10 % slower)
         int myrow = (lane < nv) ? row_of(lane) : 0;
         int k = 0;
         for (int i0 = 0; i0 < nv; i0 += 32) {
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) ovo_fused_kernel(const float
     // folds the group's histogram into exact integers and writes the 24-byte record
     auto close_group = [&](int g) {
         drain();
-        uint32_t a[DCAP];
+        uint32_t a[DCAP];                                     // control multiplicities (L2 resident, coalesced over lanes)
 #pragma unroll
         for (int q = 0; q < DCAP; ++q) a[q] = (q < Dc) ? __ldg(gmult + (long long)q * bstride) : 0u;
         unsigned long long u2 = 0, tie = 0, gt = 0;
@@ -316,9 +317,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) ovo_fused_kernel(const float
             o[2] = (unsigned long long)__double_as_longlong(sum);
         }
     };
-    int g = gy0;
-    if (g == ref) ++g;
     auto group_end_v = [&](int gg) { return pl.seg_pos[pl.group_seg[gg + 1]] - p_begin - ((ref_in && gg > ref) ? ref_len : 0); };
+    int g = (gy0 == ref) ? gy0 + 1 : gy0;
     int gend = group_end_v(g);
 
     auto append = [&](float v) {
@@ -416,11 +416,11 @@ int env_int(const char* name, int dflt) {
 
 thread_local float g_last_fused_ms = -1.0f;
 
-template <int ROWS, int STAGES, int DCAP, int BUF>
+template <int ROWS, int STAGES, int DCAP, int BUF, int MINB>
 int launch_fused_t(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, int gpc, int is_log1p, Ctab ct,
                    int bstride, double* results, long long gstride, cudaStream_t stream) {
     using L = FusedLayout<ROWS, STAGES, DCAP, BUF>;
-    auto kern = ovo_fused_kernel<ROWS, STAGES, DCAP, BUF>;
+    auto kern = ovo_fused_kernel<ROWS, STAGES, DCAP, BUF, MINB>;
     ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
     const dim3 grid((unsigned)((b + FUSED_LANES - 1) / FUSED_LANES), (unsigned)((plan->n_groups + gpc - 1) / gpc));
     kern<<<grid, FUSED_THREADS, L::BYTES, stream>>>(X, ld, gene_lb, b, *plan, gpc, is_log1p, ct, bstride,
@@ -455,7 +455,7 @@ int launch_ovo_dense_fused(const float* X, long long ld, int gene_lb, int b, con
     ILLICO_CUDA_OK(cudaMemsetAsync(ct.n_bad, 0, sizeof(int), stream));
     {
         const int rc = launch_stage_dense_tma(X, ld, gene_lb, b, plan, buf->ir_vals, buf->ir_cnt, plan->ref_seg_begin,
-                                              plan->ref_seg_end, stream);
+                                              plan->ref_seg_end, stream, /*segs_per_cta=*/1);
         if (rc != 0) return rc;
     }
     {
@@ -484,9 +484,15 @@ int launch_ovo_dense_fused(const float* X, long long ld, int gene_lb, int b, con
         ILLICO_CUDA_OK(cudaEventRecord(e0, stream));
     }
     int rc;
-    if (cfg == 1) rc = launch_fused_t<4, 4, 10, 32>(X, ld, gene_lb, b, plan, gpc, flags->is_log1p, ct, bstride, results, gstride, stream);
-    else if (cfg == 2) rc = launch_fused_t<8, 4, 10, 24>(X, ld, gene_lb, b, plan, gpc, flags->is_log1p, ct, bstride, results, gstride, stream);
-    else rc = launch_fused_t<8, 3, 10, 32>(X, ld, gene_lb, b, plan, gpc, flags->is_log1p, ct, bstride, results, gstride, stream);
+#define FUSED_ARGS X, ld, gene_lb, b, plan, gpc, flags->is_log1p, ct, bstride, results, gstride, stream
+    // ring / buffer shapes measured at the K562 shape (profiles/README.md): 5 stages of 8 rows, a 16-entry group
+    // buffer and 3 CTAs per SM is the fastest; 4 CTAs per SM with a 3-stage ring is within 3 % of it
+    switch (cfg) {
+        case 1: rc = launch_fused_t<8, 3, 10, 32, 3>(FUSED_ARGS); break;
+        case 2: rc = launch_fused_t<8, 3, 10, 16, 4>(FUSED_ARGS); break;
+        default: rc = launch_fused_t<8, 5, 10, 16, 3>(FUSED_ARGS); break;
+    }
+#undef FUSED_ARGS
     if (rc) return rc;
     if (timed) ILLICO_CUDA_OK(cudaEventRecord(e1, stream));
     {

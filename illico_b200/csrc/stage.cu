@@ -387,7 +387,7 @@ static void launch_stage_dense_t(dim3 grid, cudaStream_t stream, const float* X,
 // stage_dense_tma.cu
 bool stage_dense_tma_ok(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan);
 int launch_stage_dense_tma(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
-                           uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream);
+                           uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream, int segs_per_cta = 0);
 
 int launch_stage_dense(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
                        uint32_t* ir_cnt, cudaStream_t stream) {

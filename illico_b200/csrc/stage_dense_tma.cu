@@ -267,12 +267,12 @@ bool stage_dense_tma_ok(const float* X, long long ld, int gene_lb, int b, const 
 // Stages segments [seg_lo, seg_hi) of the plan (the whole plan: 0, n_segments; the control group alone for the fused
 // one-versus-reference path).
 int launch_stage_dense_tma(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
-                           uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream) {
+                           uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream, int segs_per_cta_req) {
     const int S = plan->n_segments;
     if (seg_lo < 0 || seg_hi > S || seg_lo >= seg_hi) { set_error("segment range [%d, %d) out of bounds", seg_lo, seg_hi); return 1; }
     long long avg = plan->n_cells / S;
     if (avg < 1) avg = 1;
-    int segs_per_cta = (int)(env_int("ILLICO_STAGE_ROWS", 512) / avg);
+    int segs_per_cta = segs_per_cta_req > 0 ? segs_per_cta_req : (int)(env_int("ILLICO_STAGE_ROWS", 512) / avg);
     if (segs_per_cta < 1) segs_per_cta = 1;
     if (segs_per_cta > TMA_MAX_SEGS) segs_per_cta = TMA_MAX_SEGS;
     if ((S + segs_per_cta - 1) / segs_per_cta > 65535) return -1;      // caller falls back to the plain kernel

@@ -349,3 +349,89 @@ def test_dense_staging_tma_and_plain_paths_agree(monkeypatch, n_genes, batch, te
     g, p, U, fc = oracle.run(X, labels, ref, is_log1p=False)
     ref_row = int(np.searchsorted(groups, ref)) if ref is not None else None
     assert_parity(tma, (p, U, fc), ref_row=ref_row, what=f"tma staging {n_genes}/{batch}/{test}")
+
+
+def _fused_case(kind, n_cells=6000, n_genes=72, seed=31):
+    """Count-like matrix whose genes exercise every route of the fused one-versus-reference path."""
+    rng = np.random.RandomState(seed)
+    X = (rng.poisson(1.0, size=(n_cells, n_genes)) * (rng.rand(n_cells, n_genes) >= 0.7)).astype(np.float32)
+    sizes = rng.randint(3, 400, size=14)
+    codes = np.repeat(np.arange(sizes.size), sizes)
+    codes = np.concatenate([codes, rng.randint(0, sizes.size, size=n_cells - codes.size)])
+    rng.shuffle(codes)
+    labels = [f"g{c:02d}" for c in codes]
+    ref_code = {"first": 0, "last": sizes.size - 1, "middle": 6}[kind.split(":")[0]]
+    ctrl = codes == ref_code
+    X[:, 1] = 0.0                                                   # all-zero gene
+    X[:, 2] = rng.poisson(30.0, n_cells)                            # > 10 distinct control values: handed back
+    X[:, 3] = np.round(rng.gamma(2.0, 2.0, n_cells), 3)             # continuous: handed back
+    X[~ctrl, 4] = rng.poisson(3.0, (~ctrl).sum()) + 20.0            # every perturbation value is absent from the control
+    X[ctrl, 5] = 0.0                                                # control all zero, perturbations not
+    X[:, 6] = rng.poisson(0.5, n_cells) - 1.0 * (rng.rand(n_cells) < 0.05)   # a few negative values
+    X[0, 7] = np.nan if False else 1.0e30                           # one huge value in some group
+    X[~ctrl, 8] = (rng.poisson(4.0, (~ctrl).sum()) * 7.0)           # more than 10 distinct values outside the control
+    X[:, 40:44] = rng.poisson(30.0, (n_cells, 4))                   # a run of handed-back genes
+    return X, labels, f"g{ref_code:02d}"
+
+
+@pytest.mark.parametrize("kind", ["first", "middle", "last", "middle:log1p", "middle:less"])
+def test_fused_ovo_routes_match_general_path_and_oracle(monkeypatch, kind):
+    """ovo_fused.cu: table genes, extras, handed-back genes (merged runs), control position, log1p, alternatives:
+    identical U to the general path and to the oracle; p / fold change within tolerance."""
+    X, labels, ref = _fused_case(kind)
+    log1p = kind.endswith("log1p")
+    if log1p:
+        X = np.log1p(np.abs(X)).astype(np.float32)
+    kw = dict(is_log1p=log1p, alternative="less" if kind.endswith("less") else "two-sided")
+    from illico_b200 import _lib
+
+    monkeypatch.setenv("ILLICO_OVO_FUSED", "1")
+    monkeypatch.setenv("ILLICO_PROFILE", "1")
+    groups, fused = _run(X, labels, ref, batch_size="auto", **kw)
+    assert _lib.load().illico_last_fused_ms() >= 0, "the fused kernel did not run"
+    monkeypatch.setenv("ILLICO_OVO_FUSED", "0")
+    _, general = _run(X, labels, ref, batch_size="auto", **kw)
+    ref_row = int(np.searchsorted(groups, ref))
+    rows = np.arange(len(groups)) != ref_row
+    np.testing.assert_array_equal(fused[1], general[1])
+    np.testing.assert_allclose(fused[0][rows], general[0][rows], rtol=1e-13, atol=2.3e-308)
+    g, p, U, fc = oracle.run(X, labels, ref, **kw)
+    fc_rtol = FC_RTOL_LOG1P_F32 if log1p else FC_RTOL
+    assert_parity(fused, (p, U, fc), ref_row=ref_row, fc_rtol=fc_rtol, what=f"fused ovo {kind}")
+
+
+def test_fused_ovo_debug_integers_and_continuous_batches(monkeypatch):
+    """Exact 2U / tie sums through the fused path's debug outputs; a mostly continuous batch skips the fused path."""
+    import ctypes as Ct
+
+    import torch
+
+    from illico_b200 import _lib, synth
+    from illico_b200.engine import DeviceMatrix, Engine, make_flags
+    from illico_b200.groups import encode_and_count_groups
+
+    X, labels = synth.k562_like(seed=41, n_cells=5000, n_genes=64, n_perts=25)
+    uniq, grpc = encode_and_count_groups(labels, synth.CONTROL)
+    eng = Engine(grpc, torch.device("cuda", 0))
+    flags = make_flags(False, True, True, "two-sided", "dense")
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("ILLICO_OVO_FUSED", fused)
+        M = DeviceMatrix("dense", X.shape, torch.from_numpy(X).cuda())
+        res = torch.zeros((eng.n_groups, X.shape[1], 3), dtype=torch.float64, device="cuda")
+        dbg = {}
+        eng.run_batch(M, 0, X.shape[1], flags, res, 0, dbg)
+        torch.cuda.synchronize()
+        out[fused] = (res.cpu().numpy(), {k: v.cpu().numpy() for k, v in dbg.items()})
+    ref_row = int(np.searchsorted(uniq, synth.CONTROL))
+    rows = np.arange(len(uniq)) != ref_row
+    for k in ("u2", "tie_sum", "tie_exact"):
+        np.testing.assert_array_equal(out["1"][1][k][rows], out["0"][1][k][rows], err_msg=k)
+    np.testing.assert_array_equal(out["1"][0][:, :, 1], out["0"][0][:, :, 1])
+    # continuous data: the table kernel flags (almost) every gene and the dispatcher takes the general path
+    Xc, labels_c = synth.k562_like(seed=42, n_cells=4000, n_genes=32, n_perts=10, continuous=True)
+    monkeypatch.setenv("ILLICO_OVO_FUSED", "1")
+    groups, got = _run(Xc, labels_c, synth.CONTROL, is_log1p=False)
+    g, p, U, fc = oracle.run(Xc, labels_c, synth.CONTROL, is_log1p=False)
+    assert_parity(got, (p, U, fc), ref_row=int(np.searchsorted(groups, synth.CONTROL)), what="continuous via dispatcher")
+    assert Ct is not None and _lib is not None
