@@ -35,6 +35,8 @@ size_t ovr_slab_qwords(const illico_plan_t*);
 // ovo_fused.cu: dense one-versus-reference in one pass (0 = done, 1 = error, -1 = not applicable)
 int launch_ovo_dense_fused(const float*, long long, int, int, const illico_plan_t*, const illico_flags_t*,
                            const illico_batch_buffers_t*, double*, long long, const illico_debug_t*, cudaStream_t);
+int launch_ovr_dense_fused(const float*, long long, int, int, const illico_plan_t*, const illico_flags_t*,
+                           const illico_batch_buffers_t*, double*, long long, const illico_debug_t*, cudaStream_t);
 size_t ovo_fused_workspace_bytes(int);
 float ovo_fused_last_ms();
 size_t ovr_table_rec_bytes(const illico_plan_t*);
@@ -122,7 +124,7 @@ size_t illico_rank_workspace_bytes(const illico_plan_t* plan, int32_t n_genes_ba
     size_t rank = ctas * per_cta + 256 + (((size_t)(n_genes_batch > 0 ? n_genes_batch : 1) + 64) * sizeof(int) + 255);
     if (plan->ref_group < 0) rank += 2 * ctas * ovr_table_rec_bytes(plan) + 256;  // table kernel: up to 8 CTAs per SM
     size_t stage = stage_csr_workspace_bytes(plan, n_genes_batch);  // CSR staging reuses the same scratch
-    if (plan->ref_group >= 0) {                                      // so do the fused path's control tables
+    {                                                                // so do the fused paths' per-gene tables
         const size_t fused = ovo_fused_workspace_bytes(n_genes_batch > 0 ? n_genes_batch : 1);
         if (fused > stage) stage = fused;
     }
@@ -160,6 +162,12 @@ int illico_ovr_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t nb
                          const illico_flags_t* flags, const illico_batch_buffers_t* buf, double* results,
                          int64_t gstride, const illico_debug_t* dbg, void* stream) {
     ILLICO_CHECK_BUF(buf);
+    if (check_plan(plan)) return 1;
+    if (plan->ref_group >= 0) { set_error("illico_ovr_dense_f32: plan has a reference group"); return 1; }
+    if (!X || !flags || !results) { set_error("illico_ovr_dense_f32: NULL argument"); return 1; }
+    // count-like data: one pass over the matrix, per-group histograms instead of staged lists (ovo_fused.cu)
+    const int rc = launch_ovr_dense_fused(X, ld, gene_lb, nb, plan, flags, buf, results, gstride, dbg, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
     if (illico_stage_dense_f32(X, ld, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
     return illico_rank_ovr(buf->ir_vals, buf->ir_cnt, nb, plan, flags, results, gstride, buf->workspace,
                            buf->workspace_bytes, dbg, stream);

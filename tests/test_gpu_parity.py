@@ -435,3 +435,39 @@ def test_fused_ovo_debug_integers_and_continuous_batches(monkeypatch):
     g, p, U, fc = oracle.run(Xc, labels_c, synth.CONTROL, is_log1p=False)
     assert_parity(got, (p, U, fc), ref_row=int(np.searchsorted(groups, synth.CONTROL)), what="continuous via dispatcher")
     assert Ct is not None and _lib is not None
+
+
+@pytest.mark.parametrize("kind", ["first", "middle:log1p", "middle:less"])
+def test_fused_ovr_routes_match_general_path_and_oracle(monkeypatch, kind):
+    """One-versus-rest through the fused pass (sample table, count extension, handed-back genes) against the general
+    path and the oracle."""
+    X, labels, _ = _fused_case(kind)
+    X[:, 6] = np.abs(X[:, 6])
+    log1p = kind.endswith("log1p")
+    if log1p:
+        X = np.log1p(np.abs(X)).astype(np.float32)
+    kw = dict(is_log1p=log1p, alternative="less" if kind.endswith("less") else "two-sided")
+    from illico_b200 import _lib
+
+    monkeypatch.setenv("ILLICO_OVR_FUSED", "1")
+    monkeypatch.setenv("ILLICO_PROFILE", "1")
+    groups, fused = _run(X, labels, None, batch_size="auto", **kw)
+    assert _lib.load().illico_last_fused_ms() >= 0, "the fused kernel did not run"
+    monkeypatch.setenv("ILLICO_OVR_FUSED", "0")
+    _, general = _run(X, labels, None, batch_size="auto", **kw)
+    np.testing.assert_array_equal(fused[1], general[1])
+    np.testing.assert_allclose(fused[0], general[0], rtol=1e-13, atol=2.3e-308)
+    g, p, U, fc = oracle.run(X, labels, None, **kw)
+    assert_parity(fused, (p, U, fc), fc_rtol=FC_RTOL_LOG1P_F32 if log1p else FC_RTOL, what=f"fused ovr {kind}")
+
+
+def test_fused_ovr_tie_sum_above_2_53(monkeypatch):
+    """300k cells, 90 % zeros: the zero block's t^3 - t alone passes 2^53, so the f64 tie sum is order dependent;
+    the fused path's per-gene kernel must reproduce the dense kernels' order (golden case `bign`, reference output)."""
+    X, labels, reference = C.CASES["bign"][0]()
+    monkeypatch.setenv("ILLICO_OVR_FUSED", "1")
+    groups, fused = _run(X, labels, None, is_log1p=False)
+    monkeypatch.setenv("ILLICO_OVR_FUSED", "0")
+    _, general = _run(X, labels, None, is_log1p=False)
+    for a, b in zip(fused[:2], general[:2]):
+        np.testing.assert_array_equal(a, b)
