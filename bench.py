@@ -282,8 +282,8 @@ def main():
         dom, dom_bytes, dom_ms = f"stage_{fmt}_kernel", stage_bytes, t_stage
     else:
         dom, dom_bytes, dom_ms = f"{test}_kernel", rank_bytes, t_rank
-    # dense one-versus-reference on count-like data takes the fused single-pass path (ovo_fused.cu): the step is
-    # control staging + table kernel + ovo_fused_kernel + epilogue, and ovo_fused_kernel is the dominant kernel.
+    # dense input with count-like values takes the fused single-pass path (fused_dense.cu): the step is
+    # table staging + fused_ctab + fused_pass_kernel + per-gene weights + epilogue; fused_pass_kernel dominates.
     # The library times that kernel itself (CUDA events on the launching stream) when ILLICO_PROFILE=1.
     fused_ms = None
     if fmt == "dense":
@@ -304,7 +304,7 @@ def main():
             fused_ms = float(np.median(fm[1:]))
             # algorithmic bytes: every streamed row read once (OVO: all but the control's) + one 24-byte record per test
             n_ref = int(grpc.counts[grpc.encoded_ref_group]) if test == "ovo" else 0
-            dom, dom_ms = "ovo_fused_kernel", fused_ms
+            dom, dom_ms = "fused_pass_kernel", fused_ms
             dom_bytes = (a.cells - n_ref) * a.genes * 4 + 24 * (G - (1 if test == "ovo" else 0)) * a.genes
     n_launch_dom = len(batches)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
@@ -321,7 +321,7 @@ def main():
                 "algorithmic_bytes_per_launch": int(dom_bytes / n_launch_dom),
                 "stage_ms": round(t_stage, 3), "rank_ms": round(t_rank, 3),
                 "fused_ms": None if fused_ms is None else round(fused_ms, 3),
-                "note": ("step = table staging (control / cell sample) + ovo_ctab + ovo_fused_kernel + epilogue; stage_ms / rank_ms "
+                "note": ("step = table staging (control / cell sample) + fused_ctab + fused_pass_kernel + epilogue; stage_ms / rank_ms "
                          "are the general two-kernel path (continuous data), timed separately for comparison")
                 if fused_ms is not None else None,
                 "path_achieved_GBps": round(path_bytes / (ms_step * 1e-3) / 1e9, 1),

@@ -32,7 +32,7 @@ int launch_ovr(const float*, const uint32_t*, int, const illico_plan_t*, const i
 int launch_ovo(const float*, const uint32_t*, int, const illico_plan_t*, const illico_flags_t*, double*, long long, void*,
                size_t, const illico_debug_t*, cudaStream_t);
 size_t ovr_slab_qwords(const illico_plan_t*);
-// ovo_fused.cu: dense one-versus-reference in one pass (0 = done, 1 = error, -1 = not applicable)
+// fused_dense.cu: dense one-versus-reference in one pass (0 = done, 1 = error, -1 = not applicable)
 int launch_ovo_dense_fused(const float*, long long, int, int, const illico_plan_t*, const illico_flags_t*,
                            const illico_batch_buffers_t*, double*, long long, const illico_debug_t*, cudaStream_t);
 int launch_ovr_dense_fused(const float*, long long, int, int, const illico_plan_t*, const illico_flags_t*,
@@ -165,7 +165,7 @@ int illico_ovr_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t nb
     if (check_plan(plan)) return 1;
     if (plan->ref_group >= 0) { set_error("illico_ovr_dense_f32: plan has a reference group"); return 1; }
     if (!X || !flags || !results) { set_error("illico_ovr_dense_f32: NULL argument"); return 1; }
-    // count-like data: one pass over the matrix, per-group histograms instead of staged lists (ovo_fused.cu)
+    // count-like data: one pass over the matrix, per-group histograms instead of staged lists (fused_dense.cu)
     const int rc = launch_ovr_dense_fused(X, ld, gene_lb, nb, plan, flags, buf, results, gstride, dbg, (cudaStream_t)stream);
     if (rc >= 0) return rc;
     if (illico_stage_dense_f32(X, ld, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
@@ -179,7 +179,7 @@ int illico_ovo_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t nb
     if (check_plan(plan)) return 1;
     if (plan->ref_group < 0) { set_error("illico_ovo_dense_f32: plan has no reference group"); return 1; }
     if (!X || !flags || !results) { set_error("illico_ovo_dense_f32: NULL argument"); return 1; }
-    // count-like data: one pass over the matrix, no staged lists (ovo_fused.cu); anything else: stage + rank
+    // count-like data: one pass over the matrix, no staged lists (fused_dense.cu); anything else: stage + rank
     const int rc = launch_ovo_dense_fused(X, ld, gene_lb, nb, plan, flags, buf, results, gstride, dbg, (cudaStream_t)stream);
     if (rc >= 0) return rc;
     if (illico_stage_dense_f32(X, ld, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;

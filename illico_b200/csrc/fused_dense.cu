@@ -1,0 +1,656 @@
+// fused_dense.cu -- dense one-versus-reference and one-versus-rest in ONE pass over the matrix, without staged
+// non-zero lists (sm_100a).
+//
+// Replaces, for genes with few distinct values (raw counts, log1p of counts), the pair stage_dense + rank kernel, i.e.
+// illico/ovo/dense_ovo.py:15-137 and illico/ovr/dense_ovr.py:15-80 with illico/utils/ranking.py:7-158 and
+// illico/utils/math.py:64-118,168-221.
+//
+// Why: writing the staged lists (1.2 GB of scattered 32-byte sectors at the K562 shape) costs the staging kernel a
+// quarter of its time although it is a ninth of its bytes, and the rank kernels read them back with 2-3x sector
+// amplification.  When a gene has at most 12 distinct non-zero values, all a test needs from a group is its histogram
+// over those values -- 12 x u16 = the 24 bytes the result occupies anyway:
+//
+//   OVO  2U_g = sum_t b_t (2 #{ref > v_t} + a_t) + z_g (2 npos + Z_ref),   a_t / b_t = multiplicity in control / g
+//        T_g  = T_ref + sum_t [(a_t + b_t)^3 - (a_t + b_t) - (a_t^3 - a_t)] + (Z^3 - Z)
+//   OVR  2R_g = sum_t b_t r2_t + z_g r2_zero,   r2_t = doubled mid-rank of v_t among all cells (from sum_g b_t)
+//
+// Steps (all on the caller's stream):
+//   1. a few segments are staged alone (stage_dense_tma.cu) -- the control group for OVO, a 16k-cell sample for OVR --
+//      and `fused_ctab_kernel` turns them into a per-gene table: distinct values ascending + multiplicities;
+//   2. `fused_pass_kernel` streams the rows through a TMA ring (one producer warp issuing bulk copies, as in
+//      stage_dense_tma.cu); lane = gene; non-zeros are compacted into a lane-private shared column (no divergence per
+//      element) and, at the end of each group, looked up in the lane's copy of the table and counted.  Values the
+//      table lacks claim a free slot of the gene's GLOBAL table with atomicCAS, so every CTA indexes a gene's values
+//      the same way.  The group's histogram is written where its result will be;
+//   3. a per-gene kernel turns the table into per-slot weights (OVO: 2 #{ref > v} + a; OVR: doubled mid-ranks, tie sum
+//      in the reference's accumulation order), and an epilogue kernel turns each 24-byte histogram into
+//      (p, U, fold change) in place, in the reference's f64 operation order (epilogue.cuh).
+// Genes that do not qualify (a 13th distinct value, negative values, NaN) are flagged and go through the general
+// stage + rank path afterwards, in merged runs; batches that are mostly such genes skip the fused path altogether.
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "tma.cuh"
+
+#include <stdlib.h>
+
+#include <vector>
+
+namespace illico {
+
+// general path (stage.cu, rank_ovo.cu, rank_ovr.cu) for the genes the fused path hands back
+int launch_stage_dense(const float*, long long, int, int, const illico_plan_t*, float*, uint32_t*, cudaStream_t);
+int launch_ovo(const float*, const uint32_t*, int, const illico_plan_t*, const illico_flags_t*, double*, long long, void*,
+               size_t, const illico_debug_t*, cudaStream_t);
+int launch_ovr(const float*, const uint32_t*, int, const illico_plan_t*, const illico_flags_t*, double*, long long, void*,
+               size_t, const illico_debug_t*, cudaStream_t);
+bool stage_dense_tma_ok(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan);
+int launch_stage_dense_tma(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
+                           uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream, int segs_per_cta = 0);
+
+namespace {
+
+constexpr int FUSED_WARPS = 8;
+constexpr int FUSED_LANES = FUSED_WARPS * 32;      // genes per CTA (lane = gene)
+constexpr int FUSED_THREADS = FUSED_LANES + 32;    // + one producer warp
+constexpr int DCAP = 12;                           // table slots per gene = u16 counters in a 24-byte record
+constexpr long long PAIR_MAX = 208063;             // above it an OVO pair's tie sum can pass 2^53 (ordered replay needed)
+
+// Per-gene tables, structure-of-arrays over the batch's genes (lane = gene accesses are coalesced).
+struct Gtab {
+    float* key;                // [DCAP][bs]  slot values (> 0; 0 = free slot); the staged sample's values come first, ascending
+    uint32_t* mult;            // [DCAP][bs]  OVO: multiplicity in the control; OVR: multiplicity among all cells
+    uint32_t* wgt;             // [DCAP][bs]  OVO: 2 #{ref > v} + a; OVR: doubled mid-rank
+    double* fval;              // [DCAP][bs]  f(value) for the fold change
+    uint32_t* nnz;             // [bs]        OVO: control non-zeros; OVR: doubled mid-rank of the zero block
+    unsigned long long* tie;   // [bs]        OVO: sum over control runs of a^3 - a; OVR: f64 bits of the gene's tie sum
+    double* sum;               // [bs]        OVO: sum of f(x) over the control; OVR: over all cells
+    int* n_bad;                // [1]         genes flagged by the table kernel
+    unsigned char* bad;        // [bs]        1 = the gene takes the general path
+};
+
+size_t gtab_bytes(int b) {
+    const size_t bs = (size_t)((b + 63) & ~63);
+    return bs * ((size_t)DCAP * 20 + 4 + 8 + 8 + 1) + 1024;
+}
+Gtab gtab_carve(void* ws, int b) {
+    const size_t bs = (size_t)((b + 63) & ~63);
+    char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    Gtab c;
+    c.fval = reinterpret_cast<double*>(p); p += bs * 8 * DCAP;
+    c.tie = reinterpret_cast<unsigned long long*>(p); p += bs * 8;
+    c.sum = reinterpret_cast<double*>(p); p += bs * 8;
+    c.key = reinterpret_cast<float*>(p); p += bs * 4 * DCAP;
+    c.mult = reinterpret_cast<uint32_t*>(p); p += bs * 4 * DCAP;
+    c.wgt = reinterpret_cast<uint32_t*>(p); p += bs * 4 * DCAP;
+    c.nnz = reinterpret_cast<uint32_t*>(p); p += bs * 4;
+    c.n_bad = reinterpret_cast<int*>(p); p += 64;
+    c.bad = reinterpret_cast<unsigned char*>(p);
+    return c;
+}
+
+// ---- 1. per-gene tables from the staged segments [seg_lo, seg_hi) -------------------------------------------------
+// One warp per gene; lane t holds table slot t in registers.  Equal values of a 32-value load are merged with
+// match.any, their leaders are inserted one after the other.
+__global__ void __launch_bounds__(256) fused_ctab_kernel(const float* __restrict__ ir_vals, const uint32_t* __restrict__ ir_cnt,
+                                                         int b, const illico_plan_t pl, int seg_lo, int seg_hi, int is_log1p,
+                                                         Gtab gt, int bs) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int S = pl.n_segments;
+    for (int j = warp; j < b; j += nwarps) {
+        float mykey = 0.0f;
+        uint32_t mycnt = 0;
+        int D = 0;
+        bool bad = false;
+        for (int s = seg_lo; s < seg_hi && !bad; ++s) {
+            const int c = (int)ir_cnt[(long long)j * S + s];
+            const float* src = ir_vals + (long long)j * pl.slot_cap + pl.seg_base[s];
+            for (int i0 = 0; i0 < c && !bad; i0 += 32) {
+                const bool valid = i0 + lane < c;
+                const float v = valid ? src[i0 + lane] : 0.0f;
+                if (__any_sync(FULL, valid && !(v > 0.0f))) { bad = true; break; }   // negative or NaN: general path
+                const unsigned same = __match_any_sync(FULL, __float_as_uint(v));
+                const bool leader = valid && (__ffs(same) - 1 == lane);
+                const uint32_t n = (uint32_t)__popc(same);
+                unsigned leaders = __ballot_sync(FULL, leader);
+                while (leaders) {
+                    const int l = __ffs(leaders) - 1;
+                    leaders &= leaders - 1;
+                    const float vv = __shfl_sync(FULL, v, l);
+                    const uint32_t nn = __shfl_sync(FULL, n, l);
+                    const unsigned hit = __ballot_sync(FULL, lane < D && mykey == vv);
+                    if (hit) {
+                        if (lane == __ffs(hit) - 1) mycnt += nn;
+                    } else if (D < DCAP) {
+                        if (lane == D) { mykey = vv; mycnt = nn; }
+                        ++D;
+                    } else {
+                        bad = true;
+                        break;
+                    }
+                }
+            }
+        }
+        if (bad) {
+            if (lane == 0) { gt.bad[j] = 1; atomicAdd(gt.n_bad, 1); }
+            continue;
+        }
+        // slots in ascending value order (position = number of smaller values); the rest are free
+        int pos = 0;
+        for (int t = 0; t < D; ++t) pos += (__shfl_sync(FULL, mykey, t) < mykey) ? 1 : 0;
+        const bool mine = lane < D;
+        if (mine) { gt.key[(long long)pos * bs + j] = mykey; gt.mult[(long long)pos * bs + j] = mycnt; }
+        if (lane >= D && lane < DCAP) { gt.key[(long long)lane * bs + j] = 0.0f; gt.mult[(long long)lane * bs + j] = 0u; }
+        const uint32_t nnz = warp_sum<uint32_t>(mine ? mycnt : 0u);
+        const unsigned long long tie = warp_sum_u64(mine ? (unsigned long long)cube_minus((long long)mycnt) : 0ull);
+        const double sum = warp_sum_f64(mine ? (double)mycnt * fc_value(mykey, is_log1p) : 0.0);
+        if (lane == 0) { gt.nnz[j] = nnz; gt.tie[j] = tie; gt.sum[j] = sum; gt.bad[j] = 0; }
+    }
+}
+
+// ---- 2. the pass over the matrix ------------------------------------------------------------------------------------
+template <int ROWS, int STAGES, int BUF>
+struct FusedLayout {
+    static constexpr int ROW_BYTES = FUSED_LANES * 4;
+    static constexpr int STAGE_BYTES = ROWS * ROW_BYTES;
+    static constexpr int RING_OFF = 0;
+    static constexpr int NZ_OFF = STAGES * STAGE_BYTES;            // float [BUF][256]   compacted non-zeros of the group
+    static constexpr int KEY_OFF = NZ_OFF + BUF * ROW_BYTES;       // float [DCAP][256]  the lane's copy of the gene's table
+    static constexpr int HIST_OFF = KEY_OFF + DCAP * ROW_BYTES;    // u16   [DCAP][256]  multiplicity in the current group
+    static constexpr int BAR_OFF = HIST_OFF + DCAP * FUSED_LANES * 2;
+    static constexpr int BYTES = BAR_OFF + 2 * STAGES * 8;
+};
+
+// OVO = true: the control group's rows are skipped (its table is what the others are ranked against).
+// OVO = false: every row is streamed and the CTA's share of each gene's whole histogram is added to gt.mult.
+template <int ROWS, int STAGES, int BUF, int MINB, bool OVO>
+__global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const float* __restrict__ X, long long ld, int gene_lb,
+                                                                         int b, const illico_plan_t pl, int groups_per_cta,
+                                                                         Gtab gt, int bs, unsigned long long* __restrict__ rec,
+                                                                         long long gstride) {
+    using L = FusedLayout<ROWS, STAGES, BUF>;
+    static_assert(32 % ROWS == 0 && BUF > ROWS, "layout");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t smem_a = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t bars = smem_a + L::BAR_OFF;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int G = pl.n_groups, ref = OVO ? pl.ref_group : -1;
+    const int gy0 = blockIdx.y * groups_per_cta, gy1 = min(G, gy0 + groups_per_cta);
+    const int p_begin = pl.seg_pos[pl.group_seg[gy0]], p_end = pl.seg_pos[pl.group_seg[gy1]];
+    const bool ref_in = ref >= gy0 && ref < gy1;
+    const int ref_p0 = ref_in ? pl.seg_pos[pl.group_seg[ref]] : 0;
+    const int ref_len = ref_in ? pl.seg_pos[pl.group_seg[ref + 1]] - ref_p0 : 0;
+    const int nv = p_end - p_begin - ref_len;                   // rows this CTA streams (the control's are skipped)
+    const int g0 = blockIdx.x * FUSED_LANES;
+    const uint32_t row_bytes = (uint32_t)min(FUSED_LANES, (b - g0 + 3) & ~3) * 4u;
+    if (nv <= 0) return;
+
+    if (t == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(bars + 8 * i, 1);
+            mbar_init(bars + 8 * (STAGES + i), FUSED_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (w == FUSED_WARPS) {
+        // ---------------- producer warp (as in stage_dense_tma.cu); virtual row i -> position in perm, control skipped
+        // (reading the permutation two groups ahead, or the group boundaries one group ahead, measured 5-10 % slower)
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        const char* base = reinterpret_cast<const char*>(X + gene_lb + g0);
+        const unsigned long long ldb = (unsigned long long)ld * 4ull;
+        auto row_of = [&](int i) {
+            int p = p_begin + i;
+            if (ref_in && p >= ref_p0) p += ref_len;
+            return pl.perm[p];
+        };
+        int myrow = (lane < nv) ? row_of(lane) : 0;
+        int k = 0;
+        for (int i0 = 0; i0 < nv; i0 += 32) {
+            const int nxt = (i0 + 32 + lane < nv) ? row_of(i0 + 32 + lane) : 0;
+            const int nrows = min(32, nv - i0);
+#pragma unroll
+            for (int q = 0; q < 32 / ROWS; ++q, ++k) {
+                if (q * ROWS >= nrows) break;
+                const int slot = k % STAGES;
+                const uint32_t full = bars + 8 * slot, empty = bars + 8 * (STAGES + slot);
+                mbar_wait(empty, ((k / STAGES) & 1) ^ 1);
+                const int rows_here = min(ROWS, nrows - q * ROWS);
+                if (lane == 0) mbar_expect_tx(full, (uint32_t)rows_here * row_bytes);
+                __syncwarp();
+                const int u = lane - q * ROWS;
+                if (u >= 0 && u < rows_here)
+                    bulk_g2s(smem_a + L::RING_OFF + slot * L::STAGE_BYTES + u * L::ROW_BYTES,
+                             base + (unsigned long long)(uint32_t)myrow * ldb, row_bytes, full, policy);
+            }
+            myrow = nxt;
+        }
+        return;
+    }
+
+    // ---------------- consumer warps: lane = gene.  All shared-memory traffic below uses explicit 32-bit shared
+    // addresses (entry q of the lane's column of an array lives at array + q * 1024 + 4 * t).
+    const int j = g0 + t;
+    const bool in_batch = j < b;
+    const uint32_t keys_a = smem_a + L::KEY_OFF + t * 4;
+    const uint32_t hist_a = smem_a + L::HIST_OFF + t * 2;
+    const uint32_t nz_a = smem_a + L::NZ_OFF + t * 4;
+    auto lds_f = [](uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; };
+    auto sts_f = [](uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
+    auto lds_h = [](uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return (uint32_t)v; };
+    auto sts_h = [](uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); };
+    bool bad = !in_batch || gt.bad[j] != 0;
+    float* gkey = gt.key + (in_batch ? j : 0);
+    // The gene's table is global: slots are filled in order, the sample's values first; every slot already taken is
+    // cached in the lane's shared column, later ones are found (or claimed) on a miss.
+    int D = 0;
+#pragma unroll
+    for (int q = 0; q < DCAP; ++q) {
+        const float kq = bad ? 0.0f : __ldcg(gkey + (long long)q * bs);
+        if (kq != 0.0f) D = q + 1;
+        sts_f(keys_a + q * L::ROW_BYTES, kq);
+        sts_h(hist_a + q * (FUSED_LANES * 2), 0u);
+    }
+    uint32_t Hacc[OVO ? 1 : DCAP];                            // OVR: this CTA's share of the gene's whole histogram
+#pragma unroll
+    for (int q = 0; q < (OVO ? 1 : DCAP); ++q) Hacc[q] = 0u;
+    uint32_t wr = nz_a;                                       // shared address of the lane's next free nz entry
+
+    // looks the buffered non-zeros up in the lane's table and bumps the group's histogram
+    auto drain = [&]() {
+        const uint32_t mywr = bad ? nz_a : wr;
+        const uint32_t maxwr = __reduce_max_sync(FULL, mywr - nz_a);
+        for (uint32_t o = 0; o < maxwr; o += L::ROW_BYTES) {
+            if (nz_a + o < mywr) {
+                const float v = lds_f(nz_a + o);
+                // counts: value c usually sits in slot c - 1; otherwise scan for equality
+                int q = (int)v - 1;
+                if (!(q >= 0 && q < D && lds_f(keys_a + q * L::ROW_BYTES) == v)) {
+                    q = 0;
+                    while (q < D && lds_f(keys_a + q * L::ROW_BYTES) != v) ++q;
+                    if (q == D) {
+                        // not cached: find or claim the value's slot in the gene's global table
+                        int slot = -1;
+                        if (v > 0.0f) {
+                            for (int r = D; r < DCAP && slot < 0; ++r) {
+                                const unsigned old = atomicCAS(reinterpret_cast<unsigned*>(gkey + (long long)r * bs), 0u,
+                                                               __float_as_uint(v));
+                                const float kv = old ? __uint_as_float(old) : v;
+                                sts_f(keys_a + r * L::ROW_BYTES, kv);
+                                D = r + 1;
+                                if (kv == v) slot = r;
+                            }
+                        }
+                        if (slot < 0) { bad = true; q = 0; }   // a 13th distinct value, a negative one or a NaN: general path
+                        else q = slot;
+                    }
+                }
+                const uint32_t ha = hist_a + q * (FUSED_LANES * 2);
+                sts_h(ha, lds_h(ha) + 1u);
+            }
+        }
+        wr = nz_a;
+    };
+    // record of group g = its histogram over the gene's table, 12 x u16 = 24 bytes, written where the result goes
+    auto close_group = [&](int g) {
+        drain();
+        unsigned long long wds[3] = {0ull, 0ull, 0ull};
+#pragma unroll
+        for (int q = 0; q < DCAP; ++q) {
+            const uint32_t bq = lds_h(hist_a + q * (FUSED_LANES * 2));
+            wds[q >> 2] |= (unsigned long long)bq << (16 * (q & 3));
+            if (!OVO) Hacc[OVO ? 0 : q] += bq;
+            sts_h(hist_a + q * (FUSED_LANES * 2), 0u);
+        }
+        if (!bad) {
+            unsigned long long* o = rec + (long long)g * gstride + (long long)j * 3;
+            o[0] = wds[0]; o[1] = wds[1]; o[2] = wds[2];
+        }
+    };
+    auto group_end_v = [&](int gg) { return pl.seg_pos[pl.group_seg[gg + 1]] - p_begin - ((ref_in && gg > ref) ? ref_len : 0); };
+    int g = (gy0 == ref) ? gy0 + 1 : gy0;
+    int gend = group_end_v(g);
+
+    auto append = [&](float v) {
+        asm volatile("{ .reg .pred p; setp.neu.f32 p, %1, 0f00000000; @p st.shared.f32 [%0], %1; @p add.u32 %0, %0, %2; }"
+                     : "+r"(wr)
+                     : "f"(v), "n"(L::ROW_BYTES)
+                     : "memory");
+    };
+    const uint32_t ring_a = smem_a + L::RING_OFF + t * 4;
+    const uint32_t wr_limit = nz_a + (uint32_t)(BUF - ROWS) * L::ROW_BYTES;
+    int slot = 0;
+    uint32_t parity = 0;
+    for (int i = 0; i < nv; i += ROWS) {
+        mbar_wait(bars + 8 * slot, parity);
+        const uint32_t src = ring_a + slot * L::STAGE_BYTES;
+        if (i + ROWS <= gend) {
+            // the whole stage lies inside the current group (the usual case): independent shared loads first
+            float v[ROWS];
+#pragma unroll
+            for (int u = 0; u < ROWS; ++u) v[u] = lds_f(src + u * L::ROW_BYTES);
+#pragma unroll
+            for (int u = 0; u < ROWS; ++u) append(v[u]);
+        } else {
+            const int nr = min(ROWS, nv - i);
+#pragma unroll 1
+            for (int u = 0; u < nr; ++u) {
+                if (i + u == gend) {                                     // CTA-uniform: the next group starts here
+                    close_group(g);
+                    ++g;
+                    if (g == ref) ++g;
+                    gend = group_end_v(g);
+                }
+                append(lds_f(src + u * L::ROW_BYTES));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * (STAGES + slot));
+        if (++slot == STAGES) { slot = 0; parity ^= 1u; }
+        if (__any_sync(FULL, wr > wr_limit)) drain();                     // keep room for one more stage
+    }
+    close_group(g);
+    if (in_batch) {
+        if (bad) {
+            gt.bad[j] = 1;
+        } else if (!OVO) {
+#pragma unroll
+            for (int q = 0; q < (OVO ? 1 : DCAP); ++q)
+                if (Hacc[q]) atomicAdd(gt.mult + (long long)q * bs + j, Hacc[q]);
+        }
+    }
+}
+
+// ---- 3a. per-gene weights ---------------------------------------------------------------------------------------------
+// Thread per gene.  Visits the gene's claimed slots in ascending value order.
+// OVO: weight of slot t = 2 #{control > v_t} + a_t (rank_ovo.cu's dw); the control's sums are already in gt.
+// OVR: gt.mult holds the whole gene's histogram; weight = doubled mid-rank r2 = 2 lo + c + 1 with the zero block below
+//      every (positive) value, as in ovr_table_kernel (rank_ovr.cu); tie sum in the dense kernels' order
+//      (illico/utils/ranking.py:31-47): zero block, then the runs ascending, sequential f64 once the exact total
+//      reaches 2^53.
+template <bool OVO>
+__global__ void __launch_bounds__(128) fused_gene_kernel(int b, const illico_plan_t pl, illico_flags_t fl, Gtab gt, int bs,
+                                                         double* dbg_tie, long long* dbg_tie_exact) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= b || gt.bad[j]) return;
+    float key[DCAP];
+    int order[DCAP];
+    int D = 0;
+    for (int q = 0; q < DCAP; ++q) {
+        const float kq = gt.key[(long long)q * bs + j];
+        if (kq == 0.0f) break;
+        int a = D - 1;
+        while (a >= 0 && key[order[a]] > kq) { order[a + 1] = order[a]; --a; }
+        key[q] = kq;
+        order[a + 1] = q;
+        ++D;
+    }
+    for (int q = D; q < DCAP; ++q) { gt.wgt[(long long)q * bs + j] = 0u; gt.fval[(long long)q * bs + j] = 0.0; }
+    if (OVO) {
+        unsigned long long above = 0;                                            // control values greater than the slot's
+        for (int a = D - 1; a >= 0; --a) {
+            const int q = order[a];
+            const unsigned long long c = gt.mult[(long long)q * bs + j];
+            gt.wgt[(long long)q * bs + j] = (uint32_t)(2ull * above + c);
+            gt.fval[(long long)q * bs + j] = fc_value(key[q], fl.is_log1p);
+            above += c;
+        }
+        return;
+    }
+    const long long n = pl.n_cells;
+    unsigned long long nnz = 0;
+    for (int q = 0; q < D; ++q) nnz += gt.mult[(long long)q * bs + j];
+    const long long n0 = n - (long long)nnz;
+    unsigned long long lo = (unsigned long long)n0, t_exact = 0;
+    double total = 0.0;
+    const unsigned long long zterm = (unsigned long long)cube_minus(n0);
+    double walk = (double)(long long)zterm;                                      // sequential accumulation, zero block first
+    for (int a = 0; a < D; ++a) {
+        const int q = order[a];
+        const unsigned long long c = gt.mult[(long long)q * bs + j];
+        gt.wgt[(long long)q * bs + j] = (uint32_t)(2ull * lo + c + 1ull);
+        const double f = fc_value(key[q], fl.is_log1p);
+        gt.fval[(long long)q * bs + j] = f;
+        total += (double)c * f;
+        const unsigned long long t3 = (unsigned long long)cube_minus((long long)c);
+        t_exact += t3;
+        walk += (double)(long long)t3;
+        lo += c;
+    }
+    const double tie = ((double)t_exact + (double)zterm >= TWO53) ? walk : (double)(t_exact + zterm);
+    gt.nnz[j] = (uint32_t)(n0 + 1);                                              // doubled mid-rank of the zero block
+    gt.sum[j] = total;
+    gt.tie[j] = (unsigned long long)__double_as_longlong(tie);
+    if (dbg_tie) dbg_tie[j] = tie;
+    if (dbg_tie_exact) dbg_tie_exact[j] = (long long)(t_exact + zterm);
+}
+
+// ---- 3b. epilogue: 24-byte histogram -> (p, U, fold change), in place ---------------------------------------------------
+// Block row = group, threads over genes (coalesced table reads, 24-byte contiguous records).
+template <bool OVO>
+__global__ void __launch_bounds__(256) fused_epilogue_kernel(int b, const illico_plan_t pl, const illico_flags_t fl, Gtab gt,
+                                                             int bs, double* __restrict__ results, long long gstride,
+                                                             long long* dbg_u2, double* dbg_tie, long long* dbg_tie_exact) {
+    const int g = blockIdx.y, ref = pl.ref_group;
+    const long long n = pl.n_cells, n_t = pl.group_size[g];
+    const long long n_r = OVO ? (long long)pl.group_size[ref] : n - n_t;         // the sample U is reported for
+    const double cc = fl.use_continuity ? 0.5 : 0.0;
+    const double mu = (double)(n_r * n_t) / 2.0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < b; j += gridDim.x * blockDim.x) {
+        if (gt.bad[j]) continue;
+        double* o = results + (long long)g * gstride + (long long)j * 3;
+        const long long di = (long long)g * b + j;
+        if (OVO && g == ref) {
+            // control row: (1, -1, fold change of the control against itself), as ovo_kernel writes it
+            const double rsum = fl.group_sums ? fl.group_sums[(long long)ref * b + j] : gt.sum[j];
+            const double mean_r = rsum / (double)n_r;
+            o[0] = 1.0; o[1] = -1.0; o[2] = (mean_r == 0.0) ? INFINITY : mean_r / mean_r;
+            if (dbg_u2) dbg_u2[di] = -2;
+            if (dbg_tie) dbg_tie[di] = 0.0;
+            if (dbg_tie_exact) dbg_tie_exact[di] = 0;
+            continue;
+        }
+        const unsigned long long* r = reinterpret_cast<const unsigned long long*>(o);
+        const unsigned long long wds[3] = {r[0], r[1], r[2]};
+        unsigned long long acc = 0, tie_nz = 0, m = 0;       // acc: OVO 2U without the zero block, OVR 2R without it
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < DCAP; ++q) {
+            const unsigned long long bq = (wds[q >> 2] >> (16 * (q & 3))) & 0xffffull;
+            if (bq) {
+                acc += bq * gt.wgt[(long long)q * bs + j];
+                sum += (double)bq * gt.fval[(long long)q * bs + j];
+                m += bq;
+                if (OVO) {
+                    const unsigned long long a = gt.mult[(long long)q * bs + j];
+                    tie_nz += bq * (3ull * a * a - 1ull + bq * (3ull * a + bq));   // (a+b)^3 - (a+b) - (a^3 - a)
+                }
+            }
+        }
+        const long long z_t = n_t - (long long)m;
+        double p, U, fc;
+        if (OVO) {
+            const long long nnz_r = gt.nnz[j], zeros_r = n_r - nnz_r;            // every control value is positive
+            if (fl.group_sums) sum = fl.group_sums[(long long)g * b + j];
+            const double rsum = fl.group_sums ? fl.group_sums[(long long)ref * b + j] : gt.sum[j];
+            const long long Z = zeros_r + z_t;
+            const unsigned long long u2 = acc + (unsigned long long)(z_t * (2ll * nnz_r + zeros_r));
+            const unsigned long long tie_exact = gt.tie[j] + tie_nz + (unsigned long long)cube_minus(Z);
+            const double tie = (double)tie_exact;                                // < 2^53: pairs of at most 208 063 cells
+            U = (double)u2 / 2.0;
+            p = compute_pval(n_r, n_t, n_r + n_t, fl.tie_correct ? tie : 0.0, U, mu, cc, fl.alternative);
+            const double mean_t = sum / (double)n_t, mean_r = rsum / (double)n_r;
+            fc = (mean_r == 0.0) ? INFINITY : mean_t / mean_r;
+            if (dbg_u2) dbg_u2[di] = (long long)u2;
+            if (dbg_tie) dbg_tie[di] = tie;
+            if (dbg_tie_exact) dbg_tie_exact[di] = (long long)tie_exact;
+        } else {
+            const unsigned long long R2 = acc + (unsigned long long)z_t * gt.nnz[j];
+            const long long u2 = 2 * n_r * n_t + n_t * (n_t + 1) - (long long)R2;
+            const double tie = __longlong_as_double((long long)gt.tie[j]);
+            U = (double)u2 / 2.0;
+            p = compute_pval(n_r, n_t, n, fl.tie_correct ? tie : 0.0, U, mu, cc, fl.alternative);
+            const double mu_t = sum / (double)n_t, mu_r = (gt.sum[j] - sum) / (double)(n - n_t);
+            fc = (mu_r == 0.0) ? INFINITY : mu_t / mu_r;
+            if (dbg_u2) dbg_u2[di] = u2;
+        }
+        o[0] = p; o[1] = U; o[2] = fc;
+    }
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+thread_local float g_last_fused_ms = -1.0f;
+
+template <int ROWS, int STAGES, int BUF, int MINB, bool OVO>
+int launch_pass_t(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, int gpc, Gtab gt, int bs,
+                  double* results, long long gstride, cudaStream_t stream) {
+    using L = FusedLayout<ROWS, STAGES, BUF>;
+    auto kern = fused_pass_kernel<ROWS, STAGES, BUF, MINB, OVO>;
+    ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+    const dim3 grid((unsigned)((b + FUSED_LANES - 1) / FUSED_LANES), (unsigned)((plan->n_groups + gpc - 1) / gpc));
+    kern<<<grid, FUSED_THREADS, L::BYTES, stream>>>(X, ld, gene_lb, b, *plan, gpc, gt, bs,
+                                                    reinterpret_cast<unsigned long long*>(results), gstride);
+    count_launch();
+    ILLICO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// The whole fused path for one gene batch.  0 = done, 1 = error, -1 = not applicable (the caller runs the general path).
+template <bool OVO>
+int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, const illico_flags_t* flags,
+              const illico_batch_buffers_t* buf, double* results, long long gstride, const illico_debug_t* dbg,
+              cudaStream_t stream) {
+    if (env_int(OVO ? "ILLICO_OVO_FUSED" : "ILLICO_OVR_FUSED", 1) == 0 || b <= 0) return -1;
+    if (!stage_dense_tma_ok(X, ld, gene_lb, b, plan)) return -1;
+    if (plan->max_group_size >= 65536 || plan->n_groups < 2 || plan->n_groups > 65535) return -1;   // u16 counters, grid.y
+    if (OVO && (long long)plan->ref_group_size + plan->max_group_size > PAIR_MAX) return -1;        // tie sums below 2^53
+    if (!OVO && flags->group_sums) return -1;
+    if (buf->workspace_bytes < gtab_bytes(b)) return -1;
+    const int bs = (b + 63) & ~63;
+    Gtab gt = gtab_carve(buf->workspace, b);
+
+    // 1. table segments: the control group (OVO) or a sample of about 16k cells (OVR: the first segments)
+    int seg_lo = plan->ref_seg_begin, seg_hi = plan->ref_seg_end;
+    if (!OVO) {
+        long long avg = plan->n_cells / plan->n_segments;
+        if (avg < 1) avg = 1;
+        seg_lo = 0;
+        seg_hi = (int)((env_int("ILLICO_OVR_FUSED_SAMPLE", 16384) + avg - 1) / avg);
+        if (seg_hi < 1) seg_hi = 1;
+        if (seg_hi > plan->n_segments) seg_hi = plan->n_segments;
+    }
+    ILLICO_CUDA_OK(cudaMemsetAsync(gt.n_bad, 0, sizeof(int), stream));
+    {
+        const int rc = launch_stage_dense_tma(X, ld, gene_lb, b, plan, buf->ir_vals, buf->ir_cnt, seg_lo, seg_hi, stream, 1);
+        if (rc != 0) return rc;
+        int blocks = (b + 7) / 8;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        fused_ctab_kernel<<<blocks, 256, 0, stream>>>(buf->ir_vals, buf->ir_cnt, b, *plan, seg_lo, seg_hi, flags->is_log1p, gt, bs);
+        count_launch();
+        ILLICO_CUDA_OK(cudaGetLastError());
+    }
+    if (!OVO)   // the sample only seeds the slots; gt.mult restarts as the whole gene's histogram
+        ILLICO_CUDA_OK(cudaMemsetAsync(gt.mult, 0, (size_t)bs * DCAP * sizeof(uint32_t), stream));
+    int n_bad = 0;
+    ILLICO_CUDA_OK(cudaMemcpyAsync(&n_bad, gt.n_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
+    if (2 * n_bad > b) return -1;   // mostly continuous data: the general path is the right one for this batch
+
+    // 2. the pass over the matrix
+    long long avg_g = plan->n_cells / plan->n_groups;
+    if (avg_g < 1) avg_g = 1;
+    int gpc = (int)(env_int("ILLICO_FUSED_ROWS", 1536) / avg_g);
+    if (gpc < 1) gpc = 1;
+    const bool timed = env_int("ILLICO_PROFILE", 0) != 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timed) {
+        ILLICO_CUDA_OK(cudaEventCreate(&e0));
+        ILLICO_CUDA_OK(cudaEventCreate(&e1));
+        ILLICO_CUDA_OK(cudaEventRecord(e0, stream));
+    }
+    // ring / buffer shapes measured at the K562 shape (profiles/README.md): stages of 8 rows, a 16-entry group buffer,
+    // 3 CTAs per SM; the 5-stage ring (74 KB of shared memory per CTA) is 6-7 % faster than the 4-stage one
+    int rc;
+    if (env_int("ILLICO_FUSED_STAGES", 5) != 4)
+        rc = launch_pass_t<8, 5, 16, 3, OVO>(X, ld, gene_lb, b, plan, gpc, gt, bs, results, gstride, stream);
+    else
+        rc = launch_pass_t<8, 4, 16, 3, OVO>(X, ld, gene_lb, b, plan, gpc, gt, bs, results, gstride, stream);
+    if (rc) return rc;
+    if (timed) ILLICO_CUDA_OK(cudaEventRecord(e1, stream));
+
+    // 3. per-gene weights, then the epilogue
+    fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, (dbg && !OVO) ? dbg->tie_sum : nullptr,
+                                                                (dbg && !OVO) ? (long long*)dbg->tie_exact : nullptr);
+    count_launch();
+    ILLICO_CUDA_OK(cudaGetLastError());
+    {
+        int gx = (b + 255) / 256;
+        if (gx > 64) gx = 64;
+        fused_epilogue_kernel<OVO><<<dim3((unsigned)gx, (unsigned)plan->n_groups), 256, 0, stream>>>(
+            b, *plan, *flags, gt, bs, results, gstride, dbg ? (long long*)dbg->u2 : nullptr,
+            (dbg && OVO) ? dbg->tie_sum : nullptr, (dbg && OVO) ? (long long*)dbg->tie_exact : nullptr);
+        count_launch();
+        ILLICO_CUDA_OK(cudaGetLastError());
+    }
+
+    // 4. genes handed back: general path, in merged runs
+    std::vector<unsigned char> bad((size_t)b);
+    ILLICO_CUDA_OK(cudaMemcpyAsync(bad.data(), gt.bad, (size_t)b, cudaMemcpyDeviceToHost, stream));
+    ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
+    if (timed) {
+        ILLICO_CUDA_OK(cudaEventElapsedTime(&g_last_fused_ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    int first = -1, last = -1, count = 0;
+    for (int j = 0; j < b; ++j)
+        if (bad[j]) { if (first < 0) first = j; last = j; ++count; }
+    if (count == 0) return 0;
+    if (dbg || flags->group_sums) return -1;   // their [G, b] side arrays are indexed by the whole batch: redo it all
+    const int gap = env_int("ILLICO_FUSED_GAP", 128);   // a launch costs about as much as this many genes
+    int lb = first;
+    while (lb <= last) {
+        int ub = lb + 1, j = lb + 1;
+        while (j <= last) {
+            if (bad[j]) { ub = j + 1; ++j; }
+            else if (j - ub < gap) ++j;
+            else break;
+        }
+        // genes [lb, ub) of the batch (good genes inside a merged run are simply recomputed)
+        if (launch_stage_dense(X, ld, gene_lb + lb, ub - lb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
+        const int rr = OVO ? launch_ovo(buf->ir_vals, buf->ir_cnt, ub - lb, plan, flags, results + (long long)lb * 3, gstride,
+                                        buf->workspace, buf->workspace_bytes, nullptr, stream)
+                           : launch_ovr(buf->ir_vals, buf->ir_cnt, ub - lb, plan, flags, results + (long long)lb * 3, gstride,
+                                        buf->workspace, buf->workspace_bytes, nullptr, stream);
+        if (rr) return 1;
+        lb = ub;
+        while (lb <= last && !bad[lb]) ++lb;
+    }
+    return 0;
+}
+
+}  // namespace
+
+float ovo_fused_last_ms() { return g_last_fused_ms; }
+
+size_t ovo_fused_workspace_bytes(int b) { return gtab_bytes(b); }
+
+int launch_ovo_dense_fused(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan,
+                           const illico_flags_t* flags, const illico_batch_buffers_t* buf, double* results, long long gstride,
+                           const illico_debug_t* dbg, cudaStream_t stream) {
+    return run_fused<true>(X, ld, gene_lb, b, plan, flags, buf, results, gstride, dbg, stream);
+}
+
+int launch_ovr_dense_fused(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan,
+                           const illico_flags_t* flags, const illico_batch_buffers_t* buf, double* results, long long gstride,
+                           const illico_debug_t* dbg, cudaStream_t stream) {
+    return run_fused<false>(X, ld, gene_lb, b, plan, flags, buf, results, gstride, dbg, stream);
+}
+
+}  // namespace illico

@@ -109,7 +109,7 @@ const char* illico_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t illico_launch_count(void);
 /* with ILLICO_PROFILE=1 in the environment: duration (ms, CUDA events on the caller's stream) of the last
- * ovo_fused_kernel launch of this thread, -1 if none (bench.py's roofline) */
+ * fused_pass_kernel launch of this thread, -1 if none (bench.py's roofline) */
 double illico_last_fused_ms(void);
 
 /* ---- staging: input formats -> group-segmented non-zero lists ------------------------------- */

@@ -13,7 +13,7 @@ cap() {  # name workload kernel-regex
   timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$3" -c 1 -f -o $o/$1 \
     python bench.py --workload $2 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $o/$1.log 2>&1
 }
-cap fused dense_ovo ovo_fused_kernel
+cap fused dense_ovo fused_pass_kernel
 cap stage_tma dense_ovr stage_dense_tma_kernel
 cap ovr dense_ovr 'ovr_.*kernel'
 cap ovo csr_ovo '^ovo_kernel|illico::ovo_kernel'

@@ -376,7 +376,7 @@ def _fused_case(kind, n_cells=6000, n_genes=72, seed=31):
 
 @pytest.mark.parametrize("kind", ["first", "middle", "last", "middle:log1p", "middle:less"])
 def test_fused_ovo_routes_match_general_path_and_oracle(monkeypatch, kind):
-    """ovo_fused.cu: table genes, extras, handed-back genes (merged runs), control position, log1p, alternatives:
+    """fused_dense.cu: table genes, extras, handed-back genes (merged runs), control position, log1p, alternatives:
     identical U to the general path and to the oracle; p / fold change within tolerance."""
     X, labels, ref = _fused_case(kind)
     log1p = kind.endswith("log1p")
