@@ -282,11 +282,11 @@ def main():
         dom, dom_bytes, dom_ms = f"stage_{fmt}_kernel", stage_bytes, t_stage
     else:
         dom, dom_bytes, dom_ms = f"{test}_kernel", rank_bytes, t_rank
-    # dense input with count-like values takes the fused single-pass path (fused_dense.cu): the step is
+    # dense input with count-like values takes the fused single-pass path (fused.cu): the step is
     # table staging + fused_ctab + fused_pass_kernel + per-gene weights + epilogue; fused_pass_kernel dominates.
     # The library times that kernel itself (CUDA events on the launching stream) when ILLICO_PROFILE=1.
     fused_ms = None
-    if fmt == "dense":
+    if fmt in ("dense", "csr"):
         os.environ["ILLICO_PROFILE"] = "1"
         fm = []
         for _ in range(4):
@@ -304,8 +304,11 @@ def main():
             fused_ms = float(np.median(fm[1:]))
             # algorithmic bytes: every streamed row read once (OVO: all but the control's) + one 24-byte record per test
             n_ref = int(grpc.counts[grpc.encoded_ref_group]) if test == "ovo" else 0
-            dom, dom_ms = "fused_pass_kernel", fused_ms
-            dom_bytes = (a.cells - n_ref) * a.genes * 4 + 24 * (G - (1 if test == "ovo" else 0)) * a.genes
+            dom, dom_ms = ("fused_pass_kernel" if fmt == "dense" else "fused_csr_pass_kernel"), fused_ms
+            if fmt == "dense":
+                dom_bytes = (a.cells - n_ref) * a.genes * 4 + 24 * (G - (1 if test == "ovo" else 0)) * a.genes
+            else:  # every stored value and index read once + the records
+                dom_bytes = nnz * 8 + (a.cells + 1) * 8 + 24 * (G - (1 if test == "ovo" else 0)) * a.genes
     n_launch_dom = len(batches)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     traffic = None  # dram bytes per launch from the committed ncu --set full capture (same shape only)

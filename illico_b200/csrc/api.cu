@@ -32,11 +32,15 @@ int launch_ovr(const float*, const uint32_t*, int, const illico_plan_t*, const i
 int launch_ovo(const float*, const uint32_t*, int, const illico_plan_t*, const illico_flags_t*, double*, long long, void*,
                size_t, const illico_debug_t*, cudaStream_t);
 size_t ovr_slab_qwords(const illico_plan_t*);
-// fused_dense.cu: dense one-versus-reference in one pass (0 = done, 1 = error, -1 = not applicable)
+// fused.cu: dense one-versus-reference in one pass (0 = done, 1 = error, -1 = not applicable)
 int launch_ovo_dense_fused(const float*, long long, int, int, const illico_plan_t*, const illico_flags_t*,
                            const illico_batch_buffers_t*, double*, long long, const illico_debug_t*, cudaStream_t);
 int launch_ovr_dense_fused(const float*, long long, int, int, const illico_plan_t*, const illico_flags_t*,
                            const illico_batch_buffers_t*, double*, long long, const illico_debug_t*, cudaStream_t);
+int launch_ovo_csr_fused(const float*, const int32_t*, const long long*, int, int, const illico_plan_t*, const illico_flags_t*,
+                         const illico_batch_buffers_t*, double*, long long, const illico_debug_t*, cudaStream_t);
+int launch_ovr_csr_fused(const float*, const int32_t*, const long long*, int, int, const illico_plan_t*, const illico_flags_t*,
+                         const illico_batch_buffers_t*, double*, long long, const illico_debug_t*, cudaStream_t);
 size_t ovo_fused_workspace_bytes(int);
 float ovo_fused_last_ms();
 size_t ovr_table_rec_bytes(const illico_plan_t*);
@@ -165,7 +169,7 @@ int illico_ovr_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t nb
     if (check_plan(plan)) return 1;
     if (plan->ref_group >= 0) { set_error("illico_ovr_dense_f32: plan has a reference group"); return 1; }
     if (!X || !flags || !results) { set_error("illico_ovr_dense_f32: NULL argument"); return 1; }
-    // count-like data: one pass over the matrix, per-group histograms instead of staged lists (fused_dense.cu)
+    // count-like data: one pass over the matrix, per-group histograms instead of staged lists (fused.cu)
     const int rc = launch_ovr_dense_fused(X, ld, gene_lb, nb, plan, flags, buf, results, gstride, dbg, (cudaStream_t)stream);
     if (rc >= 0) return rc;
     if (illico_stage_dense_f32(X, ld, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
@@ -179,7 +183,7 @@ int illico_ovo_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t nb
     if (check_plan(plan)) return 1;
     if (plan->ref_group < 0) { set_error("illico_ovo_dense_f32: plan has no reference group"); return 1; }
     if (!X || !flags || !results) { set_error("illico_ovo_dense_f32: NULL argument"); return 1; }
-    // count-like data: one pass over the matrix, no staged lists (fused_dense.cu); anything else: stage + rank
+    // count-like data: one pass over the matrix, no staged lists (fused.cu); anything else: stage + rank
     const int rc = launch_ovo_dense_fused(X, ld, gene_lb, nb, plan, flags, buf, results, gstride, dbg, (cudaStream_t)stream);
     if (rc >= 0) return rc;
     if (illico_stage_dense_f32(X, ld, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
@@ -190,6 +194,13 @@ int illico_ovr_csr_f32(const float* data, const int32_t* indices, const int64_t*
                        const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf,
                        double* results, int64_t gstride, const illico_debug_t* dbg, void* stream) {
     ILLICO_CHECK_BUF(buf);
+    if (check_plan(plan)) return 1;
+    if ((plan->ref_group >= 0) != false) { set_error("illico_ovr_csr_f32: plan / test mismatch"); return 1; }
+    if (!indptr || !flags || !results) { set_error("illico_ovr_csr_f32: NULL argument"); return 1; }
+    // count-like data: per-group histograms built in shared memory, no staged lists (fused.cu)
+    const int rc = launch_ovr_csr_fused(data, indices, (const long long*)indptr, gene_lb, nb, plan, flags, buf, results, gstride, dbg,
+                                        (cudaStream_t)stream);
+    if (rc >= 0) return rc;
     if (illico_stage_csr_f32(data, indices, indptr, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, buf->workspace,
                              buf->workspace_bytes, stream)) return 1;
     return illico_rank_ovr(buf->ir_vals, buf->ir_cnt, nb, plan, flags, results, gstride, buf->workspace,
@@ -199,6 +210,13 @@ int illico_ovo_csr_f32(const float* data, const int32_t* indices, const int64_t*
                        const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf,
                        double* results, int64_t gstride, const illico_debug_t* dbg, void* stream) {
     ILLICO_CHECK_BUF(buf);
+    if (check_plan(plan)) return 1;
+    if ((plan->ref_group >= 0) != true) { set_error("illico_ovo_csr_f32: plan / test mismatch"); return 1; }
+    if (!indptr || !flags || !results) { set_error("illico_ovo_csr_f32: NULL argument"); return 1; }
+    // count-like data: per-group histograms built in shared memory, no staged lists (fused.cu)
+    const int rc = launch_ovo_csr_fused(data, indices, (const long long*)indptr, gene_lb, nb, plan, flags, buf, results, gstride, dbg,
+                                        (cudaStream_t)stream);
+    if (rc >= 0) return rc;
     if (illico_stage_csr_f32(data, indices, indptr, gene_lb, nb, plan, buf->ir_vals, buf->ir_cnt, buf->workspace,
                              buf->workspace_bytes, stream)) return 1;
     return illico_rank_ovo(buf->ir_vals, buf->ir_cnt, nb, plan, flags, results, gstride, buf->workspace,

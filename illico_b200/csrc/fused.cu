@@ -1,4 +1,4 @@
-// fused_dense.cu -- dense one-versus-reference and one-versus-rest in ONE pass over the matrix, without staged
+// fused.cu -- dense one-versus-reference and one-versus-rest in ONE pass over the matrix, without staged
 // non-zero lists (sm_100a).
 //
 // Replaces, for genes with few distinct values (raw counts, log1p of counts), the pair stage_dense + rank kernel, i.e.
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(128) fused_gene_kernel(int b, const illico_pla
     }
     for (int q = D; q < DCAP; ++q) { gt.wgt[(long long)q * bs + j] = 0u; gt.fval[(long long)q * bs + j] = 0.0; }
     if (OVO) {
-        unsigned long long above = 0;                                            // control values greater than the slot's
+        unsigned long long above = 0, nnz = 0, tie = 0;                          // control values greater than the slot's
         for (int a = D - 1; a >= 0; --a) {
             const int q = order[a];
             const unsigned long long c = gt.mult[(long long)q * bs + j];
@@ -397,16 +397,28 @@ __global__ void __launch_bounds__(128) fused_gene_kernel(int b, const illico_pla
             gt.fval[(long long)q * bs + j] = fc_value(key[q], fl.is_log1p);
             above += c;
         }
+        double sum = 0.0;
+        for (int a = 0; a < D; ++a) {                                            // the control's own sums, ascending
+            const int q = order[a];
+            const unsigned long long c = gt.mult[(long long)q * bs + j];
+            nnz += c;
+            tie += (unsigned long long)cube_minus((long long)c);
+            sum += (double)c * gt.fval[(long long)q * bs + j];
+        }
+        gt.nnz[j] = (uint32_t)nnz;
+        gt.tie[j] = tie;
+        gt.sum[j] = sum;
         return;
     }
     const long long n = pl.n_cells;
+    const bool sparse_order = fl.tie_order == ILLICO_TIES_SPARSE;                // ovr/sparse_ovr.py:83: zero block added last
     unsigned long long nnz = 0;
     for (int q = 0; q < D; ++q) nnz += gt.mult[(long long)q * bs + j];
     const long long n0 = n - (long long)nnz;
     unsigned long long lo = (unsigned long long)n0, t_exact = 0;
     double total = 0.0;
     const unsigned long long zterm = (unsigned long long)cube_minus(n0);
-    double walk = (double)(long long)zterm;                                      // sequential accumulation, zero block first
+    double walk = sparse_order ? 0.0 : (double)(long long)zterm;                 // sequential accumulation of the runs
     for (int a = 0; a < D; ++a) {
         const int q = order[a];
         const unsigned long long c = gt.mult[(long long)q * bs + j];
@@ -419,7 +431,13 @@ __global__ void __launch_bounds__(128) fused_gene_kernel(int b, const illico_pla
         walk += (double)(long long)t3;
         lo += c;
     }
-    const double tie = ((double)t_exact + (double)zterm >= TWO53) ? walk : (double)(t_exact + zterm);
+    double tie;
+    if (sparse_order) {
+        const double x = (double)n0;                                             // n0^3 - n0 in f64, as the reference forms it
+        tie = __dadd_rn(((double)t_exact >= TWO53) ? walk : (double)t_exact, __dsub_rn(__dmul_rn(__dmul_rn(x, x), x), x));
+    } else {
+        tie = ((double)t_exact + (double)zterm >= TWO53) ? walk : (double)(t_exact + zterm);
+    }
     gt.nnz[j] = (uint32_t)(n0 + 1);                                              // doubled mid-rank of the zero block
     gt.sum[j] = total;
     gt.tie[j] = (unsigned long long)__double_as_longlong(tie);
@@ -500,9 +518,200 @@ __global__ void __launch_bounds__(256) fused_epilogue_kernel(int b, const illico
     }
 }
 
+
+// ===================== CSR input: the same histograms, built in shared memory ==========================================
+// Replaces, for count-like data, stage_csr_kernel + rank kernel (illico/ovr/sparse_ovr.py:23-208,
+// illico/ovo/sparse_ovo.py:22-260, illico/utils/sparse/csr.py:103-257).  One CTA per plan segment (<= 512 cells of one
+// group) and gene tile: it walks the segment's CSR rows once (warp per row, coalesced index/value loads) and counts
+// every stored value in a shared-memory histogram [gene][slot] (12 x u16 per gene = the 24-byte record), then writes
+// the records.  No staged lists, no sort: 8 bytes read per stored value, 24 bytes written per (gene, group).
+constexpr int CSRF_THREADS = 1024;
+constexpr int CSRF_TILE = 8192;                    // genes per CTA: 8192 x 24 B = 192 KB of shared memory
+
+// slot of value v in gene j's global table (claims a free slot if the value is new); -1 = the gene is handed back
+__device__ __forceinline__ int gtab_slot(float* gkey, int bs, float v) {
+    int q = (int)v - 1;                                                          // counts: value c sits in slot c - 1
+    if (q >= 0 && q < DCAP && __ldcg(gkey + (long long)q * bs) == v) return q;
+    if (!(v > 0.0f)) return -1;                                                  // negative or NaN
+    for (q = 0; q < DCAP; ++q) {
+        float k = __ldcg(gkey + (long long)q * bs);
+        if (k == 0.0f) {
+            const unsigned old = atomicCAS(reinterpret_cast<unsigned*>(gkey + (long long)q * bs), 0u, __float_as_uint(v));
+            k = old ? __uint_as_float(old) : v;
+        }
+        if (k == v) return q;
+    }
+    return -1;                                                                   // a 13th distinct value
+}
+
+__global__ void fused_seed_kernel(Gtab gt, int bs, int identity) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bs) return;
+#pragma unroll
+    for (int q = 0; q < DCAP; ++q) {
+        gt.key[(long long)q * bs + i] = identity ? (float)(q + 1) : 0.0f;       // raw counts: slots 1 .. 12 up front
+        gt.mult[(long long)q * bs + i] = 0u;
+    }
+    gt.bad[i] = 0;
+    if (i == 0) *gt.n_bad = 0;
+}
+
+// records of groups cut into several segments are accumulated with atomics: they start from zero
+__global__ void fused_zero_multi_kernel(int b, const illico_plan_t pl, unsigned long long* __restrict__ rec, long long gstride) {
+    const int g = blockIdx.y;
+    if (pl.group_seg[g + 1] - pl.group_seg[g] < 2) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * b; i += gridDim.x * blockDim.x) rec[(long long)g * gstride + i] = 0ull;
+}
+
+template <bool OVO>
+__global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const float* __restrict__ data, const int32_t* __restrict__ indices,
+                                                                        const long long* __restrict__ indptr, int gene_lb, int b,
+                                                                        const illico_plan_t pl, Gtab gt, int bs,
+                                                                        unsigned long long* __restrict__ rec, long long gstride) {
+    extern __shared__ __align__(16) uint32_t hist[];             // [genes of the tile][6]: 12 u16 counters per gene
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int s = blockIdx.y, g = pl.seg_group[s];
+    const int j_lo = blockIdx.x * CSRF_TILE, ng = min(CSRF_TILE, b - j_lo);
+    __shared__ int stop;
+    if (t == 0) stop = 2 * *reinterpret_cast<volatile int*>(gt.n_bad) > b;   // mostly continuous data: the general path redoes the batch
+    for (int i = t; i < ng * 6; i += CSRF_THREADS) hist[i] = 0u;
+    __syncthreads();
+    if (stop) return;
+    const int c_lo = gene_lb + j_lo, c_hi = c_lo + ng;
+    const int p0 = pl.seg_pos[s], p1 = pl.seg_pos[s + 1];
+    constexpr int NW = CSRF_THREADS / 32;
+    // the warp's rows are p0 + w, p0 + w + 32, ...: their extents are fetched up front (lane k holds row k's), so the
+    // perm -> indptr -> indices dependency is paid once per warp and not once per row
+    long long my_e0 = 0, my_e1 = 0;
+    {
+        const int p = p0 + w + lane * NW;
+        if (p < p1) {
+            const long long r = pl.perm[p];
+            my_e0 = indptr[r];
+            my_e1 = indptr[r + 1];
+        }
+    }
+    for (int p = p0 + w, k = 0; p < p1; p += NW, ++k) {
+        if (k == 32) {                                            // (segments are at most 512 cells: one round; kept general)
+            const int pp = p + lane * NW;
+            my_e0 = my_e1 = 0;
+            if (pp < p1) { const long long r = pl.perm[pp]; my_e0 = indptr[r]; my_e1 = indptr[r + 1]; }
+            k = 0;
+        }
+        long long e0 = __shfl_sync(FULL, my_e0, k);
+        const long long e1 = __shfl_sync(FULL, my_e1, k);
+        if (c_lo > 0) {                                           // first stored element of the row inside the gene window
+            long long lo = e0, hi = e1;
+            while (lo < hi) { const long long mid = (lo + hi) >> 1; if (indices[mid] < c_lo) lo = mid + 1; else hi = mid; }
+            e0 = lo;
+        }
+        // four 32-element chunks per step: the index / value loads, then the table probes, are issued together
+        for (long long e = e0 + lane; ; e += 128) {
+            int c[4];
+            float v[4], kq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c[u] = (e + 32 * u < e1) ? indices[e + 32 * u] : 0x7fffffff;
+            if (__all_sync(FULL, c[0] >= c_hi)) break;            // column indices ascend inside a row
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (c[u] < c_hi) ? __ldcs(data + e + 32 * u) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                         // probe of the usual slot (counts: value c in slot c - 1)
+                const int q = min(max((int)v[u] - 1, 0), DCAP - 1);
+                kq[u] = (v[u] != 0.0f) ? __ldcg(gt.key + (long long)q * bs + j_lo + (c[u] - c_lo)) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (v[u] != 0.0f) {                               // explicitly stored zeros are zeros
+                    const int jj = c[u] - c_lo;
+                    int q = min(max((int)v[u] - 1, 0), DCAP - 1);
+                    if (kq[u] != v[u]) q = gtab_slot(gt.key + j_lo + jj, bs, v[u]);
+                    if (q >= 0) {
+                        atomicAdd(&hist[jj * 6 + (q >> 1)], 1u << (16 * (q & 1)));
+                    } else {                                      // hand the gene back, counted once
+                        const int j = j_lo + jj;
+                        const unsigned bit = 1u << (8 * (j & 3));
+                        const unsigned old = atomicOr(reinterpret_cast<unsigned*>(gt.bad + (j & ~3)), bit);
+                        if (!(old & bit)) atomicAdd(gt.n_bad, 1);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const bool multi = pl.group_seg[g + 1] - pl.group_seg[g] > 1;
+    for (int jj = t; jj < ng; jj += CSRF_THREADS) {
+        const int j = j_lo + jj;
+        uint32_t wd[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) wd[k] = hist[jj * 6 + k];
+        if (OVO && g == pl.ref_group) {
+            // the control's histogram is the table's multiplicity column
+#pragma unroll
+            for (int q = 0; q < DCAP; ++q) {
+                const uint32_t cq = (wd[q >> 1] >> (16 * (q & 1))) & 0xffffu;
+                if (cq) atomicAdd(gt.mult + (long long)q * bs + j, cq);
+            }
+        } else if (!multi) {
+            unsigned long long* o = rec + (long long)g * gstride + (long long)j * 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) o[k] = (unsigned long long)wd[2 * k] | ((unsigned long long)wd[2 * k + 1] << 32);
+        } else {
+            uint32_t* o = reinterpret_cast<uint32_t*>(rec + (long long)g * gstride + (long long)j * 3);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) if (wd[k]) atomicAdd(o + k, wd[k]);   // u16 pairs: no carry, a group has < 65536 cells
+        }
+    }
+}
+
+// one-versus-rest: the whole gene's histogram = the sum of its groups' records
+__global__ void __launch_bounds__(256) fused_hist_sum_kernel(int b, int G, int groups_per_block, Gtab gt, int bs,
+                                                             const unsigned long long* __restrict__ rec, long long gstride) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= b || gt.bad[j]) return;
+    const int ga = blockIdx.y * groups_per_block, gb = min(G, ga + groups_per_block);
+    uint32_t acc[DCAP];
+#pragma unroll
+    for (int q = 0; q < DCAP; ++q) acc[q] = 0u;
+    for (int g = ga; g < gb; ++g) {
+        const unsigned long long* r = rec + (long long)g * gstride + (long long)j * 3;
+        const unsigned long long wds[3] = {r[0], r[1], r[2]};
+#pragma unroll
+        for (int q = 0; q < DCAP; ++q) acc[q] += (uint32_t)((wds[q >> 2] >> (16 * (q & 3))) & 0xffffull);
+    }
+#pragma unroll
+    for (int q = 0; q < DCAP; ++q)
+        if (acc[q]) atomicAdd(gt.mult + (long long)q * bs + j, acc[q]);
+}
+
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
+}
+
+// Genes handed back by a fused pass go through the general path in merged runs: a launch costs about as much as
+// ILLICO_FUSED_GAP genes, so runs closer than that are joined (good genes inside a run are simply recomputed).
+// Returns 0 = done, 1 = error, -1 = redo the whole batch through the general path.
+template <typename F>
+int hand_back(const std::vector<unsigned char>& bad, int b, bool side_arrays, F general) {
+    int first = -1, last = -1;
+    for (int j = 0; j < b; ++j)
+        if (bad[j]) { if (first < 0) first = j; last = j; }
+    if (first < 0) return 0;
+    if (side_arrays) return -1;   // debug / group-sum arrays are indexed by the whole batch
+    const int gap = env_int("ILLICO_FUSED_GAP", 128);
+    int lb = first;
+    while (lb <= last) {
+        int ub = lb + 1, j = lb + 1;
+        while (j <= last) {
+            if (bad[j]) { ub = j + 1; ++j; }
+            else if (j - ub < gap) ++j;
+            else break;
+        }
+        if (general(lb, ub)) return 1;
+        lb = ub;
+        while (lb <= last && !bad[lb]) ++lb;
+    }
+    return 0;
 }
 
 thread_local float g_last_fused_ms = -1.0f;
@@ -608,31 +817,13 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     }
-    int first = -1, last = -1, count = 0;
-    for (int j = 0; j < b; ++j)
-        if (bad[j]) { if (first < 0) first = j; last = j; ++count; }
-    if (count == 0) return 0;
-    if (dbg || flags->group_sums) return -1;   // their [G, b] side arrays are indexed by the whole batch: redo it all
-    const int gap = env_int("ILLICO_FUSED_GAP", 128);   // a launch costs about as much as this many genes
-    int lb = first;
-    while (lb <= last) {
-        int ub = lb + 1, j = lb + 1;
-        while (j <= last) {
-            if (bad[j]) { ub = j + 1; ++j; }
-            else if (j - ub < gap) ++j;
-            else break;
-        }
-        // genes [lb, ub) of the batch (good genes inside a merged run are simply recomputed)
+    return hand_back(bad, b, dbg != nullptr || flags->group_sums != nullptr, [&](int lb, int ub) {
         if (launch_stage_dense(X, ld, gene_lb + lb, ub - lb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
-        const int rr = OVO ? launch_ovo(buf->ir_vals, buf->ir_cnt, ub - lb, plan, flags, results + (long long)lb * 3, gstride,
-                                        buf->workspace, buf->workspace_bytes, nullptr, stream)
-                           : launch_ovr(buf->ir_vals, buf->ir_cnt, ub - lb, plan, flags, results + (long long)lb * 3, gstride,
-                                        buf->workspace, buf->workspace_bytes, nullptr, stream);
-        if (rr) return 1;
-        lb = ub;
-        while (lb <= last && !bad[lb]) ++lb;
-    }
-    return 0;
+        return OVO ? launch_ovo(buf->ir_vals, buf->ir_cnt, ub - lb, plan, flags, results + (long long)lb * 3, gstride,
+                                buf->workspace, buf->workspace_bytes, nullptr, stream)
+                   : launch_ovr(buf->ir_vals, buf->ir_cnt, ub - lb, plan, flags, results + (long long)lb * 3, gstride,
+                                buf->workspace, buf->workspace_bytes, nullptr, stream);
+    });
 }
 
 }  // namespace
@@ -651,6 +842,107 @@ int launch_ovr_dense_fused(const float* X, long long ld, int gene_lb, int b, con
                            const illico_flags_t* flags, const illico_batch_buffers_t* buf, double* results, long long gstride,
                            const illico_debug_t* dbg, cudaStream_t stream) {
     return run_fused<false>(X, ld, gene_lb, b, plan, flags, buf, results, gstride, dbg, stream);
+}
+
+
+int launch_stage_csr(const float*, const int32_t*, const long long*, int, int, const illico_plan_t*, float*, uint32_t*,
+                     void*, size_t, cudaStream_t);
+
+namespace {
+
+// The fused path for one gene batch of a CSR matrix.  0 = done, 1 = error, -1 = not applicable.
+template <bool OVO>
+int run_fused_csr(const float* data, const int32_t* indices, const long long* indptr, int gene_lb, int b,
+                  const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf, double* results,
+                  long long gstride, const illico_debug_t* dbg, cudaStream_t stream) {
+    if (env_int(OVO ? "ILLICO_OVO_FUSED" : "ILLICO_OVR_FUSED", 1) == 0 || env_int("ILLICO_CSR_FUSED", 1) == 0 || b <= 0) return -1;
+    if (plan->max_group_size >= 65536 || plan->n_groups < 2 || plan->n_groups > 65535 || plan->n_segments > 65535) return -1;
+    if (OVO && (long long)plan->ref_group_size + plan->max_group_size > PAIR_MAX) return -1;
+    if (!OVO && flags->group_sums) return -1;
+    if (buf->workspace_bytes < gtab_bytes(b)) return -1;
+    const int bs = (b + 63) & ~63;
+    Gtab gt = gtab_carve(buf->workspace, b);
+    unsigned long long* rec = reinterpret_cast<unsigned long long*>(results);
+    const int G = plan->n_groups;
+
+    // tables: raw counts get slots 1 .. 12 up front (log1p data claims its slots while streaming)
+    fused_seed_kernel<<<(bs + 255) / 256, 256, 0, stream>>>(gt, bs, flags->is_log1p ? 0 : 1);
+    count_launch();
+    fused_zero_multi_kernel<<<dim3(8, (unsigned)G), 256, 0, stream>>>(b, *plan, rec, gstride);
+    count_launch();
+    ILLICO_CUDA_OK(cudaGetLastError());
+
+    const bool timed = env_int("ILLICO_PROFILE", 0) != 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timed) {
+        ILLICO_CUDA_OK(cudaEventCreate(&e0));
+        ILLICO_CUDA_OK(cudaEventCreate(&e1));
+        ILLICO_CUDA_OK(cudaEventRecord(e0, stream));
+    }
+    {
+        auto kern = fused_csr_pass_kernel<OVO>;
+        const int tile = b < CSRF_TILE ? b : CSRF_TILE;
+        const size_t smem = (size_t)tile * 24;
+        ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const dim3 grid((unsigned)((b + CSRF_TILE - 1) / CSRF_TILE), (unsigned)plan->n_segments);
+        kern<<<grid, CSRF_THREADS, smem, stream>>>(data, indices, indptr, gene_lb, b, *plan, gt, bs, rec, gstride);
+        count_launch();
+        ILLICO_CUDA_OK(cudaGetLastError());
+    }
+    if (timed) ILLICO_CUDA_OK(cudaEventRecord(e1, stream));
+    int n_bad = 0;
+    ILLICO_CUDA_OK(cudaMemcpyAsync(&n_bad, gt.n_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
+    if (timed) {
+        ILLICO_CUDA_OK(cudaEventElapsedTime(&g_last_fused_ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    if (2 * n_bad > b) return -1;   // mostly continuous data: the pass stopped early, the general path does the batch
+
+    if (!OVO) {
+        const int gpb = 64;
+        fused_hist_sum_kernel<<<dim3((unsigned)((b + 255) / 256), (unsigned)((G + gpb - 1) / gpb)), 256, 0, stream>>>(b, G, gpb, gt, bs, rec,
+                                                                                                                 gstride);
+        count_launch();
+    }
+    fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, (dbg && !OVO) ? dbg->tie_sum : nullptr,
+                                                                (dbg && !OVO) ? (long long*)dbg->tie_exact : nullptr);
+    count_launch();
+    {
+        int gx = (b + 255) / 256;
+        if (gx > 64) gx = 64;
+        fused_epilogue_kernel<OVO><<<dim3((unsigned)gx, (unsigned)G), 256, 0, stream>>>(
+            b, *plan, *flags, gt, bs, results, gstride, dbg ? (long long*)dbg->u2 : nullptr,
+            (dbg && OVO) ? dbg->tie_sum : nullptr, (dbg && OVO) ? (long long*)dbg->tie_exact : nullptr);
+        count_launch();
+        ILLICO_CUDA_OK(cudaGetLastError());
+    }
+    if (n_bad == 0) return 0;
+    std::vector<unsigned char> bad((size_t)b);
+    ILLICO_CUDA_OK(cudaMemcpyAsync(bad.data(), gt.bad, (size_t)b, cudaMemcpyDeviceToHost, stream));
+    ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
+    return hand_back(bad, b, dbg != nullptr || flags->group_sums != nullptr, [&](int lb, int ub) {
+        if (launch_stage_csr(data, indices, indptr, gene_lb + lb, ub - lb, plan, buf->ir_vals, buf->ir_cnt, buf->workspace,
+                             buf->workspace_bytes, stream)) return 1;
+        return OVO ? launch_ovo(buf->ir_vals, buf->ir_cnt, ub - lb, plan, flags, results + (long long)lb * 3, gstride,
+                                buf->workspace, buf->workspace_bytes, nullptr, stream)
+                   : launch_ovr(buf->ir_vals, buf->ir_cnt, ub - lb, plan, flags, results + (long long)lb * 3, gstride,
+                                buf->workspace, buf->workspace_bytes, nullptr, stream);
+    });
+}
+
+}  // namespace
+
+int launch_ovo_csr_fused(const float* data, const int32_t* indices, const long long* indptr, int gene_lb, int b,
+                         const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf, double* results,
+                         long long gstride, const illico_debug_t* dbg, cudaStream_t stream) {
+    return run_fused_csr<true>(data, indices, indptr, gene_lb, b, plan, flags, buf, results, gstride, dbg, stream);
+}
+int launch_ovr_csr_fused(const float* data, const int32_t* indices, const long long* indptr, int gene_lb, int b,
+                         const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf, double* results,
+                         long long gstride, const illico_debug_t* dbg, cudaStream_t stream) {
+    return run_fused_csr<false>(data, indices, indptr, gene_lb, b, plan, flags, buf, results, gstride, dbg, stream);
 }
 
 }  // namespace illico

@@ -1,0 +1,20 @@
+#!/bin/bash
+out=gpurun_out/exp_csrf.log
+: > $out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 >> $out
+run() {
+  echo "== $WL $*" >> $out
+  env "$@" timeout 300 python bench.py --workload ${WL:-dense_ovr} --no-e2e --no-cpu-baseline --steps 5 --warmup 3 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); r = d['roofline']; print('ms_per_step', d['ms_per_step'], 'fused_ms', r.get('fused_ms'), 'kernel', r['kernel'], 'frac', r['frac'], 'launches', d.get('gpu_launches'))
+    elif 'Warning' not in l and 'to_sparse' not in l: print(l.rstrip())
+" >> $out
+}
+WL=csr_ovo run ILLICO_CSR_FUSED=1
+WL=csr_ovr run ILLICO_CSR_FUSED=1
+WL=csr_ovo run ILLICO_CSR_FUSED=0
+WL=dense_ovo run A=1
+WL=dense_ovr run A=1
+cat $out

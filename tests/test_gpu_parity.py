@@ -376,7 +376,7 @@ def _fused_case(kind, n_cells=6000, n_genes=72, seed=31):
 
 @pytest.mark.parametrize("kind", ["first", "middle", "last", "middle:log1p", "middle:less"])
 def test_fused_ovo_routes_match_general_path_and_oracle(monkeypatch, kind):
-    """fused_dense.cu: table genes, extras, handed-back genes (merged runs), control position, log1p, alternatives:
+    """fused.cu: table genes, extras, handed-back genes (merged runs), control position, log1p, alternatives:
     identical U to the general path and to the oracle; p / fold change within tolerance."""
     X, labels, ref = _fused_case(kind)
     log1p = kind.endswith("log1p")
@@ -471,3 +471,43 @@ def test_fused_ovr_tie_sum_above_2_53(monkeypatch):
     _, general = _run(X, labels, None, is_log1p=False)
     for a, b in zip(fused[:2], general[:2]):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("test", ["ovo", "ovr"])
+@pytest.mark.parametrize("kind", ["first", "middle:log1p", "last:less"])
+def test_fused_csr_routes_match_general_path_and_oracle(monkeypatch, test, kind):
+    """CSR input through the shared-memory histogram pass (fused.cu): count genes, genes handed back, multi-segment
+    groups (atomically accumulated records), log1p tables claimed while streaming -- against the general CSR path
+    and the oracle."""
+    from scipy import sparse
+
+    X, labels, ref = _fused_case(kind, n_cells=9000)
+    X = np.abs(X)
+    X[X > 1e20] = 3.0
+    log1p = "log1p" in kind
+    if log1p:
+        X = np.log1p(X).astype(np.float32)
+    # one big group (cut into several 512-cell segments) next to the small ones
+    labels = list(labels)
+    for i in range(0, 2400):
+        labels[i] = "g05"
+    Xs = sparse.csr_matrix(X)
+    reference = ref if test == "ovo" else None
+    kw = dict(is_log1p=log1p, alternative="less" if kind.endswith("less") else "two-sided")
+    from illico_b200 import _lib
+
+    monkeypatch.setenv("ILLICO_CSR_FUSED", "1")
+    monkeypatch.setenv("ILLICO_PROFILE", "1")
+    groups, fused = _run(Xs, labels, reference, batch_size="auto", **kw)
+    assert _lib.load().illico_last_fused_ms() >= 0, "the fused CSR pass did not run"
+    monkeypatch.setenv("ILLICO_CSR_FUSED", "0")
+    _, general = _run(Xs, labels, reference, batch_size="auto", **kw)
+    ref_row = int(np.searchsorted(groups, reference)) if reference is not None else None
+    rows = np.ones(len(groups), bool)
+    if ref_row is not None:
+        rows[ref_row] = False
+    np.testing.assert_array_equal(fused[1], general[1])
+    np.testing.assert_allclose(fused[0][rows], general[0][rows], rtol=1e-13, atol=2.3e-308)
+    g, p, U, fc = oracle.run(Xs, labels, reference, **kw)
+    assert_parity(fused, (p, U, fc), ref_row=ref_row, fc_rtol=FC_RTOL_LOG1P_F32 if log1p else FC_RTOL,
+                  what=f"fused csr {test} {kind}")
