@@ -211,15 +211,18 @@ def upload_dense(X: np.ndarray, device, gene_lb: int = 0, gene_ub: int | None = 
 
 
 def upload_sparse(X, fmt: str, device) -> DeviceMatrix:
+    """Enqueues the copies of a scipy CSR / CSC matrix.  The small ``indptr`` goes first: it is converted (int64) into
+    pageable memory, and a copy from pageable memory waits for everything queued before it -- after the two big
+    arrays it would block the host for the whole upload and nothing could overlap with it."""
     device = require_cuda(device)
     with torch.cuda.device(device):
+        indptr = torch.from_numpy(np.ascontiguousarray(X.indptr, dtype=np.int64)).to(device, non_blocking=True)
         data = torch.from_numpy(np.ascontiguousarray(X.data))
         data = data.to(device, non_blocking=True)
         raw = None
         if data.dtype != torch.float32:
             data, raw = _to_f32_or_wide(data)
         indices = torch.from_numpy(np.ascontiguousarray(X.indices, dtype=np.int32)).to(device, non_blocking=True)
-        indptr = torch.from_numpy(np.ascontiguousarray(X.indptr, dtype=np.int64)).to(device, non_blocking=True)
     return DeviceMatrix(fmt, tuple(X.shape), data, indices, indptr, raw=raw)
 
 

@@ -36,6 +36,22 @@ def _factorize_sorted(groups):
     factorisation (12 ms instead of 170 ms at 300k labels); the sorted uniques are the same."""
     import pandas as pd
 
+    if isinstance(groups, (pd.Series, pd.Index)) and isinstance(groups.dtype, pd.CategoricalDtype):
+        # AnnData keeps obs columns categorical: the codes are already there (1 ms instead of 20 ms at 300k cells);
+        # only the categories in use count, in np.unique's (sorted) order
+        cat = groups.cat if isinstance(groups, pd.Series) else groups
+        codes = np.asarray(cat.codes)
+        if (codes < 0).any():
+            raise ValueError("group labels contain missing values")
+        cats = np.asarray(cat.categories)
+        used = np.flatnonzero(np.bincount(codes, minlength=len(cats)) > 0)
+        uniq = cats[used]
+        if uniq.dtype == object and all(isinstance(x, str) for x in uniq):
+            uniq = uniq.astype(str)
+        order = np.argsort(uniq, kind="stable")
+        remap = np.full(len(cats), -1, dtype=np.int64)
+        remap[used[order]] = np.arange(used.size)
+        return uniq[order], remap[codes]
     if isinstance(groups, (pd.Series, pd.Index)):
         arr = groups.to_numpy()
     else:

@@ -202,3 +202,26 @@ def test_order_preserving_recoding_on_cpu():
         order = np.argsort(x, kind="stable")
         assert np.all(np.diff(c[order]) >= 0)
         assert np.array_equal(np.diff(c[order]) == 0, np.diff(x[order]) == 0)
+
+
+def test_categorical_labels_encode_like_strings():
+    """AnnData obs columns are categorical: the fast path gives the same groups / codes as the string path,
+    drops unused categories and keeps np.unique's order even when the categories are not sorted."""
+    import pandas as pd
+
+    from illico_b200.groups import encode_and_count_groups
+
+    rng = np.random.RandomState(3)
+    names = np.array(["zeta", "alpha", "non-targeting", "beta", "unused", "Gamma"])
+    labels = names[rng.choice([0, 1, 2, 3, 5], size=5000)]
+    ser = pd.Series(pd.Categorical(labels, categories=names))
+    u1, g1 = encode_and_count_groups(ser, "non-targeting")
+    u2, g2 = encode_and_count_groups(list(labels), "non-targeting")
+    assert list(u1) == list(u2) == sorted(set(labels))
+    np.testing.assert_array_equal(g1.encoded_groups, g2.encoded_groups)
+    np.testing.assert_array_equal(g1.counts, g2.counts)
+    assert g1.encoded_ref_group == g2.encoded_ref_group
+    import pytest
+
+    with pytest.raises(ValueError, match="not present"):
+        encode_and_count_groups(ser, "unused")
