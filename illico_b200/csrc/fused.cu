@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const f
     const int s = blockIdx.y, g = pl.seg_group[s];
     const int j_lo = blockIdx.x * CSRF_TILE, ng = min(CSRF_TILE, b - j_lo);
     __shared__ int stop;
-    if (t == 0) stop = 2 * *reinterpret_cast<volatile int*>(gt.n_bad) > b;   // mostly continuous data: the general path redoes the batch
+    if (t == 0) stop = 8 * *reinterpret_cast<volatile int*>(gt.n_bad) > b;   // many genes handed back: the general path redoes the batch
     for (int i = t; i < ng * 6; i += CSRF_THREADS) hist[i] = 0u;
     __syncthreads();
     if (stop) return;
@@ -609,11 +609,14 @@ __global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const f
         for (long long e = e0 + lane; ; e += 128) {
             int c[4];
             float v[4], kq[4];
+            // indices and values are requested together (one DRAM latency per step, not two)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) c[u] = (e + 32 * u < e1) ? indices[e + 32 * u] : 0x7fffffff;
+            for (int u = 0; u < 4; ++u) c[u] = (e + 32 * u < e1) ? __ldcs(indices + e + 32 * u) : 0x7fffffff;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (e + 32 * u < e1) ? __ldcs(data + e + 32 * u) : 0.0f;
             if (__all_sync(FULL, c[0] >= c_hi)) break;            // column indices ascend inside a row
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = (c[u] < c_hi) ? __ldcs(data + e + 32 * u) : 0.0f;
+            for (int u = 0; u < 4; ++u) if (c[u] >= c_hi) v[u] = 0.0f;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {                         // probe of the usual slot (counts: value c in slot c - 1)
                 const int q = min(max((int)v[u] - 1, 0), DCAP - 1);
@@ -691,6 +694,32 @@ int env_int(const char* name, int dflt) {
 // Genes handed back by a fused pass go through the general path in merged runs: a launch costs about as much as
 // ILLICO_FUSED_GAP genes, so runs closer than that are joined (good genes inside a run are simply recomputed).
 // Returns 0 = done, 1 = error, -1 = redo the whole batch through the general path.
+// fraction of the batch the merged runs of handed-back genes would cover (what the general path would redo)
+double hand_back_coverage(const std::vector<unsigned char>& bad, int b) {
+    const int gap = env_int("ILLICO_FUSED_GAP", 128);
+    long long covered = 0;
+    int j = 0;
+    while (j < b) {
+        if (!bad[j]) { ++j; continue; }
+        int ub = j + 1, k = j + 1;
+        while (k < b) {
+            if (bad[k]) { ub = k + 1; ++k; }
+            else if (k - ub < gap) ++k;
+            else break;
+        }
+        covered += ub - j;
+        j = ub;
+    }
+    return b > 0 ? (double)covered / (double)b : 0.0;
+}
+// The fused pass only pays off while few genes are handed back: scattered ones drag their neighbours into the merged
+// runs.  Above this coverage the general path does the whole batch (measured costs at the K562 shape: fused 2.3 ms,
+// general 3.4 ms per full batch).
+double max_hand_back() {
+    const char* v = getenv("ILLICO_FUSED_MAX_HANDBACK");
+    return v ? atof(v) : 0.3;
+}
+
 template <typename F>
 int hand_back(const std::vector<unsigned char>& bad, int b, bool side_arrays, F general) {
     int first = -1, last = -1;
@@ -766,10 +795,11 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
     }
     if (!OVO)   // the sample only seeds the slots; gt.mult restarts as the whole gene's histogram
         ILLICO_CUDA_OK(cudaMemsetAsync(gt.mult, 0, (size_t)bs * DCAP * sizeof(uint32_t), stream));
-    int n_bad = 0;
-    ILLICO_CUDA_OK(cudaMemcpyAsync(&n_bad, gt.n_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    std::vector<unsigned char> bad((size_t)b);
+    ILLICO_CUDA_OK(cudaMemcpyAsync(bad.data(), gt.bad, (size_t)b, cudaMemcpyDeviceToHost, stream));
     ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
-    if (2 * n_bad > b) return -1;   // mostly continuous data: the general path is the right one for this batch
+    // genes the table step already hands back (continuous data, high counts): is the fused pass still worth it?
+    if (hand_back_coverage(bad, b) > max_hand_back()) return -1;
 
     // 2. the pass over the matrix
     long long avg_g = plan->n_cells / plan->n_groups;
@@ -809,7 +839,6 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
     }
 
     // 4. genes handed back: general path, in merged runs
-    std::vector<unsigned char> bad((size_t)b);
     ILLICO_CUDA_OK(cudaMemcpyAsync(bad.data(), gt.bad, (size_t)b, cudaMemcpyDeviceToHost, stream));
     ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
     if (timed) {
@@ -898,7 +927,7 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     }
-    if (2 * n_bad > b) return -1;   // mostly continuous data: the pass stopped early, the general path does the batch
+    if (8 * n_bad > b) return -1;   // the pass stopped early (continuous data, high counts): the general path does the batch
 
     if (!OVO) {
         const int gpb = 64;
@@ -922,6 +951,7 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
     std::vector<unsigned char> bad((size_t)b);
     ILLICO_CUDA_OK(cudaMemcpyAsync(bad.data(), gt.bad, (size_t)b, cudaMemcpyDeviceToHost, stream));
     ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
+    if (hand_back_coverage(bad, b) > 2.0 * max_hand_back()) return -1;   // the merged runs are most of the batch anyway
     return hand_back(bad, b, dbg != nullptr || flags->group_sums != nullptr, [&](int lb, int ub) {
         if (launch_stage_csr(data, indices, indptr, gene_lb + lb, ub - lb, plan, buf->ir_vals, buf->ir_cnt, buf->workspace,
                              buf->workspace_bytes, stream)) return 1;

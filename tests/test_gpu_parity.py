@@ -387,6 +387,8 @@ def test_fused_ovo_routes_match_general_path_and_oracle(monkeypatch, kind):
 
     monkeypatch.setenv("ILLICO_OVO_FUSED", "1")
     monkeypatch.setenv("ILLICO_PROFILE", "1")
+    monkeypatch.setenv("ILLICO_FUSED_MAX_HANDBACK", "1.0")   # keep the fused pass although many genes are handed back
+    monkeypatch.setenv("ILLICO_FUSED_GAP", "2")              # ... in several separate runs
     groups, fused = _run(X, labels, ref, batch_size="auto", **kw)
     assert _lib.load().illico_last_fused_ms() >= 0, "the fused kernel did not run"
     monkeypatch.setenv("ILLICO_OVO_FUSED", "0")
@@ -451,6 +453,8 @@ def test_fused_ovr_routes_match_general_path_and_oracle(monkeypatch, kind):
 
     monkeypatch.setenv("ILLICO_OVR_FUSED", "1")
     monkeypatch.setenv("ILLICO_PROFILE", "1")
+    monkeypatch.setenv("ILLICO_FUSED_MAX_HANDBACK", "1.0")
+    monkeypatch.setenv("ILLICO_FUSED_GAP", "2")
     groups, fused = _run(X, labels, None, batch_size="auto", **kw)
     assert _lib.load().illico_last_fused_ms() >= 0, "the fused kernel did not run"
     monkeypatch.setenv("ILLICO_OVR_FUSED", "0")
@@ -498,6 +502,8 @@ def test_fused_csr_routes_match_general_path_and_oracle(monkeypatch, test, kind)
 
     monkeypatch.setenv("ILLICO_CSR_FUSED", "1")
     monkeypatch.setenv("ILLICO_PROFILE", "1")
+    monkeypatch.setenv("ILLICO_FUSED_MAX_HANDBACK", "1.0")
+    monkeypatch.setenv("ILLICO_FUSED_GAP", "2")
     groups, fused = _run(Xs, labels, reference, batch_size="auto", **kw)
     assert _lib.load().illico_last_fused_ms() >= 0, "the fused CSR pass did not run"
     monkeypatch.setenv("ILLICO_CSR_FUSED", "0")
@@ -511,3 +517,20 @@ def test_fused_csr_routes_match_general_path_and_oracle(monkeypatch, test, kind)
     g, p, U, fc = oracle.run(Xs, labels, reference, **kw)
     assert_parity(fused, (p, U, fc), ref_row=ref_row, fc_rtol=FC_RTOL_LOG1P_F32 if log1p else FC_RTOL,
                   what=f"fused csr {test} {kind}")
+
+
+@pytest.mark.parametrize("fmt", ["dense", "csr"])
+def test_fused_gate_falls_back_when_many_genes_are_handed_back(monkeypatch, fmt):
+    """Default policy: a batch whose handed-back genes (merged runs) cover more than 30 % of it is done by the general
+    path as a whole; the answer is the same either way."""
+    X, labels, ref = _fused_case("middle")
+    X = np.abs(X)
+    X[X > 1e20] = 3.0
+    Xf = C.to_format(X, fmt)
+    from illico_b200 import _lib
+
+    before = _lib.launch_count()
+    groups, got = _run(Xf, labels, ref, is_log1p=False)
+    assert _lib.launch_count() > before
+    g, p, U, fc = oracle.run(Xf, labels, ref, is_log1p=False)
+    assert_parity(got, (p, U, fc), ref_row=int(np.searchsorted(groups, ref)), what=f"gate {fmt}")
