@@ -446,23 +446,41 @@ __global__ void __launch_bounds__(128) fused_gene_kernel(int b, const illico_pla
 }
 
 // ---- 3b. epilogue: 24-byte histogram -> (p, U, fold change), in place ---------------------------------------------------
-// Block row = group, threads over genes (coalesced table reads, 24-byte contiguous records).
+// Thread = gene, looping over a slice of the groups: the gene's table (weights, multiplicities, f(value)) and scalars
+// stay in registers, so the unrolled 12-slot fold has no loads and no address arithmetic; records of adjacent genes
+// are adjacent, so every warp access is a contiguous 768-byte run.
+constexpr int EPI_GROUPS = 16;   // groups per thread
 template <bool OVO>
-__global__ void __launch_bounds__(256) fused_epilogue_kernel(int b, const illico_plan_t pl, const illico_flags_t fl, Gtab gt,
+__global__ void __launch_bounds__(256, 3) fused_epilogue_kernel(int b, const illico_plan_t pl, const illico_flags_t fl, Gtab gt,
                                                              int bs, double* __restrict__ results, long long gstride,
                                                              long long* dbg_u2, double* dbg_tie, long long* dbg_tie_exact) {
-    const int g = blockIdx.y, ref = pl.ref_group;
-    const long long n = pl.n_cells, n_t = pl.group_size[g];
-    const long long n_r = OVO ? (long long)pl.group_size[ref] : n - n_t;         // the sample U is reported for
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= b || gt.bad[j]) return;
+    const int G = pl.n_groups, ref = pl.ref_group;
+    const int ga = blockIdx.y * EPI_GROUPS, gb = min(G, ga + EPI_GROUPS);
+    uint32_t wgt[DCAP], mult[OVO ? DCAP : 1];
+    double fval[DCAP];
+#pragma unroll
+    for (int q = 0; q < DCAP; ++q) {
+        wgt[q] = gt.wgt[(long long)q * bs + j];
+        fval[q] = gt.fval[(long long)q * bs + j];
+        if (OVO) mult[OVO ? q : 0] = gt.mult[(long long)q * bs + j];
+    }
+    const long long n = pl.n_cells;
     const double cc = fl.use_continuity ? 0.5 : 0.0;
-    const double mu = (double)(n_r * n_t) / 2.0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < b; j += gridDim.x * blockDim.x) {
-        if (gt.bad[j]) continue;
+    const long long g_nnz = gt.nnz[j];                       // OVO: control non-zeros; OVR: doubled mid-rank of the zero block
+    const unsigned long long g_tie = gt.tie[j];              // OVO: control tie term; OVR: f64 bits of the gene's tie sum
+    const double g_sum = gt.sum[j];                          // OVO: control sum; OVR: whole-gene sum
+    const long long n_ref = OVO ? (long long)pl.group_size[ref] : 0;
+    for (int g = ga; g < gb; ++g) {
+        const long long n_t = pl.group_size[g];
+        const long long n_r = OVO ? n_ref : n - n_t;         // the sample U is reported for
+        const double mu = (double)(n_r * n_t) / 2.0;
         double* o = results + (long long)g * gstride + (long long)j * 3;
         const long long di = (long long)g * b + j;
         if (OVO && g == ref) {
             // control row: (1, -1, fold change of the control against itself), as ovo_kernel writes it
-            const double rsum = fl.group_sums ? fl.group_sums[(long long)ref * b + j] : gt.sum[j];
+            const double rsum = fl.group_sums ? fl.group_sums[(long long)ref * b + j] : g_sum;
             const double mean_r = rsum / (double)n_r;
             o[0] = 1.0; o[1] = -1.0; o[2] = (mean_r == 0.0) ? INFINITY : mean_r / mean_r;
             if (dbg_u2) dbg_u2[di] = -2;
@@ -472,17 +490,18 @@ __global__ void __launch_bounds__(256) fused_epilogue_kernel(int b, const illico
         }
         const unsigned long long* r = reinterpret_cast<const unsigned long long*>(o);
         const unsigned long long wds[3] = {r[0], r[1], r[2]};
-        unsigned long long acc = 0, tie_nz = 0, m = 0;       // acc: OVO 2U without the zero block, OVR 2R without it
+        unsigned long long acc = 0, tie_nz = 0;              // acc: OVO 2U without the zero block, OVR 2R without it
+        uint32_t m = 0;
         double sum = 0.0;
 #pragma unroll
         for (int q = 0; q < DCAP; ++q) {
-            const unsigned long long bq = (wds[q >> 2] >> (16 * (q & 3))) & 0xffffull;
+            const uint32_t bq = (uint32_t)(wds[q >> 2] >> (16 * (q & 3))) & 0xffffu;
             if (bq) {
-                acc += bq * gt.wgt[(long long)q * bs + j];
-                sum += (double)bq * gt.fval[(long long)q * bs + j];
+                acc += (unsigned long long)bq * wgt[q];
+                sum += (double)bq * fval[q];
                 m += bq;
                 if (OVO) {
-                    const unsigned long long a = gt.mult[(long long)q * bs + j];
+                    const unsigned long long a = mult[OVO ? q : 0];
                     tie_nz += bq * (3ull * a * a - 1ull + bq * (3ull * a + bq));   // (a+b)^3 - (a+b) - (a^3 - a)
                 }
             }
@@ -490,13 +509,13 @@ __global__ void __launch_bounds__(256) fused_epilogue_kernel(int b, const illico
         const long long z_t = n_t - (long long)m;
         double p, U, fc;
         if (OVO) {
-            const long long nnz_r = gt.nnz[j], zeros_r = n_r - nnz_r;            // every control value is positive
+            const long long zeros_r = n_r - g_nnz;           // every control value is positive
             if (fl.group_sums) sum = fl.group_sums[(long long)g * b + j];
-            const double rsum = fl.group_sums ? fl.group_sums[(long long)ref * b + j] : gt.sum[j];
+            const double rsum = fl.group_sums ? fl.group_sums[(long long)ref * b + j] : g_sum;
             const long long Z = zeros_r + z_t;
-            const unsigned long long u2 = acc + (unsigned long long)(z_t * (2ll * nnz_r + zeros_r));
-            const unsigned long long tie_exact = gt.tie[j] + tie_nz + (unsigned long long)cube_minus(Z);
-            const double tie = (double)tie_exact;                                // < 2^53: pairs of at most 208 063 cells
+            const unsigned long long u2 = acc + (unsigned long long)(z_t * (2ll * g_nnz + zeros_r));
+            const unsigned long long tie_exact = g_tie + tie_nz + (unsigned long long)cube_minus(Z);
+            const double tie = (double)tie_exact;            // < 2^53: pairs of at most 208 063 cells
             U = (double)u2 / 2.0;
             p = compute_pval(n_r, n_t, n_r + n_t, fl.tie_correct ? tie : 0.0, U, mu, cc, fl.alternative);
             const double mean_t = sum / (double)n_t, mean_r = rsum / (double)n_r;
@@ -505,19 +524,18 @@ __global__ void __launch_bounds__(256) fused_epilogue_kernel(int b, const illico
             if (dbg_tie) dbg_tie[di] = tie;
             if (dbg_tie_exact) dbg_tie_exact[di] = (long long)tie_exact;
         } else {
-            const unsigned long long R2 = acc + (unsigned long long)z_t * gt.nnz[j];
+            const unsigned long long R2 = acc + (unsigned long long)z_t * (unsigned long long)g_nnz;
             const long long u2 = 2 * n_r * n_t + n_t * (n_t + 1) - (long long)R2;
-            const double tie = __longlong_as_double((long long)gt.tie[j]);
+            const double tie = __longlong_as_double((long long)g_tie);
             U = (double)u2 / 2.0;
             p = compute_pval(n_r, n_t, n, fl.tie_correct ? tie : 0.0, U, mu, cc, fl.alternative);
-            const double mu_t = sum / (double)n_t, mu_r = (gt.sum[j] - sum) / (double)(n - n_t);
+            const double mu_t = sum / (double)n_t, mu_r = (g_sum - sum) / (double)(n - n_t);
             fc = (mu_r == 0.0) ? INFINITY : mu_t / mu_r;
             if (dbg_u2) dbg_u2[di] = u2;
         }
         o[0] = p; o[1] = U; o[2] = fc;
     }
 }
-
 
 // ===================== CSR input: the same histograms, built in shared memory ==========================================
 // Replaces, for count-like data, stage_csr_kernel + rank kernel (illico/ovr/sparse_ovr.py:23-208,
@@ -829,9 +847,7 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
     count_launch();
     ILLICO_CUDA_OK(cudaGetLastError());
     {
-        int gx = (b + 255) / 256;
-        if (gx > 64) gx = 64;
-        fused_epilogue_kernel<OVO><<<dim3((unsigned)gx, (unsigned)plan->n_groups), 256, 0, stream>>>(
+        fused_epilogue_kernel<OVO><<<dim3((unsigned)((b + 255) / 256), (unsigned)((plan->n_groups + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
             b, *plan, *flags, gt, bs, results, gstride, dbg ? (long long*)dbg->u2 : nullptr,
             (dbg && OVO) ? dbg->tie_sum : nullptr, (dbg && OVO) ? (long long*)dbg->tie_exact : nullptr);
         count_launch();
@@ -909,6 +925,9 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
         ILLICO_CUDA_OK(cudaEventRecord(e0, stream));
     }
     {
+        // raw counts (identity tables): row-at-a-time kernel without atomics; log1p data: tables claimed on the fly
+        // (An atomics-free variant -- the whole CTA applies one row at a time, plain LDS/STS -- measured 1.5-2.7 x
+        // slower: 150 CTA-wide barriers per segment cost more than the shared atomics they avoid.)
         auto kern = fused_csr_pass_kernel<OVO>;
         const int tile = b < CSRF_TILE ? b : CSRF_TILE;
         const size_t smem = (size_t)tile * 24;
@@ -939,9 +958,7 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
                                                                 (dbg && !OVO) ? (long long*)dbg->tie_exact : nullptr);
     count_launch();
     {
-        int gx = (b + 255) / 256;
-        if (gx > 64) gx = 64;
-        fused_epilogue_kernel<OVO><<<dim3((unsigned)gx, (unsigned)G), 256, 0, stream>>>(
+        fused_epilogue_kernel<OVO><<<dim3((unsigned)((b + 255) / 256), (unsigned)((G + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
             b, *plan, *flags, gt, bs, results, gstride, dbg ? (long long*)dbg->u2 : nullptr,
             (dbg && OVO) ? dbg->tie_sum : nullptr, (dbg && OVO) ? (long long*)dbg->tie_exact : nullptr);
         count_launch();
