@@ -138,49 +138,130 @@ def asymptotic_wilcoxon(
     )
 
 
+class _PinnedSlot:
+    """One slot of the host-side ring: pinned staging arrays (grown on demand) + the event that says the device has
+    finished copying out of them."""
+
+    def __init__(self):
+        self.bufs: dict = {}
+        self.copied = None  # torch.cuda.Event recorded on the copy stream after the slot's H2D copies
+
+    def stage(self, name: str, arr: np.ndarray) -> torch.Tensor:
+        """Copies ``arr`` into the slot's pinned buffer ``name`` (reader thread) and returns the pinned view."""
+        arr = np.ascontiguousarray(arr)
+        buf = self.bufs.get(name)
+        if buf is None or buf.numel() < arr.size or buf.dtype != torch.from_numpy(arr[:0]).dtype:
+            buf = torch.empty(max(arr.size, 1), dtype=torch.from_numpy(arr[:0]).dtype, pin_memory=True)
+            self.bufs[name] = buf
+        view = buf[: arr.size]
+        np.copyto(view.numpy(), arr.reshape(-1), casting="no")
+        return view
+
+
 def _run_backed(data_handler: DataHandler, iterator, engine: Engine, flags, results, n_readers: int) -> None:
-    """Out-of-core input: reader threads slice the next batches from disk while the GPU ranks the current one."""
-    q: Queue = Queue(maxsize=max(2, n_readers))
-    it = iter(iterator)
+    """Out-of-core input (BASELINE config 4): gene batches stream disk -> pinned ring -> HBM -> kernels.
+
+    Reader threads slice the next batches from the backed container straight into pinned staging buffers (a ring of
+    ``n_readers + 2`` slots); the main thread enqueues each batch's ``cudaMemcpyAsync`` on a copy stream and the
+    kernels on the compute stream, ordered by events, so the disk read and H2D copy of batch ``i + 1`` overlap the
+    ranking of batch ``i`` (the reference's joblib threads overlap I/O and numba kernels the same way,
+    ``asymptotic_wilcoxon.py:212-249``)."""
+    from .engine import CSC, DENSE, DeviceMatrix, _to_f32_or_wide
+
+    dev = engine.device
+    order = list(iterator)
+    n_slots = n_readers + 2
+    free_slots: Queue = Queue()
+    for _ in range(n_slots):
+        free_slots.put(_PinnedSlot())
+    ready: Queue = Queue(maxsize=n_slots)
+    it = iter(enumerate(order))
     lock = threading.Lock()
-    errors: list = []
+    fmt = data_handler.kernel_data_format().value
 
     def reader():
         while True:
             with lock:
                 nxt = next(it, None)
             if nxt is None:
-                q.put(None)
+                ready.put(None)
                 return
+            i, (lb, ub) = nxt
             try:
-                q.put((nxt, data_handler.fetch(*nxt)))
+                slot = free_slots.get()
+                if slot.copied is not None:
+                    slot.copied.synchronize()   # the device is done reading this slot's previous batch
+                data, bounds = data_handler.fetch(lb, ub)
+                if fmt == DENSE:
+                    staged = {"shape": data.shape, "x": slot.stage("x", data)}
+                else:
+                    staged = {"shape": data.shape, "data": slot.stage("data", data.data),
+                              "indices": slot.stage("indices", np.asarray(data.indices, dtype=np.int32)),
+                              "indptr": slot.stage("indptr", np.asarray(data.indptr, dtype=np.int64))}
+                ready.put((i, lb, ub, bounds, slot, staged))
             except BaseException as e:  # surfaced on the main thread
-                errors.append(e)
-                q.put(None)
+                ready.put(e)
                 return
 
     threads = [threading.Thread(target=reader, daemon=True) for _ in range(n_readers)]
     for t in threads:
         t.start()
-    done = 0
-    pending: dict = {}
-    order = list(iterator)
-    nxt_i = 0
-    while done < n_readers:
-        item = q.get()
+    compute = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(device=dev)
+    done, nxt_i, pending, error = 0, 0, {}, None
+    queued = None   # (M, bounds, lb) of the batch whose copies are enqueued but whose kernels are not
+
+    def enqueue_copies(lb, bounds, slot, staged):
+        with torch.cuda.stream(copy_stream):
+            # device buffers are allocated on the copy stream; the copies run while the previous batch ranks
+            dv = {k: v.to(dev, non_blocking=True) for k, v in staged.items() if k != "shape"}
+            slot.copied = torch.cuda.Event()
+            slot.copied.record(copy_stream)
+        free_slots.put(slot)
+        return (dv, staged["shape"], bounds, lb, slot.copied)
+
+    def rank(q):
+        dv, shape, bounds, lb, copied = q
+        compute.wait_event(copied)
+        for t_ in dv.values():
+            t_.record_stream(compute)   # allocated on the copy stream, consumed on the compute stream
+        if fmt == DENSE:
+            n, bsz = shape
+            x, raw = dv["x"].view(n, bsz), None
+            if x.dtype != torch.float32:
+                x, raw = _to_f32_or_wide(x)
+            M = DeviceMatrix(DENSE, (n, bsz), x, raw=raw)
+        else:
+            data, raw = dv["data"], None
+            if data.dtype != torch.float32:
+                data, raw = _to_f32_or_wide(data)
+            M = DeviceMatrix(fmt, tuple(shape), data, dv["indices"], dv["indptr"], raw=raw)
+        engine.run_batch(M, bounds[0], bounds[1], flags, results, lb)
+
+    while done < n_readers and error is None:
+        item = ready.get()
         if item is None:
             done += 1
-        else:
-            pending[item[0]] = item[1]
-        while nxt_i < len(order) and order[nxt_i] in pending:  # keep the gene order deterministic
-            lb, ub = order[nxt_i]
-            operator(data_handler, lb, ub, engine, flags, results, fetched=pending.pop(order[nxt_i]))
+            continue
+        if isinstance(item, BaseException):
+            error = item
+            break
+        pending[item[0]] = item
+        while nxt_i in pending:  # keep the gene order deterministic
+            _i, lb, ub, bounds, slot, staged = pending.pop(nxt_i)
+            nxt = enqueue_copies(lb, bounds, slot, staged)   # batch i + 1 starts copying ...
+            if queued is not None:
+                rank(queued)                                  # ... while batch i ranks (the dispatcher may block the host)
+            queued = nxt
             nxt_i += 1
+    if queued is not None and error is None:
+        rank(queued)
     for t in threads:
-        t.join()
-    if errors:
-        raise errors[0]
+        t.join(timeout=0.1 if error is not None else None)
+    if error is not None:
+        raise error
     assert nxt_i == len(order)
+    del CSC
 
 
 _ = (math, GroupContainer, Test, dispatcher_registry)
