@@ -6,7 +6,7 @@ batch dispatchers under it, computed by hand-written sm_100a CUDA kernels behind
 """
 __version__ = "0.1.0"
 
-__all__ = ["asymptotic_wilcoxon", "__version__"]
+__all__ = ["asymptotic_wilcoxon", "register_into_reference", "__version__"]
 
 
 def __getattr__(name):
@@ -15,5 +15,9 @@ def __getattr__(name):
         from .asymptotic_wilcoxon import asymptotic_wilcoxon as fn
 
         globals()["asymptotic_wilcoxon"] = fn  # rebind: the submodule import bound the module to this name
+        return fn
+    if name == "register_into_reference":
+        from .registry import register_into_reference as fn
+
         return fn
     raise AttributeError(name)

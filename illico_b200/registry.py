@@ -180,6 +180,47 @@ class BackedCSCDataHandler(DataHandler):
         return 0
 
 
+class TorchDenseDataHandler(InRAMDataHandler):
+    """A 2-D ``torch.Tensor``: CUDA tensors are used where they are (no host round trip -- SURVEY section 8f.3), CPU
+    tensors go through the ndarray path."""
+
+    def _upload(self, X, device):
+        import torch
+
+        if X.ndim != 2:
+            raise ValueError("expression matrix must be two-dimensional")
+        if X.is_cuda:
+            from .engine import _to_f32_or_wide
+
+            d, raw = (X, None) if X.dtype == torch.float32 else _to_f32_or_wide(X)
+            if d is not None and d.stride(1) != 1:
+                d = d.contiguous()
+            return DeviceMatrix(DENSE, tuple(X.shape), d, raw=raw)
+        return upload_dense(X.numpy(), device)
+
+    def kernel_data_format(self):
+        return KernelDataFormat.DENSE
+
+    def footprint(self):
+        return self.data.numel() * self.data.element_size()
+
+
+def register_into_reference() -> bool:
+    """Puts the six GPU dispatchers into the reference's own ``dispatcher_registry`` (``illico/utils/registry.py:61-64,
+    193-202``) so that ``illico.asymptotic_wilcoxon(..., precompile=False)`` runs its batches on the B200 (INTEGRATION.md,
+    section 2).  Returns False when ``illico`` is not importable."""
+    try:
+        from illico.utils import registry as ref
+    except Exception:
+        return False
+    from . import dispatch as gpu
+
+    for fmt in ref.KernelDataFormat:
+        for test in ref.Test:
+            ref.dispatcher_registry[(test, fmt)] = getattr(gpu, f"{fmt.value}_{test.value}_mwu_kernel_over_contiguous_col_chunk")
+    return True
+
+
 def _register_optional_backends() -> None:
     """h5py / anndata are optional: register their backed containers when importable."""
     try:
@@ -196,6 +237,13 @@ def _register_optional_backends() -> None:
         pass
 
 
+def _register_torch() -> None:
+    import torch
+
+    data_handler_registry.register(torch.Tensor)(TorchDenseDataHandler)
+
+
 _register_optional_backends()
+_register_torch()
 
 from . import dispatch  # noqa: E402,F401  (registers the six GPU dispatchers)

@@ -534,3 +534,19 @@ def test_fused_gate_falls_back_when_many_genes_are_handed_back(monkeypatch, fmt)
     assert _lib.launch_count() > before
     g, p, U, fc = oracle.run(Xf, labels, ref, is_log1p=False)
     assert_parity(got, (p, U, fc), ref_row=int(np.searchsorted(groups, ref)), what=f"gate {fmt}")
+
+
+def test_device_resident_torch_input():
+    """a CUDA tensor is used where it is (no host round trip); same answer as the ndarray path."""
+    import torch
+
+    from illico_b200 import synth
+
+    X, labels = synth.k562_like(seed=51, n_cells=3000, n_genes=40, n_perts=8)
+    _, want = _run(X, labels, synth.CONTROL, is_log1p=False)
+    _, got = _run(torch.from_numpy(X).cuda(), labels, synth.CONTROL, is_log1p=False)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+    _, got64 = _run(torch.from_numpy(X.astype(np.float64)).cuda(), labels, None, is_log1p=False)
+    _, want64 = _run(X, labels, None, is_log1p=False)
+    np.testing.assert_array_equal(got64[1], want64[1])

@@ -225,3 +225,49 @@ def test_categorical_labels_encode_like_strings():
 
     with pytest.raises(ValueError, match="not present"):
         encode_and_count_groups(ser, "unused")
+
+
+def test_register_into_reference_registry():
+    """the six GPU dispatchers replace the numba ones in the reference's own registry
+    (only where the reference is importable: the build container)."""
+    import os
+    import sys
+
+    import pytest
+
+    if not os.path.isdir("/root/reference/illico"):
+        pytest.skip("reference not present")
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    try:
+        import _ref_harness  # stubs anndata / h5py and puts the reference on sys.path
+
+        _ref_harness.import_reference()
+    except Exception as e:  # pragma: no cover
+        pytest.skip(f"reference not importable: {e}")
+    try:
+        from illico.utils import registry as ref
+    except Exception as e:  # pragma: no cover
+        pytest.skip(f"reference not importable: {e}")
+    import illico_b200
+    from illico_b200 import dispatch as gpu
+
+    saved = dict(ref.dispatcher_registry)
+    try:
+        assert illico_b200.register_into_reference() is True
+        for fmt in ref.KernelDataFormat:
+            for test in ref.Test:
+                fn = ref.dispatcher_registry.get(test, fmt) if hasattr(ref.dispatcher_registry, "get") else None
+                fn = ref.dispatcher_registry[(test, fmt)]
+                assert fn is getattr(gpu, f"{fmt.value}_{test.value}_mwu_kernel_over_contiguous_col_chunk")
+    finally:
+        ref.dispatcher_registry.clear()
+        ref.dispatcher_registry.update(saved)
+
+
+def test_torch_tensor_handler_registered():
+    import torch
+
+    from illico_b200.registry import TorchDenseDataHandler, data_handler_registry
+
+    h = data_handler_registry.get(torch.zeros((4, 3)))
+    assert isinstance(h, TorchDenseDataHandler) and h.kernel_data_format().value == "dense"
