@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--sorted-cells", action="store_true", help="experiment: cells already in group order")
+    ap.add_argument("--continuous", action="store_true",
+                    help="stress variant (SURVEY 8d): log1p of library-size-normalised counts, almost no ties among the "
+                         "non-zeros; takes the general stage + rank path")
     return ap.parse_args()
 
 
@@ -179,6 +182,11 @@ def main():
     if a.sorted_cells:
         labels = sorted(labels)
     Xdev = synth.k562_like_torch(a.seed + 1000 * rank, a.cells, a.genes, device=dev)
+    if a.continuous:
+        for r0 in range(0, a.cells, 16384):   # in place, chunked: log1p(x / library size * 1e4)
+            blk = Xdev[r0:r0 + 16384]
+            lib = blk.sum(dim=1, keepdim=True) + 1.0
+            blk.copy_(torch.log1p(blk / lib * 1.0e4))
     uniq, grpc = encode_and_count_groups(labels, reference)
     G = grpc.counts.size
     n_tests_rank = G * a.genes
@@ -406,7 +414,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 keys / int64 ranks / f64 epilogue",
             "data": "synthetic", "impl": "b200",
             "config": {"workload": f"K562-shape {fmt} {test.upper()}: {a.cells} cells x {a.genes} genes x {G} groups per GPU"
-                                   + (", reference=non-targeting" if test == "ovo" else ""),
+                                   + (", reference=non-targeting" if test == "ovo" else "")
+                                   + (", continuous values (log1p of normalised counts)" if a.continuous else ""),
                        "format": fmt, "test": test, "cells": a.cells, "genes_per_gpu": a.genes, "groups": G,
                        "nnz_fraction": round(nnz / (a.cells * a.genes), 4), "gene_batches": len(batches),
                        "l2": "inputs larger than L2 (9.6 GB streamed per step), no explicit flush",

@@ -610,6 +610,9 @@ __global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const f
         }
     }
     for (int p = p0 + w, k = 0; p < p1; p += NW, ++k) {
+        // continuous data: every gene overflows its 12 slots within a few rows -- stop before the (slow) miss path
+        // has been walked for a whole segment; the host then runs the general path
+        if (8 * *reinterpret_cast<volatile int*>(gt.n_bad) > b) break;
         if (k == 32) {                                            // (segments are at most 512 cells: one round; kept general)
             const int pp = p + lane * NW;
             my_e0 = my_e1 = 0;
@@ -645,7 +648,7 @@ __global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const f
                 if (v[u] != 0.0f) {                               // explicitly stored zeros are zeros
                     const int jj = c[u] - c_lo;
                     int q = min(max((int)v[u] - 1, 0), DCAP - 1);
-                    if (kq[u] != v[u]) q = gtab_slot(gt.key + j_lo + jj, bs, v[u]);
+                    if (kq[u] != v[u]) q = gt.bad[j_lo + jj] ? -1 : gtab_slot(gt.key + j_lo + jj, bs, v[u]);
                     if (q >= 0) {
                         atomicAdd(&hist[jj * 6 + (q >> 1)], 1u << (16 * (q & 1)));
                     } else {                                      // hand the gene back, counted once
