@@ -80,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -221,12 +221,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(a.warmup, 3)):
-        step()
-    barrier()
+    # A step takes 2-4 ms, far below nvidia-smi's sampling period, and the SM clock needs tens of milliseconds of load
+    # to reach its boost state.  So the sampler starts first, the warm-up runs the requested steps and then keeps the
+    # same load up for at least 0.6 s (untimed), the K timed steps follow at once, and the load continues for 0.3 s
+    # after them: every clock sample is taken under the step's load, with the timed region in the middle.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_load = time.perf_counter()
+    n_warm = 0
+    while n_warm < max(a.warmup, 3) or time.perf_counter() - t_load < 0.6:
+        step()
+        n_warm += 1
+        if n_warm % 8 == 0:
+            torch.cuda.synchronize(dev)
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -234,14 +242,20 @@ def main():
     for _ in range(a.steps):
         step()
     e1.record()
+    launches_mark = _lib.launch_count()
+    t_post = time.perf_counter()
+    while time.perf_counter() - t_post < 0.3:
+        step()
     barrier()
-    launches = _lib.launch_count() - l0
+    launches = launches_mark - l0
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / a.steps
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = f"{n_warm} warm-up steps (>= 0.6 s of the same load) + the {a.steps} timed steps + 0.3 s of the same load"
 
     # ---- per-kernel timing of one step (stage vs rank), for the roofline of the dominant kernel
     lib = eng.lib
@@ -409,7 +423,7 @@ def main():
         total_tests = n_tests_rank * world
         line = {
             "metric": "gene_x_group_tests_per_s", "value": round(total_tests / (ms_step * 1e-3), 1), "unit": "tests/s",
-            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(ms_step, 4),
+            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "warmup_steps_run": n_warm, "ms_per_step": round(ms_step, 4),
             "wall_s_per_step": round(ms_step * 1e-3, 6),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 keys / int64 ranks / f64 epilogue",
             "data": "synthetic", "impl": "b200",

@@ -8,6 +8,9 @@ for wl in dense_ovo dense_ovr csr_ovo csr_ovr; do
   timeout 900 python bench.py --workload $wl > $o/bench_$wl.json 2> $o/bench_$wl.err
   ILLICO_OVO_FUSED=0 ILLICO_OVR_FUSED=0 timeout 900 python bench.py --workload $wl --no-e2e --no-cpu-baseline > $o/bench_general_$wl.json 2> $o/bench_general_$wl.err
 done
+for wl in dense_ovo dense_ovr csr_ovo csr_ovr; do
+  timeout 900 python bench.py --workload $wl --continuous --no-e2e --no-cpu-baseline --steps 3 > $o/bench_continuous_$wl.json 2> $o/bench_continuous_$wl.err
+done
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $o/bench_reference.json 2> $o/bench_reference.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/launches_dense_ovo.csv \
   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $o/launches.log 2>&1
