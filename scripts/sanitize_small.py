@@ -21,4 +21,18 @@ for name in ("edge", "negatives", "k562_mini_cont"):
             out = asymptotic_wilcoxon(FakeAnnData(C.to_format(X, fmt), labels), is_log1p=False, group_keys="pert",
                                       reference=ref, return_array=True)
             assert np.isfinite(out[2][:, :, 1]).all()
+# count data: the fused single-pass kernels (TMA ring + mbarriers, shared-memory histograms), with genes handed back
+from illico_b200 import synth  # noqa: E402
+
+os.environ["ILLICO_FUSED_MAX_HANDBACK"] = "1.0"
+os.environ["ILLICO_FUSED_GAP"] = "2"
+X, labels = synth.k562_like(seed=3, n_cells=3000, n_genes=24, n_perts=9)
+X[:, 5] = np.random.RandomState(0).poisson(30.0, X.shape[0])   # more than 12 distinct values: handed back
+for fmt in ("dense", "csr"):
+    for ref in (None, synth.CONTROL):
+        for log1p in (False, True):
+            Xi = np.log1p(X).astype(np.float32) if log1p else X
+            out = asymptotic_wilcoxon(FakeAnnData(C.to_format(Xi, fmt), labels), is_log1p=log1p, group_keys="pert",
+                                      reference=ref, return_array=True)
+            assert np.isfinite(out[2][:, :, 1]).all()
 print("sanitize run ok")
