@@ -43,6 +43,14 @@
  *   ir_cnt    : uint32 [n_genes_batch, n_segments] how many values each (gene, segment) slot holds
  *   results   : double [n_groups, result_gene_stride/3 .., 3] = (p_value, statistic, fold_change),
  *               the layout of the reference's `results[G, N, 3]` (asymptotic_wilcoxon.py:210, 241-244).
+ *
+ * The dense and CSR dispatchers (illico_{ovr,ovo}_{dense,csr}_f32) take a shorter road when the batch is count-like
+ * (at most 12 distinct non-zero values per gene): ONE pass over the input writes each group's histogram over the
+ * gene's value table into the 24 bytes its result will occupy, and an epilogue turns it into (p, U, fold change) in
+ * place -- no staged lists, no rank kernel (illico_b200/csrc/fused.cu; same statistics bit for bit).  Genes that
+ * do not qualify are finished by the stage + rank kernels above, through the same buffers; the caller sees no
+ * difference except that `workspace` must be illico_rank_workspace_bytes() large (it also holds the per-gene
+ * tables) and that the call may synchronise `stream` to read back which genes were handed over.
  */
 #ifndef ILLICO_B200_H
 #define ILLICO_B200_H
