@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 import warnings
 from dataclasses import dataclass
 
@@ -70,6 +71,9 @@ class Engine:
         self._buf_genes = 0
         self._ir_vals = self._ir_cnt = self._ws = None
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # The reference calls its dispatchers from joblib threads (ctypes drops the GIL): one batch at a time per engine,
+        # since the batch buffers, the per-gene tables and the dispatcher's host read-backs belong to one call.
+        self._lock = threading.RLock()
 
     # ---- sizes ---------------------------------------------------------------------------------------
     @property
@@ -125,6 +129,10 @@ class Engine:
 
         ``results`` is a device tensor ``[G, N_total, 3]`` float64 (contiguous).
         """
+        with self._lock:
+            return self._run_batch_locked(M, lb, ub, flags, results, result_gene0, debug)
+
+    def _run_batch_locked(self, M, lb, ub, flags, results, result_gene0, debug=None) -> None:
         b = ub - lb
         if b <= 0:
             return

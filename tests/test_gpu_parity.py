@@ -550,3 +550,30 @@ def test_device_resident_torch_input():
     _, got64 = _run(torch.from_numpy(X.astype(np.float64)).cuda(), labels, None, is_log1p=False)
     _, want64 = _run(X, labels, None, is_log1p=False)
     np.testing.assert_array_equal(got64[1], want64[1])
+
+
+@pytest.mark.parametrize("fmt", ["dense", "csr"])
+def test_dispatchers_called_from_concurrent_threads(fmt):
+    """The reference drives its dispatchers from joblib threads (ctypes releases the GIL): concurrent calls on one
+    engine must give the same chunks as sequential ones (illico/asymptotic_wilcoxon.py:212-249)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from illico_b200 import dispatch, synth
+    from illico_b200.groups import encode_and_count_groups
+
+    X, labels = synth.k562_like(seed=61, n_cells=4000, n_genes=96, n_perts=15)
+    X[:, 7] = np.random.RandomState(1).poisson(25.0, X.shape[0])      # a gene the fused path hands back
+    Xf = C.to_format(X, fmt)
+    if fmt != "dense":
+        Xf = dispatch.CSRMatrix(Xf.data, Xf.indices, Xf.indptr, Xf.shape)
+    uniq, grpc = encode_and_count_groups(labels, synth.CONTROL)
+    fn = getattr(dispatch, f"{fmt}_ovo_mwu_kernel_over_contiguous_col_chunk")
+    chunks = [(lb, min(96, lb + 16)) for lb in range(0, 96, 16)]
+    seq = [fn(Xf, lb, ub, grpc, False, True, True, "two-sided") for lb, ub in chunks]
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        par = list(ex.map(lambda c: fn(Xf, c[0], c[1], grpc, False, True, True, "two-sided"), chunks * 3))
+    for k, got in enumerate(par):
+        want = seq[k % len(chunks)]
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+    dispatch.clear_caches()
