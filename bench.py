@@ -397,11 +397,10 @@ def main():
         if rank == 0:
             import pandas as pd
 
+            from illico_b200.asymptotic_wilcoxon import _result_frame
+
             t0 = time.perf_counter()
-            rows = pd.Series(out[0], name="pert", dtype=str)
-            cols = pd.Series(out[1], name="feature", dtype=str)
-            pd.DataFrame(out[2].reshape(-1, 3), index=pd.MultiIndex.from_product([rows, cols]),
-                         columns=["p_value", "statistic", "fold_change"])
+            _result_frame(out[0], out[1], out[2])   # what the default (DataFrame) return adds to the call
             extra["dataframe_s"] = round(time.perf_counter() - t0, 4)
         del out
 

@@ -129,13 +129,25 @@ def asymptotic_wilcoxon(
     out = host.numpy()
     if return_array:
         return unique_raw_groups, np.asarray(adata.var_names), out
-    cols = pd.Series(adata.var_names, name="feature", dtype=str)
-    rows = pd.Series(unique_raw_groups, name="pert", dtype=str)
-    return pd.DataFrame(
-        data=out.reshape(-1, 3),
-        index=pd.MultiIndex.from_product([rows, cols], names=["pert", "feature"]),
-        columns=["p_value", "statistic", "fold_change"],
-    )
+    return _result_frame(unique_raw_groups, adata.var_names, out)
+
+
+def _result_frame(groups, var_names, out: np.ndarray) -> pd.DataFrame:
+    """The reference's result (``asymptotic_wilcoxon.py:252-256``): same index as ``MultiIndex.from_product([groups,
+    var_names], names=["pert", "feature"])`` and the same three float64 columns, but the index is built from its codes
+    and the values are a view of the (pinned) result array: 15 ms instead of 0.2-0.45 s at 16 M rows."""
+    G, N = out.shape[0], out.shape[1]
+    rows = pd.Index(pd.Series(groups, dtype=str), name="pert")
+    cols = pd.Index(pd.Series(var_names, dtype=str), name="feature")
+    if not (rows.is_unique and cols.is_unique):   # from_product factorises duplicated labels: keep its semantics
+        index = pd.MultiIndex.from_product([pd.Series(groups, name="pert", dtype=str), pd.Series(var_names, name="feature", dtype=str)],
+                                           names=["pert", "feature"])
+    else:
+        ct = lambda n: np.int8 if n < 2**7 else np.int16 if n < 2**15 else np.int32 if n < 2**31 else np.int64  # noqa: E731
+        index = pd.MultiIndex(levels=[rows, cols],
+                              codes=[np.repeat(np.arange(G, dtype=ct(G)), N), np.tile(np.arange(N, dtype=ct(N)), G)],
+                              names=["pert", "feature"], verify_integrity=False)
+    return pd.DataFrame(out.reshape(-1, 3), index=index, columns=["p_value", "statistic", "fold_change"], copy=False)
 
 
 class _PinnedSlot:

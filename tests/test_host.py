@@ -271,3 +271,31 @@ def test_torch_tensor_handler_registered():
 
     h = data_handler_registry.get(torch.zeros((4, 3)))
     assert isinstance(h, TorchDenseDataHandler) and h.kernel_data_format().value == "dense"
+
+
+def test_result_frame_matches_from_product():
+    """The fast DataFrame assembly gives exactly what the reference builds (asymptotic_wilcoxon.py:252-256)."""
+    import pandas as pd
+
+    from illico_b200.asymptotic_wilcoxon import _result_frame
+
+    rng = np.random.RandomState(0)
+    groups = np.array(["b", "non-targeting", "a10", "a2"])
+    var_names = pd.Index([f"g{i}" for i in range(7)])
+    out = rng.rand(len(groups), len(var_names), 3)
+    got = _result_frame(groups, var_names, out)
+    want = pd.DataFrame(
+        data=out.reshape(-1, 3),
+        index=pd.MultiIndex.from_product([pd.Series(groups, name="pert", dtype=str), pd.Series(var_names, name="feature", dtype=str)],
+                                         names=["pert", "feature"]),
+        columns=["p_value", "statistic", "fold_change"])
+    pd.testing.assert_frame_equal(got, want)
+    assert got.index.names == ["pert", "feature"]
+    assert got.loc[("a10", "g3"), "statistic"] == out[2, 3, 1]
+    # duplicated gene names: from_product's semantics are kept
+    dup = pd.Index(["g0", "g1", "g0"])
+    got = _result_frame(groups, dup, out[:, :3])
+    want = pd.DataFrame(out[:, :3].reshape(-1, 3), index=pd.MultiIndex.from_product(
+        [pd.Series(groups, name="pert", dtype=str), pd.Series(dup, name="feature", dtype=str)], names=["pert", "feature"]),
+        columns=["p_value", "statistic", "fold_change"])
+    pd.testing.assert_frame_equal(got, want)
