@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--sorted-cells", action="store_true", help="experiment: cells already in group order")
+    ap.add_argument("--high-count-frac", type=float, default=0.0,
+                    help="experiment: this fraction of the genes (scattered) gets Poisson(30) counts, i.e. more distinct "
+                         "values than the fused path's 12-slot table holds (they are handed back to the general path)")
     ap.add_argument("--continuous", action="store_true",
                     help="stress variant (SURVEY 8d): log1p of library-size-normalised counts, almost no ties among the "
                          "non-zeros; takes the general stage + rank path")
@@ -182,6 +185,11 @@ def main():
     if a.sorted_cells:
         labels = sorted(labels)
     Xdev = synth.k562_like_torch(a.seed + 1000 * rank, a.cells, a.genes, device=dev)
+    if a.high_count_frac > 0:
+        gsel = torch.randperm(a.genes, device=dev, generator=torch.Generator(device=dev).manual_seed(7))[: max(1, int(a.genes * a.high_count_frac))]
+        for r0 in range(0, a.cells, 16384):
+            blk = Xdev[r0:r0 + 16384]
+            blk[:, gsel] = torch.poisson(torch.full((blk.shape[0], gsel.numel()), 30.0, device=dev))
     if a.continuous:
         for r0 in range(0, a.cells, 16384):   # in place, chunked: log1p(x / library size * 1e4)
             blk = Xdev[r0:r0 + 16384]

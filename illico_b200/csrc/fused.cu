@@ -585,9 +585,16 @@ template <bool OVO>
 __global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const float* __restrict__ data, const int32_t* __restrict__ indices,
                                                                         const long long* __restrict__ indptr, int gene_lb, int b,
                                                                         const illico_plan_t pl, Gtab gt, int bs,
-                                                                        unsigned long long* __restrict__ rec, long long gstride) {
+                                                                        unsigned long long* __restrict__ rec, long long gstride,
+                                                                        uint32_t* __restrict__ scratch, int scratch_words, int split) {
+    // scratch (optional): one zeroed copy of the tile's histogram per SM in global memory.  Shared-memory atomics run at
+    // about 1.4 cycles per lane-op; the L2 atomic units are separate hardware, so `split` of every 4 chunks of a step
+    // are counted there with fire-and-forget reductions and merged (and re-zeroed) when the CTA writes its records.
     extern __shared__ __align__(16) uint32_t hist[];             // [genes of the tile][6]: 12 u16 counters per gene
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    uint32_t* ghist = scratch ? scratch + (size_t)smid * scratch_words : nullptr;
     const int s = blockIdx.y, g = pl.seg_group[s];
     const int j_lo = blockIdx.x * CSRF_TILE, ng = min(CSRF_TILE, b - j_lo);
     __shared__ int stop;
@@ -650,7 +657,8 @@ __global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const f
                     int q = min(max((int)v[u] - 1, 0), DCAP - 1);
                     if (kq[u] != v[u]) q = gt.bad[j_lo + jj] ? -1 : gtab_slot(gt.key + j_lo + jj, bs, v[u]);
                     if (q >= 0) {
-                        atomicAdd(&hist[jj * 6 + (q >> 1)], 1u << (16 * (q & 1)));
+                        if (ghist && u < split) atomicAdd(&ghist[jj * 6 + (q >> 1)], 1u << (16 * (q & 1)));   // L2 reduction
+                        else atomicAdd(&hist[jj * 6 + (q >> 1)], 1u << (16 * (q & 1)));
                     } else {                                      // hand the gene back, counted once
                         const int j = j_lo + jj;
                         const unsigned bit = 1u << (8 * (j & 3));
@@ -661,6 +669,7 @@ __global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const f
             }
         }
     }
+    if (ghist) __threadfence();                                   // this thread's reductions are performed
     __syncthreads();
     const bool multi = pl.group_seg[g + 1] - pl.group_seg[g] > 1;
     for (int jj = t; jj < ng; jj += CSRF_THREADS) {
@@ -668,6 +677,13 @@ __global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const f
         uint32_t wd[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) wd[k] = hist[jj * 6 + k];
+        if (ghist) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const uint32_t x = __ldcg(ghist + jj * 6 + k);
+                if (x) { wd[k] += x; ghist[jj * 6 + k] = 0u; }    // u16 pairs: no carry; left zeroed for the SM's next CTA
+            }
+        }
         if (OVO && g == pl.ref_group) {
             // the control's histogram is the table's multiplicity column
 #pragma unroll
@@ -705,6 +721,30 @@ __global__ void __launch_bounds__(256) fused_hist_sum_kernel(int b, int G, int g
 #pragma unroll
     for (int q = 0; q < DCAP; ++q)
         if (acc[q]) atomicAdd(gt.mult + (long long)q * bs + j, acc[q]);
+}
+
+// ---- compacted hand-back (dense): the flagged genes' columns are gathered into a small row-major matrix, the general
+// path runs on it, and its results are scattered back -- cost follows the number of flagged genes (a scattered fraction f
+// of the genes costs about 8 f of one pass over the matrix: every 4-byte element drags its 32-byte sector along).
+__global__ void __launch_bounds__(256) gather_genes_kernel(const float* __restrict__ X, long long ld, int gene_lb,
+                                                           const int* __restrict__ list, int nb, int nbp, int n,
+                                                           float* __restrict__ Xc) {
+    const long long total = (long long)n * nbp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / nbp;
+        const int k = (int)(i - r * nbp);
+        Xc[i] = (k < nb) ? __ldg(X + r * ld + gene_lb + list[k]) : 0.0f;
+    }
+}
+__global__ void __launch_bounds__(256) scatter_results_kernel(const double* __restrict__ tmp, int nb, int nbp,
+                                                              const int* __restrict__ list, int G,
+                                                              double* __restrict__ results, long long gstride) {
+    const long long total = (long long)G * nb * 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long g = i / (3ll * nb);
+        const int rem = (int)(i - g * 3ll * nb), k = rem / 3, c = rem - 3 * k;
+        results[g * gstride + 3ll * list[k] + c] = tmp[(g * nbp + k) * 3 + c];
+    }
 }
 
 int env_int(const char* name, int dflt) {
@@ -820,7 +860,12 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
     ILLICO_CUDA_OK(cudaMemcpyAsync(bad.data(), gt.bad, (size_t)b, cudaMemcpyDeviceToHost, stream));
     ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
     // genes the table step already hands back (continuous data, high counts): is the fused pass still worth it?
-    if (hand_back_coverage(bad, b) > max_hand_back()) return -1;
+    {
+        int nb0 = 0;
+        for (int j = 0; j < b; ++j) nb0 += bad[j] ? 1 : 0;
+        const bool compactable = env_int("ILLICO_FUSED_COMPACT", 0) != 0 && !dbg && !flags->group_sums && 8ll * nb0 <= b;
+        if (!compactable && hand_back_coverage(bad, b) > max_hand_back()) return -1;
+    }
 
     // 2. the pass over the matrix
     long long avg_g = plan->n_cells / plan->n_groups;
@@ -864,6 +909,41 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
         ILLICO_CUDA_OK(cudaEventElapsedTime(&g_last_fused_ms, e0, e1));
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
+    }
+    {
+        // few flagged genes, scattered: gather their columns and run the general path on the compact matrix
+        std::vector<int> list;
+        for (int j = 0; j < b; ++j) if (bad[j]) list.push_back(j);
+        const int nb = (int)list.size(), nbp = (nb + 3) & ~3;
+        const bool side_arrays = dbg != nullptr || flags->group_sums != nullptr;
+        const long long n = plan->n_cells;
+        // carve-up of the batch's staged-list buffer (sized for b genes): lists of nbp genes | Xc | tmp results | list
+        const size_t ir_floats = (size_t)b * (size_t)plan->slot_cap;
+        size_t off = ((size_t)nbp * (size_t)plan->slot_cap + 63) & ~(size_t)63;
+        const size_t xc_off = off; off += ((size_t)n * nbp + 63) & ~(size_t)63;
+        const size_t tmp_off = off; off += ((size_t)plan->n_groups * nbp * 6 + 63) & ~(size_t)63;   // doubles = 2 floats
+        const size_t list_off = off; off += (size_t)nbp + 64;
+        if (nb > 0 && !side_arrays && env_int("ILLICO_FUSED_COMPACT", 0) != 0 && 8ll * nb <= b && off <= ir_floats &&
+            hand_back_coverage(bad, b) > 2.0 * (double)nb / (double)b) {
+            float* Xc = buf->ir_vals + xc_off;
+            double* tmp = reinterpret_cast<double*>(buf->ir_vals + tmp_off);
+            int* dlist = reinterpret_cast<int*>(buf->ir_vals + list_off);
+            ILLICO_CUDA_OK(cudaMemcpyAsync(dlist, list.data(), (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, stream));
+            gather_genes_kernel<<<148 * 16, 256, 0, stream>>>(X, ld, gene_lb, dlist, nb, nbp, (int)n, Xc);
+            count_launch();
+            ILLICO_CUDA_OK(cudaGetLastError());
+            if (launch_stage_dense(Xc, nbp, 0, nbp, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
+            const int rr = OVO ? launch_ovo(buf->ir_vals, buf->ir_cnt, nbp, plan, flags, tmp, 3ll * nbp, buf->workspace,
+                                            buf->workspace_bytes, nullptr, stream)
+                               : launch_ovr(buf->ir_vals, buf->ir_cnt, nbp, plan, flags, tmp, 3ll * nbp, buf->workspace,
+                                            buf->workspace_bytes, nullptr, stream);
+            if (rr) return 1;
+            scatter_results_kernel<<<148 * 4, 256, 0, stream>>>(tmp, nb, nbp, dlist, plan->n_groups, results, gstride);
+            count_launch();
+            ILLICO_CUDA_OK(cudaGetLastError());
+            ILLICO_CUDA_OK(cudaStreamSynchronize(stream));   // `list` (pageable) must outlive its copy
+            return 0;
+        }
     }
     return hand_back(bad, b, dbg != nullptr || flags->group_sums != nullptr, [&](int lb, int ub) {
         if (launch_stage_dense(X, ld, gene_lb + lb, ub - lb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
@@ -936,7 +1016,19 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
         const size_t smem = (size_t)tile * 24;
         ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const dim3 grid((unsigned)((b + CSRF_TILE - 1) / CSRF_TILE), (unsigned)plan->n_segments);
-        kern<<<grid, CSRF_THREADS, smem, stream>>>(data, indices, indptr, gene_lb, b, *plan, gt, bs, rec, gstride);
+        // per-SM global histogram copies behind the per-gene tables, if the workspace has room (experiment knob)
+        uint32_t* scratch = nullptr;
+        const int split = env_int("ILLICO_CSR_L2_SPLIT", 0);
+        int dev = 0, sms = 0;
+        ILLICO_CUDA_OK(cudaGetDevice(&dev));
+        ILLICO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const size_t scratch_bytes = (size_t)(sms + 16) * tile * 24;   // SM ids can exceed the SM count by a few
+        const size_t off = (gtab_bytes(b) + 255) & ~(size_t)255;
+        if (split > 0 && grid.x == 1 && buf->workspace_bytes >= off + scratch_bytes) {
+            scratch = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(buf->workspace) + off);
+            ILLICO_CUDA_OK(cudaMemsetAsync(scratch, 0, scratch_bytes, stream));
+        }
+        kern<<<grid, CSRF_THREADS, smem, stream>>>(data, indices, indptr, gene_lb, b, *plan, gt, bs, rec, gstride, scratch, tile * 6, split);
         count_launch();
         ILLICO_CUDA_OK(cudaGetLastError());
     }
