@@ -585,16 +585,9 @@ template <bool OVO>
 __global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const float* __restrict__ data, const int32_t* __restrict__ indices,
                                                                         const long long* __restrict__ indptr, int gene_lb, int b,
                                                                         const illico_plan_t pl, Gtab gt, int bs,
-                                                                        unsigned long long* __restrict__ rec, long long gstride,
-                                                                        uint32_t* __restrict__ scratch, int scratch_words, int split) {
-    // scratch (optional): one zeroed copy of the tile's histogram per SM in global memory.  Shared-memory atomics run at
-    // about 1.4 cycles per lane-op; the L2 atomic units are separate hardware, so `split` of every 4 chunks of a step
-    // are counted there with fire-and-forget reductions and merged (and re-zeroed) when the CTA writes its records.
+                                                                        unsigned long long* __restrict__ rec, long long gstride) {
     extern __shared__ __align__(16) uint32_t hist[];             // [genes of the tile][6]: 12 u16 counters per gene
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    uint32_t* ghist = scratch ? scratch + (size_t)smid * scratch_words : nullptr;
     const int s = blockIdx.y, g = pl.seg_group[s];
     const int j_lo = blockIdx.x * CSRF_TILE, ng = min(CSRF_TILE, b - j_lo);
     __shared__ int stop;
@@ -657,8 +650,7 @@ __global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const f
                     int q = min(max((int)v[u] - 1, 0), DCAP - 1);
                     if (kq[u] != v[u]) q = gt.bad[j_lo + jj] ? -1 : gtab_slot(gt.key + j_lo + jj, bs, v[u]);
                     if (q >= 0) {
-                        if (ghist && u < split) atomicAdd(&ghist[jj * 6 + (q >> 1)], 1u << (16 * (q & 1)));   // L2 reduction
-                        else atomicAdd(&hist[jj * 6 + (q >> 1)], 1u << (16 * (q & 1)));
+                        atomicAdd(&hist[jj * 6 + (q >> 1)], 1u << (16 * (q & 1)));
                     } else {                                      // hand the gene back, counted once
                         const int j = j_lo + jj;
                         const unsigned bit = 1u << (8 * (j & 3));
@@ -669,7 +661,6 @@ __global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const f
             }
         }
     }
-    if (ghist) __threadfence();                                   // this thread's reductions are performed
     __syncthreads();
     const bool multi = pl.group_seg[g + 1] - pl.group_seg[g] > 1;
     for (int jj = t; jj < ng; jj += CSRF_THREADS) {
@@ -677,13 +668,6 @@ __global__ void __launch_bounds__(CSRF_THREADS, 1) fused_csr_pass_kernel(const f
         uint32_t wd[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) wd[k] = hist[jj * 6 + k];
-        if (ghist) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const uint32_t x = __ldcg(ghist + jj * 6 + k);
-                if (x) { wd[k] += x; ghist[jj * 6 + k] = 0u; }    // u16 pairs: no carry; left zeroed for the SM's next CTA
-            }
-        }
         if (OVO && g == pl.ref_group) {
             // the control's histogram is the table's multiplicity column
 #pragma unroll
@@ -863,7 +847,7 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
     {
         int nb0 = 0;
         for (int j = 0; j < b; ++j) nb0 += bad[j] ? 1 : 0;
-        const bool compactable = env_int("ILLICO_FUSED_COMPACT", 0) != 0 && !dbg && !flags->group_sums && 8ll * nb0 <= b;
+        const bool compactable = env_int("ILLICO_FUSED_COMPACT", 1) != 0 && !dbg && !flags->group_sums && 8ll * nb0 <= b;
         if (!compactable && hand_back_coverage(bad, b) > max_hand_back()) return -1;
     }
 
@@ -923,7 +907,7 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
         const size_t xc_off = off; off += ((size_t)n * nbp + 63) & ~(size_t)63;
         const size_t tmp_off = off; off += ((size_t)plan->n_groups * nbp * 6 + 63) & ~(size_t)63;   // doubles = 2 floats
         const size_t list_off = off; off += (size_t)nbp + 64;
-        if (nb > 0 && !side_arrays && env_int("ILLICO_FUSED_COMPACT", 0) != 0 && 8ll * nb <= b && off <= ir_floats &&
+        if (nb > 0 && !side_arrays && env_int("ILLICO_FUSED_COMPACT", 1) != 0 && 8ll * nb <= b && off <= ir_floats &&
             hand_back_coverage(bad, b) > 2.0 * (double)nb / (double)b) {
             float* Xc = buf->ir_vals + xc_off;
             double* tmp = reinterpret_cast<double*>(buf->ir_vals + tmp_off);
@@ -1016,19 +1000,9 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
         const size_t smem = (size_t)tile * 24;
         ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const dim3 grid((unsigned)((b + CSRF_TILE - 1) / CSRF_TILE), (unsigned)plan->n_segments);
-        // per-SM global histogram copies behind the per-gene tables, if the workspace has room (experiment knob)
-        uint32_t* scratch = nullptr;
-        const int split = env_int("ILLICO_CSR_L2_SPLIT", 0);
-        int dev = 0, sms = 0;
-        ILLICO_CUDA_OK(cudaGetDevice(&dev));
-        ILLICO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const size_t scratch_bytes = (size_t)(sms + 16) * tile * 24;   // SM ids can exceed the SM count by a few
-        const size_t off = (gtab_bytes(b) + 255) & ~(size_t)255;
-        if (split > 0 && grid.x == 1 && buf->workspace_bytes >= off + scratch_bytes) {
-            scratch = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(buf->workspace) + off);
-            ILLICO_CUDA_OK(cudaMemsetAsync(scratch, 0, scratch_bytes, stream));
-        }
-        kern<<<grid, CSRF_THREADS, smem, stream>>>(data, indices, indptr, gene_lb, b, *plan, gt, bs, rec, gstride, scratch, tile * 6, split);
+        // (Counting part of the updates in a per-SM global histogram with L2 reductions instead of shared atomics
+        // measured 1.4-1.9 x slower.)
+        kern<<<grid, CSRF_THREADS, smem, stream>>>(data, indices, indptr, gene_lb, b, *plan, gt, bs, rec, gstride);
         count_launch();
         ILLICO_CUDA_OK(cudaGetLastError());
     }
