@@ -28,6 +28,7 @@ constexpr int WARP_CAP = 1024;   // keys per warp buffer in the warp tier
 constexpr int GROUP_CHUNK = 2048;  // groups handled per sweep (bounds the deferred lists)
 constexpr int DT_CAP = 22;         // distinct control values for the table fast path (<= small_cap)
 constexpr int DT_HASH = 64;        // slots of the key -> table-index hash (load factor <= 1/3)
+constexpr int ST_CAP = 1024;      // distinct control values kept in the shared-memory search table
 constexpr int FAST_MAX = 96;       // largest group (non-zeros) a single thread streams through the table path
 
 struct OvoParams {
@@ -43,6 +44,7 @@ struct OvoParams {
     int ref_cap;             // capacity (keys) of each of the two control buffers
     int small_cap;           // thread-tier capacity (keys per thread)
     int scratch_words;       // shared scratch (control ping-pong partner, later the tier buffers)
+    int use_search_table;    // ILLICO_OVO_SEARCH_TABLE
     long long* dbg_u2;
     double* dbg_tie;
     long long* dbg_tie_exact;
@@ -56,14 +58,28 @@ struct RefInfo {
     long long n_ref;
     unsigned long long tie;  // sum over control non-zero runs of a^3 - a
     double sum;              // sum of f(x) over the control
+    // search table (optional, st_n >= 0): the control's distinct keys ascending and the position of each one's first
+    // occurrence in `keys` (st_lo[st_n] = nnz).  A rank then costs a binary search over <= 1024 shared-memory entries
+    // instead of one over the whole sorted control, which lives in the CTA's global slab when it is large: measured
+    // 25 ms per dense high-count gene without it (every probe a dependent L2 load).
+    const uint32_t* st_key;
+    const int* st_lo;
+    int st_n;
 };
 
 // contribution of one distinct perturbation value (key, multiplicity b)
 __device__ __forceinline__ void rank_value(const RefInfo& R, uint32_t key, long long b, unsigned long long& u2,
                                            unsigned long long& tie) {
-    int lo = lower_bound_u32(R.keys, R.nnz, key);
-    int hi = lo;
-    if (lo < R.nnz && R.keys[lo] == key) hi = upper_bound_u32(R.keys, R.nnz, key);
+    int lo, hi;
+    if (R.st_n >= 0) {
+        const int t = lower_bound_u32(R.st_key, R.st_n, key);
+        lo = R.st_lo[t];
+        hi = (t < R.st_n && R.st_key[t] == key) ? R.st_lo[t + 1] : lo;
+    } else {
+        lo = lower_bound_u32(R.keys, R.nnz, key);
+        hi = lo;
+        if (lo < R.nnz && R.keys[lo] == key) hi = upper_bound_u32(R.keys, R.nnz, key);
+    }
     long long a = hi - lo;
     long long gt = (long long)(R.nnz - hi) + ((key < KEY_ZERO) ? R.zeros : 0);
     u2 += (unsigned long long)(b * (2 * gt + a));
@@ -152,6 +168,8 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
     uint2* hkv = (uint2*)(dA3 + DT_CAP);                    // [DT_HASH]  open-addressed {float bits, byte offset of the bin}
     uint32_t* dkey = (uint32_t*)(hkv + DT_HASH);            // [DT_CAP]   distinct control keys, ascending
     int* dlo = (int*)(dkey + DT_CAP);                       // [DT_CAP+1] first position of each in the sorted control
+    uint32_t* st_key = (uint32_t*)(dlo + DT_CAP + 1);       // [ST_CAP]   search table: distinct control keys, ascending
+    int* st_lo = (int*)(st_key + ST_CAP);                   // [ST_CAP+1] first position of each
 
     uint32_t* slab = P.slab + (long long)blockIdx.x * P.slab_words;
     const int maxg = pl.max_group_size;
@@ -231,6 +249,31 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
         __syncthreads();
         const int D = counters[6];
         const bool table = D <= DT_CAP;
+        // ---- search table for controls with more distinct values than the histogram path takes (D counts them all)
+        R.st_key = st_key; R.st_lo = st_lo; R.st_n = -1;
+        if (!table && D <= ST_CAP && P.use_search_table) {
+            // ordered compaction of the run starts of rA: chunks of OVO_THREADS elements, ballot + warp totals
+            int base = 0;
+            for (int i0 = 0; i0 < nref_nz; i0 += OVO_THREADS) {
+                const int i = i0 + tid;
+                const bool head = i < nref_nz && (i == 0 || rA[i - 1] != rA[i]);
+                const unsigned bal = __ballot_sync(FULL, head);
+                if (lane == 0) hist[w] = (uint32_t)__popc(bal);
+                __syncthreads();
+                int before = 0, total = 0;
+                for (int ww = 0; ww < OVO_NW; ++ww) { const int c = (int)hist[ww]; if (ww < w) before += c; total += c; }
+                if (head) {
+                    const int slot = base + before + __popc(bal & ((1u << lane) - 1u));
+                    st_key[slot] = rA[i];
+                    st_lo[slot] = i;
+                }
+                base += total;
+                __syncthreads();
+            }
+            if (tid == 0) st_lo[D] = nref_nz;
+            R.st_n = D;
+            __syncthreads();
+        }
         if (table && tid == 0) {
             for (int a = 1; a < D; ++a) {  // order the <= 22 entries by position (= by key)
                 const uint32_t k = dkey[a];
@@ -499,7 +542,7 @@ static int launch_ovo_t(OvoParams& P, const illico_plan_t* plan, void* workspace
     // shared memory: fixed part + control buffer + scratch.  Genes whose control has more non-zeros than ref_cap
     // keep the control in the CTA's global slab.
     const size_t fixed = (size_t)(NW * 256 + RADIX_AUX_WORDS + GROUP_CHUNK + 8) * 4 + 32 * 8 * 2 + 3 * DT_CAP * 8 +
-                         (2 * DT_CAP + 1) * 4 + DT_HASH * 8 + 64;
+                         (2 * DT_CAP + 1) * 4 + DT_HASH * 8 + 64 + (2 * ST_CAP + 1) * 4;
     const int small_cap = DT_CAP;
     int scratch_words = small_cap * NT;               // thread tier: small_cap keys per thread
     if (scratch_words < 2 * WARP_CAP) scratch_words = 2 * WARP_CAP;  // at least two warp-tier buffers
@@ -513,6 +556,7 @@ static int launch_ovo_t(OvoParams& P, const illico_plan_t* plan, void* workspace
     const size_t need = fixed + (size_t)(ref_cap + scratch_words) * 4;
     if (need > (size_t)max_smem) { set_error("ovo_kernel needs %zu bytes of shared memory", need); return 1; }
     P.ref_cap = ref_cap; P.small_cap = small_cap; P.scratch_words = scratch_words;
+    P.use_search_table = env_int("ILLICO_OVO_SEARCH_TABLE", 1);
     auto kern = ovo_kernel<NT, MIN_CTAS>;
     ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     int occ = 0;
