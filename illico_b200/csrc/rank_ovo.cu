@@ -175,10 +175,11 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
     const int maxg = pl.max_group_size;
     uint32_t* gA = slab;            // block-tier group buffers (global)
     uint32_t* gB = slab + maxg;
-    const int nwb = min(OVO_NW, P.scratch_words / WARP_CAP);  // warps that own a warp-tier buffer
+    __shared__ int mmax3[3];
 
     const int ref_s0 = pl.group_seg[ref], ref_s1 = pl.group_seg[ref + 1];
     if (tid < 8) counters[tid] = 0;
+    if (tid < 3) mmax3[tid] = 0;
     int cc = 0;  // chunk counter: chunk c uses counter set c % 3 and clears set (c + 1) % 3 for the next chunk
     __syncthreads();
 
@@ -305,7 +306,8 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
         for (int g0 = 0; g0 < G; g0 += GROUP_CHUNK) {
             const int g1 = min(G, g0 + GROUP_CHUNK);
             int* cnt_m = counters + 2 * (cc % 3);      // [0] medium list length, [1] big list length
-            if (tid == 0) { const int nx = 2 * ((cc + 1) % 3); counters[nx] = 0; counters[nx + 1] = 0; }
+            int* m_max = mmax3 + (cc % 3);             // largest non-zero count among the chunk's warp-tier groups
+            if (tid == 0) { const int nx = (cc + 1) % 3; counters[2 * nx] = 0; counters[2 * nx + 1] = 0; mmax3[nx] = 0; }
             ++cc;
             // ---- thread tier
             for (int g = g0 + tid; g < g1; g += OVO_THREADS) {
@@ -402,10 +404,12 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                     }
                     // too many values the control does not have: a whole warp ranks this group (general path)
                     mlist[atomicAdd(&cnt_m[0], 1)] = (uint16_t)(g - g0);
+                    atomicMax(m_max, m);
                     continue;
                 }
                 if (m > P.small_cap) {
                     mlist[atomicAdd(&cnt_m[0], 1)] = (uint16_t)(g - g0);
+                    atomicMax(m_max, m);
                     continue;
                 }
                 double sum = 0.0;
@@ -439,6 +443,10 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
             // ---- warp tier (usually empty: then this barrier is the only one of the chunk)
             const int nm = cnt_m[0];
             if (nm == 0) continue;
+            // warp-tier buffers: 512 keys each when every group of the chunk fits (all 8 warps then own one; with 1024-key
+            // buffers only 5 do -- a dense high-count gene has all its 2000 groups here, and its CTA is the kernel's tail)
+            const int wcap = (*m_max <= WARP_CAP / 2) ? WARP_CAP / 2 : WARP_CAP;
+            const int nwb = min(OVO_NW, P.scratch_words / wcap);
             for (int e = w; e < nm && w < nwb; e += nwb) {
                 const int g = g0 + mlist[e];
                 const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
@@ -448,7 +456,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                     if (lane == 0) blist[atomicAdd(&cnt_m[1], 1)] = (uint16_t)(g - g0);
                     continue;
                 }
-                uint32_t* buf = scratch + w * WARP_CAP;
+                uint32_t* buf = scratch + w * wcap;
                 int k = 0;
                 for (int s = s0; s < s1; ++s) {
                     const int c = (int)cnt[s];
