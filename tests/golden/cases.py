@@ -88,6 +88,24 @@ def _batched():
     return X, labels, labels[0]
 
 
+def _highcount():
+    """Dense, highly expressed genes: dozens of distinct values per gene, every group above the thread tier of the
+    general OVO kernel (search table, warp tier), far more than the fused path's 12-slot table (handed back), next to
+    plain count genes that stay on the fused path."""
+    rng = np.random.RandomState(13)
+    n = 6_000
+    X = (rng.poisson(1.0, size=(n, 16)) * (rng.rand(n, 16) >= 0.8)).astype(np.float32)
+    for j, lam in ((1, 30.0), (6, 80.0), (7, 12.0), (12, 300.0)):
+        X[:, j] = rng.poisson(lam, n)
+    X[:, 9] = rng.poisson(25.0, n) * (rng.rand(n) >= 0.5)
+    sizes = np.array([900, 40, 700, 33, 260, 150, 5, 1100])          # the reference group is the largest
+    codes = np.repeat(np.arange(sizes.size), sizes)
+    codes = np.concatenate([codes, rng.randint(0, sizes.size, size=n - codes.size)])
+    rng.shuffle(codes)
+    labels = [f"g{c}" for c in codes]
+    return X, labels, "g7"
+
+
 def _grid(fmts, tests, ccs=(True,), tcs=(True,), alts=("two-sided",), log1p=(False,)):
     return list(itertools.product(fmts, tests, ccs, tcs, alts, log1p))
 
@@ -106,6 +124,7 @@ CASES = {
     "log1p32": (_log1p32, _grid(ALL_FMT, BOTH, log1p=(True,)), 10),
     "log1p64": (_log1p64, _grid(ALL_FMT, BOTH, log1p=(True,)), 10),
     "batched": (_batched, _grid(ALL_FMT, BOTH), 128),
+    "highcount": (_highcount, _grid(ALL_FMT, BOTH, alts=("two-sided", "greater")), 16),
 }
 
 
