@@ -13,9 +13,8 @@ What changed relative to the reference's driver (same contract, different machin
 """
 from __future__ import annotations
 
-import math
 import threading
-from queue import Queue
+from queue import Empty, Queue
 from typing import Literal
 
 import numpy as np
@@ -24,8 +23,8 @@ import torch
 from scipy import sparse
 
 from .engine import CSR, Engine, make_flags, require_cuda
-from .groups import GroupContainer, encode_and_count_groups
-from .registry import DataHandler, Test, data_handler_registry, dispatcher_registry  # noqa: F401
+from .groups import encode_and_count_groups
+from .registry import DataHandler, data_handler_registry
 
 __all__ = ["asymptotic_wilcoxon"]
 
@@ -92,6 +91,8 @@ def asymptotic_wilcoxon(
 
     # In-RAM input: start the host->device copy first; it runs (asynchronously for pinned memory) while the
     # host encodes the groups and builds the plan.
+    if device is None and isinstance(X, torch.Tensor) and X.is_cuda:
+        device = X.device          # a device-resident matrix is ranked where it lives
     dev = require_cuda(device)
     if data_handler.in_ram:
         with torch.cuda.device(dev):
@@ -178,7 +179,7 @@ def _run_backed(data_handler: DataHandler, iterator, engine: Engine, flags, resu
     kernels on the compute stream, ordered by events, so the disk read and H2D copy of batch ``i + 1`` overlap the
     ranking of batch ``i`` (the reference's joblib threads overlap I/O and numba kernels the same way,
     ``asymptotic_wilcoxon.py:212-249``)."""
-    from .engine import CSC, DENSE, DeviceMatrix, _to_f32_or_wide
+    from .engine import DENSE, DeviceMatrix, _to_f32_or_wide
 
     dev = engine.device
     order = list(iterator)
@@ -191,16 +192,24 @@ def _run_backed(data_handler: DataHandler, iterator, engine: Engine, flags, resu
     lock = threading.Lock()
     fmt = data_handler.kernel_data_format().value
 
+    stop = threading.Event()
+
     def reader():
-        while True:
+        while not stop.is_set():
+            # the slot comes FIRST: whoever holds the lowest outstanding batch index then already owns a slot, so the
+            # ring can never fill up with later batches while the batch the main thread waits for starves
+            try:
+                slot = free_slots.get(timeout=0.05)
+            except Empty:
+                continue
             with lock:
                 nxt = next(it, None)
             if nxt is None:
+                free_slots.put(slot)
                 ready.put(None)
                 return
             i, (lb, ub) = nxt
             try:
-                slot = free_slots.get()
                 if slot.copied is not None:
                     slot.copied.synchronize()   # the device is done reading this slot's previous batch
                 data, bounds = data_handler.fetch(lb, ub)
@@ -220,7 +229,7 @@ def _run_backed(data_handler: DataHandler, iterator, engine: Engine, flags, resu
         t.start()
     compute = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(device=dev)
-    done, nxt_i, pending, error = 0, 0, {}, None
+    done, nxt_i, pending = 0, 0, {}
     queued = None   # (M, bounds, lb) of the batch whose copies are enqueued but whose kernels are not
 
     def enqueue_copies(lb, bounds, slot, staged):
@@ -250,30 +259,32 @@ def _run_backed(data_handler: DataHandler, iterator, engine: Engine, flags, resu
             M = DeviceMatrix(fmt, tuple(shape), data, dv["indices"], dv["indptr"], raw=raw)
         engine.run_batch(M, bounds[0], bounds[1], flags, results, lb)
 
-    while done < n_readers and error is None:
-        item = ready.get()
-        if item is None:
-            done += 1
-            continue
-        if isinstance(item, BaseException):
-            error = item
-            break
-        pending[item[0]] = item
-        while nxt_i in pending:  # keep the gene order deterministic
-            _i, lb, ub, bounds, slot, staged = pending.pop(nxt_i)
-            nxt = enqueue_copies(lb, bounds, slot, staged)   # batch i + 1 starts copying ...
-            if queued is not None:
-                rank(queued)                                  # ... while batch i ranks (the dispatcher may block the host)
-            queued = nxt
-            nxt_i += 1
-    if queued is not None and error is None:
-        rank(queued)
-    for t in threads:
-        t.join(timeout=0.1 if error is not None else None)
-    if error is not None:
-        raise error
-    assert nxt_i == len(order)
-    del CSC
-
-
-_ = (math, GroupContainer, Test, dispatcher_registry)
+    try:
+        while done < n_readers:
+            item = ready.get()
+            if item is None:
+                done += 1
+                continue
+            if isinstance(item, BaseException):
+                raise item
+            pending[item[0]] = item
+            while nxt_i in pending:  # keep the gene order deterministic
+                _i, lb, ub, bounds, slot, staged = pending.pop(nxt_i)
+                nxt = enqueue_copies(lb, bounds, slot, staged)   # batch i + 1 starts copying ...
+                if queued is not None:
+                    rank(queued)                                  # ... while batch i ranks
+                queued = nxt
+                nxt_i += 1
+        if queued is not None:
+            rank(queued)
+        assert nxt_i == len(order)
+    finally:
+        # error or not, no reader may stay blocked on a queue (they hold pinned buffers): stop them and drain
+        stop.set()
+        while any(t.is_alive() for t in threads):
+            try:
+                ready.get(timeout=0.02)
+            except Empty:
+                pass
+        for t in threads:
+            t.join()

@@ -529,7 +529,11 @@ __global__ void __launch_bounds__(256, 3) fused_epilogue_kernel(int b, const ill
             const double tie = __longlong_as_double((long long)g_tie);
             U = (double)u2 / 2.0;
             p = compute_pval(n_r, n_t, n, fl.tie_correct ? tie : 0.0, U, mu, cc, fl.alternative);
-            const double mu_t = sum / (double)n_t, mu_r = (g_sum - sum) / (double)(n - n_t);
+            // rest-of-cells mean: exactly zero when this group holds every non-zero of the gene (the reference's total is
+            // the sum of the per-group sums, so its `total - sum` is an exact 0 there; a total accumulated in another
+            // order could leave an ulp and turn the +inf fold change into 1e16)
+            const bool all_here = (long long)m == n - (g_nnz - 1);
+            const double mu_t = sum / (double)n_t, mu_r = all_here ? 0.0 : (g_sum - sum) / (double)(n - n_t);
             fc = (mu_r == 0.0) ? INFINITY : mu_t / mu_r;
             if (dbg_u2) dbg_u2[di] = u2;
         }

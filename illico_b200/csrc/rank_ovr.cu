@@ -571,7 +571,8 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
             const double mu = (double)(n_r * n_t) / 2.0;
             const double p = compute_pval(n_r, n_t, n, P.flags.tie_correct ? tie : 0.0, U, mu, cc, P.flags.alternative);
             const double mu_t = sum / (double)n_t;
-            const double mu_r = (total - sum) / (double)(n - n_t);
+            // exactly zero when the group holds every non-zero of the gene (see fused_epilogue_kernel)
+            const double mu_r = (nnz_g == nnz) ? 0.0 : (total - sum) / (double)(n - n_t);
             double* o = P.results + (long long)g * P.gstride + (long long)j * 3;
             o[0] = p; o[1] = U; o[2] = (mu_r == 0.0) ? INFINITY : mu_t / mu_r;
             if (P.dbg_u2) P.dbg_u2[(long long)g * P.n_genes + j] = u2;

@@ -192,6 +192,10 @@ class TorchDenseDataHandler(InRAMDataHandler):
         if X.is_cuda:
             from .engine import _to_f32_or_wide
 
+            want = torch.device(device)
+            if want.type == "cuda" and want.index is not None and X.device != want:
+                raise ValueError(f"expression tensor lives on {X.device} but the run was asked for {want}; move the tensor "
+                                 "or pass device=X.device (a kernel never reads another GPU's memory)")
             d, raw = (X, None) if X.dtype == torch.float32 else _to_f32_or_wide(X)
             if d is not None and d.stride(1) != 1:
                 d = d.contiguous()

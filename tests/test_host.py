@@ -299,3 +299,21 @@ def test_result_frame_matches_from_product():
         [pd.Series(groups, name="pert", dtype=str), pd.Series(dup, name="feature", dtype=str)], names=["pert", "feature"]),
         columns=["p_value", "statistic", "fold_change"])
     pd.testing.assert_frame_equal(got, want)
+
+
+def test_dispatch_cache_keys_follow_content_not_addresses():
+    """a matrix transformed in place, or a relabelled GroupContainer, must never hit a stale cache entry."""
+    from illico_b200 import dispatch
+
+    rng = np.random.RandomState(3)
+    X = rng.poisson(1.0, size=(500, 40)).astype(np.float32)
+    fp0 = dispatch._fingerprint(X)
+    assert dispatch._fingerprint(X) == fp0
+    np.log1p(X, out=X)                                # the standard in-place scanpy step
+    assert dispatch._fingerprint(X) != fp0
+    big = np.zeros(3_000_000, dtype=np.float32)       # sampled fingerprint: both ends and the strided sample are covered
+    f = dispatch._fingerprint(big)
+    big[-1] = 1.0
+    assert dispatch._fingerprint(big) != f
+    assert dispatch._fingerprint(np.asfortranarray(X)) == dispatch._fingerprint(np.asfortranarray(X))
+    assert isinstance(dispatch._fingerprint(X[::2, ::3]), int)   # non-contiguous views are sampled too
