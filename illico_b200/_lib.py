@@ -57,6 +57,8 @@ SIGNATURES = {
     "illico_last_error": (C.c_char_p, []),
     "illico_launch_count": (_i64, []),
     "illico_last_fused_ms": (C.c_double, []),
+    "illico_profile_report": (_i64, [C.c_char_p, _i64]),
+    "illico_memcpy2d_async": (C.c_int, [_vp, _sz, _vp, _sz, _sz, _sz, C.c_int, _vp]),
     "illico_stage_dense_f32": (C.c_int, [_vp, _i64, _i32, _i32, _PP, _vp, _vp, _vp]),
     "illico_stage_csr_workspace_bytes": (_sz, [_PP, _i32]),
     "illico_stage_csr_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _PP, _vp, _vp, _vp, _sz, _vp]),
@@ -72,6 +74,9 @@ SIGNATURES = {
     "illico_ovo_csr_f32": _DISPATCH_SPARSE,
     "illico_ovr_csc_f32": _DISPATCH_SPARSE,
     "illico_ovo_csc_f32": _DISPATCH_SPARSE,
+    "illico_bh_workspace_bytes": (_sz, [_i32, _i32]),
+    "illico_bh_adjust": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "illico_compute_pval_batch": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
 }
 
 _lib = None
@@ -108,3 +113,14 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().illico_launch_count())
+
+
+def profile_report() -> dict:
+    """``{kernel name: (total ms, launches)}`` of the launches recorded since the last call (``ILLICO_PROFILE=1``)."""
+    buf = C.create_string_buffer(1 << 16)
+    load().illico_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, n = line.split("\t")
+        out[name] = (float(ms), int(n))
+    return out

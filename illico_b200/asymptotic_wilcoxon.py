@@ -22,14 +22,17 @@ import pandas as pd
 import torch
 from scipy import sparse
 
-from .engine import CSR, Engine, make_flags, require_cuda
+from . import hostio
+from .engine import CSR, DeviceMatrix, Engine, make_flags, require_cuda
 from .groups import encode_and_count_groups
 from .registry import DataHandler, data_handler_registry
 
 __all__ = ["asymptotic_wilcoxon"]
 
 
-def _batches(n_genes: int, batch_size, engine: Engine, in_ram: bool):
+def _batches(lb: int, ub: int, batch_size, engine: Engine, in_ram: bool):
+    """Gene batches of the shard ``[lb, ub)`` (global gene indices)."""
+    n_genes = ub - lb
     if isinstance(batch_size, (int, np.integer)) and not isinstance(batch_size, bool):
         if batch_size <= 0:
             raise ValueError(f"Invalid batch_size value: {batch_size}. Must be 'auto' or an integer.")
@@ -41,12 +44,12 @@ def _batches(n_genes: int, batch_size, engine: Engine, in_ram: bool):
     else:
         raise ValueError(f"Invalid batch_size value: {batch_size}. Must be 'auto' or an integer.")
     step = max(1, step)
-    bounds = list(range(0, n_genes, step)) + [n_genes]
+    bounds = list(range(lb, ub, step)) + [ub]
     return list(zip(bounds[:-1], bounds[1:]))
 
 
 def operator(data_handler: DataHandler, lb: int, ub: int, engine: Engine, flags, results: torch.Tensor,
-             fetched=None) -> None:
+             fetched=None, result_gene0: int | None = None) -> None:
     """One gene batch: fetch -> device -> stage + rank, written into ``results[:, lb:ub, :]`` on the device
     (the reference's ``operator``, ``asymptotic_wilcoxon.py:29-68``)."""
     n_cols = data_handler.data.shape[1]
@@ -55,8 +58,41 @@ def operator(data_handler: DataHandler, lb: int, ub: int, engine: Engine, flags,
     if fetched is None:
         fetched = data_handler.fetch(lb, ub)
     data, bounds = fetched
-    M = data_handler.to_device(data, engine)
-    engine.run_batch(M, bounds[0], bounds[1], flags, results, lb)
+    M = data if isinstance(data, DeviceMatrix) else data_handler.to_device(data, engine)
+    engine.run_batch(M, bounds[0], bounds[1], flags, results, lb if result_gene0 is None else result_gene0)
+
+
+def _device_list(device, devices) -> list:
+    """``device`` (one GPU, the reference-compatible default) or ``devices`` ("all", a count, or a list)."""
+    if devices is None:
+        return [require_cuda(device)]
+    if device is not None:
+        raise ValueError("pass either device= or devices=, not both")
+    require_cuda(None)
+    n_all = torch.cuda.device_count()
+    if isinstance(devices, str):
+        if devices != "all":
+            raise ValueError(f"devices must be 'all', a count or a list of devices, got {devices!r}")
+        devs = list(range(n_all))
+    elif isinstance(devices, (int, np.integer)):
+        if not 1 <= int(devices) <= n_all:
+            raise ValueError(f"devices={devices}: this host has {n_all} CUDA devices")
+        devs = list(range(int(devices)))
+    else:
+        devs = list(devices)
+    out = [require_cuda(torch.device("cuda", d) if isinstance(d, (int, np.integer)) else d) for d in devs]
+    if not out or len({str(d) for d in out}) != len(out):
+        raise ValueError("devices must name at least one GPU, each once")
+    return out
+
+
+class _Shard:
+    """One GPU's share of a run: a contiguous gene range, its engine, its result slab."""
+
+    def __init__(self, device, lb, ub):
+        self.device, self.lb, self.ub = device, lb, ub
+        self.error = None
+        self.started = None     # (DeviceMatrix, bounds) of an upload started before the worker runs
 
 
 def asymptotic_wilcoxon(
@@ -72,68 +108,168 @@ def asymptotic_wilcoxon(
     layer: str | None = None,
     precompile: bool = True,
     device=None,
+    devices=None,
     return_array: bool = False,
+    p_adjust: bool = False,
+    log2_fold_change: bool = False,
 ):
-    """Asymptotic Mann-Whitney / Wilcoxon rank-sum tests for every (group, gene) on a B200.
+    """Asymptotic Mann-Whitney / Wilcoxon rank-sum tests for every (group, gene) on B200 GPUs.
 
     Same parameters and result as ``illico.asymptotic_wilcoxon``: a ``pd.DataFrame`` indexed by
     ``MultiIndex.from_product([groups, var_names], names=["pert", "feature"])`` with float64 columns
     ``p_value``, ``statistic`` (U of the reference / rest sample) and ``fold_change``.
 
-    Extra keyword arguments (not in the reference): ``device`` (CUDA device, default current) and
-    ``return_array`` (return ``(groups, var_names, results[G, N, 3])`` and skip the DataFrame).
+    Extra keyword arguments (not in the reference):
+      ``device``   CUDA device (default: the current one, or where a CUDA-tensor matrix lives);
+      ``devices``  ``"all"``, a count or a list: the genes are split into one contiguous shard per GPU; one host thread
+                   per GPU uploads its shard, ranks it and writes its ``results[:, lb:ub]`` slab straight into the one
+                   pinned result array -- no collective, no second process, one copy of ``adata`` in host memory
+                   (the reference's thread pool over gene batches, ``asymptotic_wilcoxon.py:212-249``, across GPUs);
+      ``return_array``  return ``(groups, var_names, results[G, N, 3])`` and skip the DataFrame;
+      ``p_adjust`` / ``log2_fold_change``  add the columns ``p_adj`` (Benjamini-Hochberg over the genes of each group,
+                   what ``scanpy.tl.rank_genes_groups`` reports as ``pvals_adj``) and ``log2_fold_change``.
     """
     del precompile  # kernels are compiled ahead of time
     X = adata.layers[layer] if layer is not None else adata.X
     if isinstance(X, (sparse.csr_array, sparse.csc_array)):
         X = sparse.csr_matrix(X) if isinstance(X, sparse.csr_array) else sparse.csc_matrix(X)
     data_handler = data_handler_registry.get(X)  # KeyError for unsupported containers, like the reference
-
-    # In-RAM input: start the host->device copy first; it runs (asynchronously for pinned memory) while the
-    # host encodes the groups and builds the plan.
-    if device is None and isinstance(X, torch.Tensor) and X.is_cuda:
+    if devices is None and device is None and isinstance(X, torch.Tensor) and X.is_cuda:
         device = X.device          # a device-resident matrix is ranked where it lives
-    dev = require_cuda(device)
-    if data_handler.in_ram:
-        with torch.cuda.device(dev):
-            data_handler.to_device(X, dev)
-
-    # the reference goes through `.tolist()` + a dict loop (utils/groups.py:42-45); same encoding, vectorised
-    unique_raw_groups, grpc = encode_and_count_groups(groups=adata.obs[group_keys], ref_group=reference)
+    devs = _device_list(device, devices)
     n_cells, n_genes = X.shape
-    if grpc.encoded_groups.size != n_cells:
-        raise ValueError(f"{grpc.encoded_groups.size} group labels for {n_cells} cells")
-
-    engine = Engine(grpc, dev)
     fmt = data_handler.kernel_data_format().value
-    flags = make_flags(is_log1p, use_continuity, tie_correct, alternative, fmt)
-    iterator = _batches(n_genes, batch_size, engine, data_handler.in_ram)
+    flags_for = lambda: make_flags(is_log1p, use_continuity, tie_correct, alternative, fmt)  # noqa: E731
+    flags_for()  # validates `alternative` before any work starts
+    if not (batch_size == "auto" or (isinstance(batch_size, (int, np.integer)) and not isinstance(batch_size, bool)
+                                      and batch_size > 0)):
+        raise ValueError(f"Invalid batch_size value: {batch_size}. Must be 'auto' or an integer.")
 
-    with torch.cuda.device(engine.device):
-        results = torch.empty((engine.n_groups, n_genes, 3), dtype=torch.float64, device=engine.device)
-        if data_handler.in_ram:
-            M = data_handler.to_device(X, engine)
-            if fmt == CSR and not engine.check_csr_sorted(M):
-                raise ValueError(
-                    "Input data matrix indices are not sorted. This is very unusual and may lead to incorrect results. "
-                    "This can be the result of operations like `adata[:, np.random.choice(…)]` that do not preserve sorting."
-                    "Please make sure that indices used to chunk the adata or the expression matrix have been sorted "
-                    "prior to computing DE genes."
-                )
-            for lb, ub in iterator:
-                operator(data_handler, lb, ub, engine, flags, results)
-        else:
-            _run_backed(data_handler, iterator, engine, flags, results, max(1, int(n_threads)))
-        host = torch.empty(results.shape, dtype=torch.float64, pin_memory=True)
-        host.copy_(results, non_blocking=True)
-        torch.cuda.current_stream(engine.device).synchronize()
-    out = host.numpy()
+    from .parallel import gene_shard
+
+    shards = [_Shard(d, *gene_shard(n_genes, r, len(devs))) for r, d in enumerate(devs)]
+    shards = [sh for sh in shards if sh.ub > sh.lb] or [_Shard(devs[0], 0, n_genes)]
+    plan_ready = threading.Event()
+    shared: dict = {}
+
+    def run_shard(sh: _Shard):
+        """Everything one GPU does, on its own host thread: upload its gene shard (started before the groups are
+        encoded), rank it batch by batch, deliver its slab."""
+        try:
+            if len(shards) > 1:
+                hostio.bind_thread_to_device_node(sh.device.index if sh.device.index is not None else 0)
+            with torch.cuda.device(sh.device):
+                M = bounds = None
+                if data_handler.in_ram:
+                    M, bounds = sh.started or data_handler.upload_shard(sh.lb, sh.ub, sh.device)
+                plan_ready.wait()
+                if "error" in shared:
+                    return
+                engine = Engine(shared["grpc"], sh.device, host_plan=shared["host_plan"])
+                flags = flags_for()
+                res = torch.empty((engine.n_groups, sh.ub - sh.lb, 3), dtype=torch.float64, device=sh.device)
+                if data_handler.in_ram:
+                    M.ready()
+                    if fmt == CSR and not engine.check_csr_sorted(M):
+                        raise ValueError(
+                            "Input data matrix indices are not sorted. This is very unusual and may lead to incorrect results. "
+                            "This can be the result of operations like `adata[:, np.random.choice(…)]` that do not preserve sorting."
+                            "Please make sure that indices used to chunk the adata or the expression matrix have been sorted "
+                            "prior to computing DE genes."
+                        )
+                    off = bounds[0] - sh.lb      # gene g of the run is column g + off of the device matrix
+                    for lb, ub in _batches(sh.lb, sh.ub, batch_size, engine, True):
+                        engine.run_batch(M, lb + off, ub + off, flags, res, lb - sh.lb)
+                else:
+                    _run_backed(data_handler, _batches(sh.lb, sh.ub, batch_size, engine, False), engine, flags, res,
+                                max(1, int(n_threads)), gene0=sh.lb)
+                hostio.d2h_slab(shared["host"], res, sh.lb)
+                torch.cuda.current_stream(sh.device).synchronize()
+        except BaseException as e:  # re-raised on the calling thread
+            sh.error = e
+
+    workers = []
+    if len(shards) > 1:
+        workers = [threading.Thread(target=run_shard, args=(sh,), daemon=True) for sh in shards]
+        for t in workers:
+            t.start()
+    try:
+        # the reference goes through `.tolist()` + a dict loop (utils/groups.py:42-45); same encoding, vectorised.
+        # With several GPUs the uploads are already running on the workers' threads while this happens.
+        if len(shards) == 1 and data_handler.in_ram:
+            # single GPU: start the upload from this thread, then encode while it is in flight
+            with torch.cuda.device(shards[0].device):
+                shards[0].started = data_handler.upload_shard(shards[0].lb, shards[0].ub, shards[0].device)
+        unique_raw_groups, grpc = encode_and_count_groups(groups=adata.obs[group_keys], ref_group=reference)
+        if grpc.encoded_groups.size != n_cells:
+            raise ValueError(f"{grpc.encoded_groups.size} group labels for {n_cells} cells")
+        from .groups import build_plan
+
+        shared["grpc"], shared["host_plan"] = grpc, build_plan(grpc, _seg_max())
+        G = int(grpc.counts.size)
+        shared["host"] = torch.empty((G, n_genes, 3), dtype=torch.float64, pin_memory=True)
+    except BaseException:
+        shared["error"] = True
+        plan_ready.set()
+        for t in workers:
+            t.join()
+        raise
+    plan_ready.set()
+    if workers:
+        for t in workers:
+            t.join()
+    else:
+        run_shard(shards[0])
+    for sh in shards:
+        if sh.error is not None:
+            raise sh.error
+    out = shared["host"].numpy()
+    extra = {}
+    if p_adjust:
+        extra["p_adj"] = _bh_adjust(out, shards[0].device)
+    if log2_fold_change:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            extra["log2_fold_change"] = np.log2(out[:, :, 2])
     if return_array:
+        if extra:
+            return unique_raw_groups, np.asarray(adata.var_names), out, extra
         return unique_raw_groups, np.asarray(adata.var_names), out
-    return _result_frame(unique_raw_groups, adata.var_names, out)
+    return _result_frame(unique_raw_groups, adata.var_names, out, extra)
 
 
-def _result_frame(groups, var_names, out: np.ndarray) -> pd.DataFrame:
+def _bh_adjust(out: np.ndarray, device) -> np.ndarray:
+    """Benjamini-Hochberg adjusted p-values over the genes of each group, ``[G, N]`` (needs every gene of a group, so
+    it runs once on the gathered result, on one GPU: ``illico_bh_adjust``)."""
+    import ctypes as C
+
+    from . import _lib
+
+    G, N = out.shape[0], out.shape[1]
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        res = torch.from_numpy(out).to(device, non_blocking=True)
+        padj = torch.empty((G, N), dtype=torch.float64, device=device)
+        ws = torch.empty(int(lib.illico_bh_workspace_bytes(G, N)), dtype=torch.uint8, device=device)
+        st = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(lib.illico_bh_adjust(res.data_ptr(), 3 * N, 3, G, N, padj.data_ptr(), ws.data_ptr(), ws.numel(), st),
+                   "illico_bh_adjust")
+        host = torch.empty((G, N), dtype=torch.float64, pin_memory=True)
+        host.copy_(padj, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+    del C
+    return host.numpy()
+
+
+def _seg_max() -> int:
+    import os
+
+    try:
+        return int(os.environ.get("ILLICO_B200_SEG_MAX", 512))
+    except ValueError:
+        return 512
+
+
+def _result_frame(groups, var_names, out: np.ndarray, extra: dict | None = None) -> pd.DataFrame:
     """The reference's result (``asymptotic_wilcoxon.py:252-256``): same index as ``MultiIndex.from_product([groups,
     var_names], names=["pert", "feature"])`` and the same three float64 columns, but the index is built from its codes
     and the values are a view of the (pinned) result array: 15 ms instead of 0.2-0.45 s at 16 M rows."""
@@ -148,7 +284,10 @@ def _result_frame(groups, var_names, out: np.ndarray) -> pd.DataFrame:
         index = pd.MultiIndex(levels=[rows, cols],
                               codes=[np.repeat(np.arange(G, dtype=ct(G)), N), np.tile(np.arange(N, dtype=ct(N)), G)],
                               names=["pert", "feature"], verify_integrity=False)
-    return pd.DataFrame(out.reshape(-1, 3), index=index, columns=["p_value", "statistic", "fold_change"], copy=False)
+    df = pd.DataFrame(out.reshape(-1, 3), index=index, columns=["p_value", "statistic", "fold_change"], copy=False)
+    for name, plane in (extra or {}).items():     # optional columns (default call: none, the reference's frame exactly)
+        df[name] = plane.reshape(-1)
+    return df
 
 
 class _PinnedSlot:
@@ -171,7 +310,7 @@ class _PinnedSlot:
         return view
 
 
-def _run_backed(data_handler: DataHandler, iterator, engine: Engine, flags, results, n_readers: int) -> None:
+def _run_backed(data_handler: DataHandler, iterator, engine: Engine, flags, results, n_readers: int, gene0: int = 0) -> None:
     """Out-of-core input (BASELINE config 4): gene batches stream disk -> pinned ring -> HBM -> kernels.
 
     Reader threads slice the next batches from the backed container straight into pinned staging buffers (a ring of
@@ -257,7 +396,7 @@ def _run_backed(data_handler: DataHandler, iterator, engine: Engine, flags, resu
             if data.dtype != torch.float32:
                 data, raw = _to_f32_or_wide(data)
             M = DeviceMatrix(fmt, tuple(shape), data, dv["indices"], dv["indptr"], raw=raw)
-        engine.run_batch(M, bounds[0], bounds[1], flags, results, lb)
+        engine.run_batch(M, bounds[0], bounds[1], flags, results, lb - gene0)
 
     try:
         while done < n_readers:

@@ -2,7 +2,14 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -18,6 +25,34 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- per-kernel profiling (ILLICO_PROFILE=1) ----------------------------------------------------------------
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static thread_local cudaEvent_t g_prof_open = nullptr;
+static thread_local const char* g_prof_name = nullptr;
+
+bool profiling_on() {
+    const char* v = getenv("ILLICO_PROFILE");
+    return v && v[0] != '0' && v[0] != 0;
+}
+void prof_begin(const char* name, cudaStream_t stream) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, stream);
+    g_prof_open = e;
+    g_prof_name = name;
+}
+void prof_end(cudaStream_t stream) {
+    if (!g_prof_open) return;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(ProfRec{g_prof_name, g_prof_open, e});
+    g_prof_open = nullptr;
+}
 
 // kernels' host launchers (stage.cu, rank_ovr.cu, rank_ovo.cu)
 int launch_stage_dense(const float*, long long, int, int, const illico_plan_t*, float*, uint32_t*, cudaStream_t);
@@ -76,6 +111,49 @@ int illico_abi_version(void) { return ILLICO_ABI_VERSION; }
 const char* illico_last_error(void) { return g_err; }
 int64_t illico_launch_count(void) { return (int64_t)g_launches.load(); }
 double illico_last_fused_ms(void) { return (double)ovo_fused_last_ms(); }
+
+int64_t illico_profile_report(char* out, int64_t cap) {
+    std::vector<ProfRec> recs;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        recs.swap(g_prof);
+    }
+    std::map<std::string, std::pair<double, long long>> acc;
+    std::vector<std::string> order;
+    for (auto& r : recs) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            auto it = acc.find(r.name);
+            if (it == acc.end()) { order.push_back(r.name); acc[r.name] = {0.0, 0}; it = acc.find(r.name); }
+            it->second.first += ms;
+            it->second.second += 1;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    std::string txt;
+    char line[256];
+    for (auto& nm : order) {
+        snprintf(line, sizeof(line), "%s\t%.6f\t%lld\n", nm.c_str(), acc[nm].first, acc[nm].second);
+        txt += line;
+    }
+    if (out && cap > 0) {
+        const size_t n = txt.size() < (size_t)(cap - 1) ? txt.size() : (size_t)(cap - 1);
+        memcpy(out, txt.data(), n);
+        out[n] = 0;
+    }
+    return (int64_t)txt.size();
+}
+
+int illico_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height,
+                          int kind, void* stream) {
+    if (!dst || !src) { set_error("illico_memcpy2d_async: NULL pointer"); return 1; }
+    if (kind != 1 && kind != 2) { set_error("illico_memcpy2d_async: kind must be 1 (host to device) or 2 (device to host)"); return 1; }
+    if (width_bytes == 0 || height == 0) return 0;
+    ILLICO_CUDA_OK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height,
+                                     kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
 
 int illico_stage_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t n_genes_batch, const illico_plan_t* plan,
                            float* ir_vals, uint32_t* ir_cnt, void* stream) {

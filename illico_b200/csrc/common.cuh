@@ -13,6 +13,25 @@ constexpr unsigned FULL = 0xffffffffu;
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Per-kernel timing for bench.py's roofline (ILLICO_PROFILE=1): every launch made through ILLICO_LAUNCH is bracketed
+// by two CUDA events on the launching stream; illico_profile_report() adds them up per kernel name.  Off by default
+// (one getenv per launch).
+bool profiling_on();
+void prof_begin(const char* name, cudaStream_t stream);
+void prof_end(cudaStream_t stream);
+struct ProfScope {
+    cudaStream_t s;
+    bool on;
+    ProfScope(const char* name, cudaStream_t stream) : s(stream), on(profiling_on()) { if (on) prof_begin(name, s); }
+    ~ProfScope() { if (on) prof_end(s); }
+};
+#define ILLICO_LAUNCH(name, stream, ...)              \
+    do {                                              \
+        ::illico::ProfScope _ps(name, stream);        \
+        __VA_ARGS__;                                  \
+        ::illico::count_launch();                     \
+    } while (0)
+
 #define ILLICO_CUDA_OK(expr)                                                                       \
     do {                                                                                           \
         cudaError_t _e = (expr);                                                                   \

@@ -801,9 +801,8 @@ int launch_pass_t(const float* X, long long ld, int gene_lb, int b, const illico
     auto kern = fused_pass_kernel<ROWS, STAGES, BUF, MINB, OVO>;
     ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
     const dim3 grid((unsigned)((b + FUSED_LANES - 1) / FUSED_LANES), (unsigned)((plan->n_groups + gpc - 1) / gpc));
-    kern<<<grid, FUSED_THREADS, L::BYTES, stream>>>(X, ld, gene_lb, b, *plan, gpc, gt, bs,
-                                                    reinterpret_cast<unsigned long long*>(results), gstride);
-    count_launch();
+    ILLICO_LAUNCH("fused_pass_kernel", stream, kern<<<grid, FUSED_THREADS, L::BYTES, stream>>>(X, ld, gene_lb, b, *plan, gpc, gt, bs,
+                                                    reinterpret_cast<unsigned long long*>(results), gstride));
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -838,8 +837,7 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
         if (rc != 0) return rc;
         int blocks = (b + 7) / 8;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        fused_ctab_kernel<<<blocks, 256, 0, stream>>>(buf->ir_vals, buf->ir_cnt, b, *plan, seg_lo, seg_hi, flags->is_log1p, gt, bs);
-        count_launch();
+        ILLICO_LAUNCH("fused_ctab_kernel", stream, fused_ctab_kernel<<<blocks, 256, 0, stream>>>(buf->ir_vals, buf->ir_cnt, b, *plan, seg_lo, seg_hi, flags->is_log1p, gt, bs));
         ILLICO_CUDA_OK(cudaGetLastError());
     }
     if (!OVO)   // the sample only seeds the slots; gt.mult restarts as the whole gene's histogram
@@ -878,15 +876,13 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
     if (timed) ILLICO_CUDA_OK(cudaEventRecord(e1, stream));
 
     // 3. per-gene weights, then the epilogue
-    fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, (dbg && !OVO) ? dbg->tie_sum : nullptr,
-                                                                (dbg && !OVO) ? (long long*)dbg->tie_exact : nullptr);
-    count_launch();
+    ILLICO_LAUNCH("fused_gene_kernel", stream, fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, (dbg && !OVO) ? dbg->tie_sum : nullptr,
+                                                                (dbg && !OVO) ? (long long*)dbg->tie_exact : nullptr));
     ILLICO_CUDA_OK(cudaGetLastError());
     {
-        fused_epilogue_kernel<OVO><<<dim3((unsigned)((b + 255) / 256), (unsigned)((plan->n_groups + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
+        ILLICO_LAUNCH("fused_epilogue_kernel", stream, fused_epilogue_kernel<OVO><<<dim3((unsigned)((b + 255) / 256), (unsigned)((plan->n_groups + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
             b, *plan, *flags, gt, bs, results, gstride, dbg ? (long long*)dbg->u2 : nullptr,
-            (dbg && OVO) ? dbg->tie_sum : nullptr, (dbg && OVO) ? (long long*)dbg->tie_exact : nullptr);
-        count_launch();
+            (dbg && OVO) ? dbg->tie_sum : nullptr, (dbg && OVO) ? (long long*)dbg->tie_exact : nullptr));
         ILLICO_CUDA_OK(cudaGetLastError());
     }
 
@@ -917,8 +913,7 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
             double* tmp = reinterpret_cast<double*>(buf->ir_vals + tmp_off);
             int* dlist = reinterpret_cast<int*>(buf->ir_vals + list_off);
             ILLICO_CUDA_OK(cudaMemcpyAsync(dlist, list.data(), (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, stream));
-            gather_genes_kernel<<<148 * 16, 256, 0, stream>>>(X, ld, gene_lb, dlist, nb, nbp, (int)n, Xc);
-            count_launch();
+            ILLICO_LAUNCH("gather_genes_kernel", stream, gather_genes_kernel<<<148 * 16, 256, 0, stream>>>(X, ld, gene_lb, dlist, nb, nbp, (int)n, Xc));
             ILLICO_CUDA_OK(cudaGetLastError());
             if (launch_stage_dense(Xc, nbp, 0, nbp, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
             const int rr = OVO ? launch_ovo(buf->ir_vals, buf->ir_cnt, nbp, plan, flags, tmp, 3ll * nbp, buf->workspace,
@@ -926,8 +921,7 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
                                : launch_ovr(buf->ir_vals, buf->ir_cnt, nbp, plan, flags, tmp, 3ll * nbp, buf->workspace,
                                             buf->workspace_bytes, nullptr, stream);
             if (rr) return 1;
-            scatter_results_kernel<<<148 * 4, 256, 0, stream>>>(tmp, nb, nbp, dlist, plan->n_groups, results, gstride);
-            count_launch();
+            ILLICO_LAUNCH("scatter_results_kernel", stream, scatter_results_kernel<<<148 * 4, 256, 0, stream>>>(tmp, nb, nbp, dlist, plan->n_groups, results, gstride));
             ILLICO_CUDA_OK(cudaGetLastError());
             ILLICO_CUDA_OK(cudaStreamSynchronize(stream));   // `list` (pageable) must outlive its copy
             return 0;
@@ -982,10 +976,8 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
     const int G = plan->n_groups;
 
     // tables: raw counts get slots 1 .. 12 up front (log1p data claims its slots while streaming)
-    fused_seed_kernel<<<(bs + 255) / 256, 256, 0, stream>>>(gt, bs, flags->is_log1p ? 0 : 1);
-    count_launch();
-    fused_zero_multi_kernel<<<dim3(8, (unsigned)G), 256, 0, stream>>>(b, *plan, rec, gstride);
-    count_launch();
+    ILLICO_LAUNCH("fused_seed_kernel", stream, fused_seed_kernel<<<(bs + 255) / 256, 256, 0, stream>>>(gt, bs, flags->is_log1p ? 0 : 1));
+    ILLICO_LAUNCH("fused_zero_multi_kernel", stream, fused_zero_multi_kernel<<<dim3(8, (unsigned)G), 256, 0, stream>>>(b, *plan, rec, gstride));
     ILLICO_CUDA_OK(cudaGetLastError());
 
     const bool timed = env_int("ILLICO_PROFILE", 0) != 0;
@@ -1006,8 +998,7 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
         const dim3 grid((unsigned)((b + CSRF_TILE - 1) / CSRF_TILE), (unsigned)plan->n_segments);
         // (Counting part of the updates in a per-SM global histogram with L2 reductions instead of shared atomics
         // measured 1.4-1.9 x slower.)
-        kern<<<grid, CSRF_THREADS, smem, stream>>>(data, indices, indptr, gene_lb, b, *plan, gt, bs, rec, gstride);
-        count_launch();
+        ILLICO_LAUNCH("fused_csr_pass_kernel", stream, kern<<<grid, CSRF_THREADS, smem, stream>>>(data, indices, indptr, gene_lb, b, *plan, gt, bs, rec, gstride));
         ILLICO_CUDA_OK(cudaGetLastError());
     }
     if (timed) ILLICO_CUDA_OK(cudaEventRecord(e1, stream));
@@ -1023,18 +1014,15 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
 
     if (!OVO) {
         const int gpb = 64;
-        fused_hist_sum_kernel<<<dim3((unsigned)((b + 255) / 256), (unsigned)((G + gpb - 1) / gpb)), 256, 0, stream>>>(b, G, gpb, gt, bs, rec,
-                                                                                                                 gstride);
-        count_launch();
+        ILLICO_LAUNCH("fused_hist_sum_kernel", stream, fused_hist_sum_kernel<<<dim3((unsigned)((b + 255) / 256), (unsigned)((G + gpb - 1) / gpb)), 256, 0, stream>>>(b, G, gpb, gt, bs, rec,
+                                                                                                                 gstride));
     }
-    fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, (dbg && !OVO) ? dbg->tie_sum : nullptr,
-                                                                (dbg && !OVO) ? (long long*)dbg->tie_exact : nullptr);
-    count_launch();
+    ILLICO_LAUNCH("fused_gene_kernel", stream, fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, (dbg && !OVO) ? dbg->tie_sum : nullptr,
+                                                                (dbg && !OVO) ? (long long*)dbg->tie_exact : nullptr));
     {
-        fused_epilogue_kernel<OVO><<<dim3((unsigned)((b + 255) / 256), (unsigned)((G + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
+        ILLICO_LAUNCH("fused_epilogue_kernel", stream, fused_epilogue_kernel<OVO><<<dim3((unsigned)((b + 255) / 256), (unsigned)((G + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
             b, *plan, *flags, gt, bs, results, gstride, dbg ? (long long*)dbg->u2 : nullptr,
-            (dbg && OVO) ? dbg->tie_sum : nullptr, (dbg && OVO) ? (long long*)dbg->tie_exact : nullptr);
-        count_launch();
+            (dbg && OVO) ? dbg->tie_sum : nullptr, (dbg && OVO) ? (long long*)dbg->tie_exact : nullptr));
         ILLICO_CUDA_OK(cudaGetLastError());
     }
     if (n_bad == 0) return 0;

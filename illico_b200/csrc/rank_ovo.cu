@@ -578,8 +578,7 @@ static int launch_ovo_t(OvoParams& P, const illico_plan_t* plan, void* workspace
         if (grid < 1) { set_error("rank workspace too small: %zu bytes", workspace_bytes); return 1; }
     }
     P.slab = (uint32_t*)workspace; P.slab_words = (long long)slab_words;
-    kern<<<grid, NT, need, stream>>>(P);
-    count_launch();
+    ILLICO_LAUNCH("ovo_kernel", stream, kern<<<grid, NT, need, stream>>>(P));
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -603,9 +602,8 @@ int launch_ovo(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const 
         int* d_max = reinterpret_cast<int*>(workspace);
         int h_max = 0;
         ILLICO_CUDA_OK(cudaMemsetAsync(d_max, 0, sizeof(int), stream));
-        max_ref_nnz_kernel<<<(n_genes + 255) / 256, 256, 0, stream>>>(ir_cnt, n_genes, plan->n_segments, plan->ref_seg_begin,
-                                                                      plan->ref_seg_end, d_max);
-        count_launch();
+        ILLICO_LAUNCH("max_ref_nnz_kernel", stream, max_ref_nnz_kernel<<<(n_genes + 255) / 256, 256, 0, stream>>>(ir_cnt, n_genes, plan->n_segments, plan->ref_seg_begin,
+                                                                      plan->ref_seg_end, d_max));
         ILLICO_CUDA_OK(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, stream));
         ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
         P.ref_cap = h_max;

@@ -682,14 +682,12 @@ int launch_ovr(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const 
             P.table_rec = reinterpret_cast<uint4*>(reinterpret_cast<char*>(workspace) + slabs);
             P.table_rec_stride = (long long)(rec_cta / 16);
         }
-        ovr_table_kernel<<<tgrid, T_THREADS, 0, stream>>>(P);
-        count_launch();
+        ILLICO_LAUNCH("ovr_table_kernel", stream, ovr_table_kernel<<<tgrid, T_THREADS, 0, stream>>>(P));
         ILLICO_CUDA_OK(cudaGetLastError());
     } else {
         P.todo = nullptr; P.todo_count = nullptr;
     }
-    ovr_kernel<<<grid, OVR_THREADS, need, stream>>>(P);
-    count_launch();
+    ILLICO_LAUNCH("ovr_kernel", stream, ovr_kernel<<<grid, OVR_THREADS, need, stream>>>(P));
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -16,7 +16,8 @@ constexpr int RADIX_AUX_WORDS = 40;
 // Pointers may be shared or global (generic addressing).  Passes in which every key has the same
 // digit are skipped (integer-valued floats have two constant low bytes).  Returns the buffer that
 // holds the sorted keys.  Must be called by all threads of the block.
-static __device__ __noinline__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, uint32_t* hist, uint32_t* aux) {
+template <typename KeyT>
+static __device__ __noinline__ KeyT* block_radix_sort_t(KeyT* a, KeyT* b, int n, uint32_t* hist, uint32_t* aux) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, NW = blockDim.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     if (n <= 1) return a;
@@ -24,7 +25,7 @@ static __device__ __noinline__ uint32_t* block_radix_sort(uint32_t* a, uint32_t*
     const int beg = min(w * chunk, n), end = min(beg + chunk, n);
     uint32_t* myhist = hist + w * 256;
 
-    for (int shift = 0; shift < 32; shift += 8) {
+    for (int shift = 0; shift < (int)sizeof(KeyT) * 8; shift += 8) {
         for (int i = tid; i < NW * 256; i += blockDim.x) hist[i] = 0;
         if (tid == 0) aux[32] = 0;
         __syncthreads();
@@ -32,7 +33,7 @@ static __device__ __noinline__ uint32_t* block_radix_sort(uint32_t* a, uint32_t*
         for (int i0 = beg; i0 < end; i0 += 32) {
             int i = i0 + lane;
             bool valid = i < end;
-            uint32_t d = valid ? ((a[i] >> shift) & 255u) : (256u + lane);
+            uint32_t d = valid ? ((uint32_t)(a[i] >> shift) & 255u) : (256u + lane);
             unsigned peers = __match_any_sync(FULL, d);
             if (valid && lane == __ffs(peers) - 1) myhist[d] += __popc(peers);
             __syncwarp();
@@ -64,8 +65,8 @@ static __device__ __noinline__ uint32_t* block_radix_sort(uint32_t* a, uint32_t*
         for (int i0 = beg; i0 < end; i0 += 32) {
             int i = i0 + lane;
             bool valid = i < end;
-            uint32_t key = valid ? a[i] : 0u;
-            uint32_t d = valid ? ((key >> shift) & 255u) : (256u + lane);
+            KeyT key = valid ? a[i] : KeyT(0);
+            uint32_t d = valid ? ((uint32_t)(key >> shift) & 255u) : (256u + lane);
             unsigned peers = __match_any_sync(FULL, d);
             uint32_t pos = valid ? myhist[d] + __popc(peers & lt) : 0u;
             if (valid) b[pos] = key;
@@ -74,9 +75,12 @@ static __device__ __noinline__ uint32_t* block_radix_sort(uint32_t* a, uint32_t*
             __syncwarp();
         }
         __syncthreads();
-        uint32_t* t = a; a = b; b = t;
+        KeyT* t = a; a = b; b = t;
     }
     return a;
+}
+static __device__ __forceinline__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, uint32_t* hist, uint32_t* aux) {
+    return block_radix_sort_t<uint32_t>(a, b, n, hist, aux);
 }
 
 // Bitonic sort of P (power of two) keys in shared memory by ONE warp.

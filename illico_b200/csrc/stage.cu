@@ -381,7 +381,8 @@ __global__ void check_csr_sorted_kernel(const int32_t* __restrict__ indices, con
 template <bool TILE, int VEC>
 static void launch_stage_dense_t(dim3 grid, cudaStream_t stream, const float* X, long long ld, int gene_lb, int b,
                                  const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, int segs_per_cta) {
-    stage_dense_kernel<TILE, VEC><<<grid, STAGE_WARPS * 32, 0, stream>>>(X, ld, gene_lb, b, *plan, ir_vals, ir_cnt, segs_per_cta);
+    ILLICO_LAUNCH("stage_dense_kernel", stream,
+                  stage_dense_kernel<TILE, VEC><<<grid, STAGE_WARPS * 32, 0, stream>>>(X, ld, gene_lb, b, *plan, ir_vals, ir_cnt, segs_per_cta));
 }
 
 // stage_dense_tma.cu
@@ -422,7 +423,6 @@ int launch_stage_dense(const float* X, long long ld, int gene_lb, int b, const i
     else if (tile) launch_stage_dense_t<true, 1>(grid, stream, X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta);
     else if (vec2) launch_stage_dense_t<false, 2>(grid, stream, X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta);
     else launch_stage_dense_t<false, 1>(grid, stream, X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta);
-    count_launch();
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -444,8 +444,7 @@ int launch_stage_csr(const float* data, const int32_t* indices, const long long*
     int32_t* split = reinterpret_cast<int32_t*>(workspace);
     long long blocks = ((long long)plan->n_cells + 7) / 8;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    csr_split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indices, indptr, plan->n_cells, gene_lb, b, K, split);
-    count_launch();
+    ILLICO_LAUNCH("csr_split_kernel", stream, csr_split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indices, indptr, plan->n_cells, gene_lb, b, K, split));
     ILLICO_CUDA_OK(cudaGetLastError());
     const int S = plan->n_segments;
     long long avg = plan->n_cells / S;
@@ -462,9 +461,8 @@ int launch_stage_csr(const float* data, const int32_t* indices, const long long*
     const size_t smem = CSR_MAX_ROWS * 8 + CSR_CAP * 4 + (2 * CSR_GC + 1) * 4 + CSR_MAX_ROWS * 4 + 9 * 4 +
                         CSR_MAX_SEGS * CSR_GC * 2 + 16;
     ILLICO_CUDA_OK(cudaFuncSetAttribute(stage_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stage_csr_kernel<<<dim3((unsigned)K, (unsigned)gy), CSR_THREADS, smem, stream>>>(data, indices, indptr, gene_lb, b, K, split,
-                                                                                     *plan, ir_vals, ir_cnt, segs_per_cta);
-    count_launch();
+    ILLICO_LAUNCH("stage_csr_kernel", stream, stage_csr_kernel<<<dim3((unsigned)K, (unsigned)gy), CSR_THREADS, smem, stream>>>(data, indices, indptr, gene_lb, b, K, split,
+                                                                                     *plan, ir_vals, ir_cnt, segs_per_cta));
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -473,8 +471,7 @@ int launch_stage_csc(const float* data, const int32_t* indices, const long long*
                      const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, cudaStream_t stream) {
     if (b <= 0) return 0;
     int blocks = b < 148 * 32 ? b : 148 * 32;
-    stage_csc_kernel<<<blocks, 256, 0, stream>>>(data, indices, indptr, gene_lb, b, *plan, ir_vals, ir_cnt);
-    count_launch();
+    ILLICO_LAUNCH("stage_csc_kernel", stream, stage_csc_kernel<<<blocks, 256, 0, stream>>>(data, indices, indptr, gene_lb, b, *plan, ir_vals, ir_cnt));
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -486,8 +483,7 @@ int launch_check_csr_sorted(const int32_t* indices, const long long* indptr, lon
     if (n_rows > 0) {
         long long blocks = (n_rows + 7) / 8;
         if (blocks > 148 * 32) blocks = 148 * 32;
-        check_csr_sorted_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indices, indptr, n_rows, d_flag);
-        count_launch();
+        ILLICO_LAUNCH("check_csr_sorted_kernel", stream, check_csr_sorted_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indices, indptr, n_rows, d_flag));
         ILLICO_CUDA_OK(cudaGetLastError());
     }
     int h = -1;

@@ -246,9 +246,9 @@ int launch_t(const float* X, long long ld, int gene_lb, int b, const illico_plan
     const size_t smem = L::bytes(segs_per_cta);
     auto kern = stage_dense_tma_kernel<VEC, ROWS, STAGES>;
     ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(gx, gy), TMA_THREADS, smem, stream>>>(X, ld, gene_lb, b, *plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi,
-                                                      env_int("ILLICO_STAGE_TMA_NOSTORE", 0));  // measurement aid: read path alone
-    count_launch();
+    ILLICO_LAUNCH("stage_dense_tma_kernel", stream,
+                  kern<<<dim3(gx, gy), TMA_THREADS, smem, stream>>>(X, ld, gene_lb, b, *plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi,
+                                                                    env_int("ILLICO_STAGE_TMA_NOSTORE", 0)));  // (measurement aid: read path alone)
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 import threading
 import warnings
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 
 import numpy as np
 import torch
@@ -29,20 +29,34 @@ def _env_int(name: str, default: int) -> int:
 
 @dataclass
 class DeviceMatrix:
-    """An expression matrix resident in HBM, in one of the three kernel formats."""
+    """An expression matrix (or a gene shard of one) resident in HBM, in one of the three kernel formats."""
 
     fmt: str
     shape: tuple
-    data: torch.Tensor            # dense: [n, ld] float32 ; sparse: [nnz] float32
+    data: torch.Tensor | None     # dense: [n, ld] float32 ; sparse: [nnz] float32
     indices: torch.Tensor | None = None   # int32 [nnz]
     indptr: torch.Tensor | None = None    # int64
     gene_offset: int = 0          # genes [gene_offset, gene_offset + shape[1]) of the caller's matrix
     raw: torch.Tensor | None = None  # values float32 cannot hold exactly (float64 / big integers), as float64:
     #                                  `data` is then unused and every batch is recoded (Engine._run_batch_wide)
+    pending: list = field(default_factory=list)   # hostio.Pending uploads still in flight
+    unconverted: torch.Tensor | None = None       # uploaded values of another dtype, converted once the upload is in
 
     @property
     def ld(self) -> int:
         return int(self.data.stride(0)) if self.fmt == DENSE else 0
+
+    def ready(self) -> "DeviceMatrix":
+        """Joins the uploads (the current stream then waits for their copies) and converts non-float32 values.
+        Call from the thread, and under the stream, that is going to launch kernels on this matrix."""
+        if self.pending:
+            for p in self.pending:
+                p.finish()
+            self.pending = []
+        if self.unconverted is not None:
+            self.data, self.raw = _to_f32_or_wide(self.unconverted)
+            self.unconverted = None
+        return self
 
 
 def require_cuda(device=None) -> torch.device:
@@ -55,11 +69,12 @@ def require_cuda(device=None) -> torch.device:
 
 
 class Engine:
-    def __init__(self, grpc: GroupContainer, device=None, seg_max: int | None = None):
+    def __init__(self, grpc: GroupContainer, device=None, seg_max: int | None = None, host_plan: HostPlan | None = None):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.grpc = grpc
-        self.host_plan: HostPlan = build_plan(grpc, seg_max or _env_int("ILLICO_B200_SEG_MAX", 512))
+        # the host-side plan does not depend on the device: one per run, shared by the engines of all GPUs
+        self.host_plan: HostPlan = host_plan or build_plan(grpc, seg_max or _env_int("ILLICO_B200_SEG_MAX", 512))
         hp = self.host_plan
         with torch.cuda.device(self.device):
             self._tables = {k: torch.from_numpy(getattr(hp, k)).to(self.device) for k in HostPlan.TABLES}
@@ -140,6 +155,8 @@ class Engine:
             raise ValueError(f"matrix has {M.shape[0]} cells, groups describe {self.host_plan.n_cells}")
         if lb < 0 or ub > M.shape[1]:
             raise ValueError(f"Invalid chunk bounds: {(lb, ub)} for data with {M.shape[1]} columns.")
+        with torch.cuda.device(self.device):
+            M.ready()
         if M.raw is not None:
             return self._run_batch_wide(M, lb, ub, flags, results, result_gene0, debug)
         self._ensure_buffers(b)
@@ -198,40 +215,68 @@ class Engine:
                 debug[k] = torch.cat(parts, dim=-1)
 
 
-def upload_dense(X: np.ndarray, device, gene_lb: int = 0, gene_ub: int | None = None) -> DeviceMatrix:
-    """Enqueues the copy of ``X[:, gene_lb:gene_ub]`` (any real dtype) into a float32 device matrix.
-    Asynchronous when ``X`` lives in pinned memory: the caller can keep working on the host meanwhile."""
+_TORCH_OK = (np.float32, np.float64, np.float16, np.int8, np.uint8, np.int16, np.int32, np.int64)
+
+
+def _uploadable(a: np.ndarray) -> np.ndarray:
+    """Host arrays of dtypes torch cannot hold (unsigned 16/32/64-bit, bool, ...) are widened on the host."""
+    if a.dtype.type in _TORCH_OK:
+        return a
+    if a.dtype.kind in "ui" and a.dtype.itemsize < 8:
+        return a.astype(np.int64)
+    return a.astype(np.float64)
+
+
+def _torch_dtype(a: np.ndarray):
+    return torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype
+
+
+def upload_dense(X, device, gene_lb: int = 0, gene_ub: int | None = None) -> DeviceMatrix:
+    """Starts the copy of ``X[:, gene_lb:gene_ub]`` (any real dtype) into a device matrix and returns at once: pinned
+    sources go out as one strided asynchronous copy, pageable ones through the pinned staging ring of
+    :mod:`illico_b200.hostio` (worker threads), so the caller keeps working on the host meanwhile.
+    ``DeviceMatrix.ready()`` joins."""
+    from . import hostio
+
     device = require_cuda(device)
     n, N = X.shape
     gene_ub = N if gene_ub is None else gene_ub
-    view = X[:, gene_lb:gene_ub]
+    if isinstance(X, torch.Tensor):
+        X = X.numpy()
+    view = _uploadable(np.asarray(X[:, gene_lb:gene_ub]))
     with torch.cuda.device(device):
-        with warnings.catch_warnings():  # read-only inputs (memmap, backed arrays) are only read from
-            warnings.simplefilter("ignore", UserWarning)
-            t = torch.from_numpy(view) if isinstance(view, np.ndarray) else view
-        raw = None
-        if t.dtype == torch.float32:
-            d = torch.empty((n, gene_ub - gene_lb), dtype=torch.float32, device=device)
-            d.copy_(t, non_blocking=True)
-        else:
-            d, raw = _to_f32_or_wide(t.to(device))
-    return DeviceMatrix(DENSE, (n, gene_ub - gene_lb), d, gene_offset=gene_lb, raw=raw)
+        d = torch.empty((n, gene_ub - gene_lb), dtype=_torch_dtype(view), device=device)
+        pend = hostio.h2d_2d(d, view)
+    if d.dtype == torch.float32:
+        return DeviceMatrix(DENSE, (n, gene_ub - gene_lb), d, gene_offset=gene_lb, pending=[pend])
+    return DeviceMatrix(DENSE, (n, gene_ub - gene_lb), None, gene_offset=gene_lb, pending=[pend], unconverted=d)
 
 
-def upload_sparse(X, fmt: str, device) -> DeviceMatrix:
-    """Enqueues the copies of a scipy CSR / CSC matrix.  The small ``indptr`` goes first: it is converted (int64) into
-    pageable memory, and a copy from pageable memory waits for everything queued before it -- after the two big
-    arrays it would block the host for the whole upload and nothing could overlap with it."""
+def upload_sparse(X, fmt: str, device, gene_lb: int = 0, gene_ub: int | None = None) -> DeviceMatrix:
+    """Starts the copies of a scipy CSR / CSC matrix (or a ``(data, indices, indptr, shape)`` namedtuple).  A CSC matrix
+    can be cut to the gene shard ``[gene_lb, gene_ub)`` (its columns are contiguous); a CSR matrix always goes up whole
+    (every row holds all genes) and the kernels select the gene range.  The small ``indptr`` goes first: it is
+    converted (int64) into pageable memory, and a copy from pageable memory waits for everything queued before it."""
+    from . import hostio
+
     device = require_cuda(device)
+    n, N = X.shape
+    data, indices, indptr = np.asarray(X.data), np.asarray(X.indices), np.asarray(X.indptr)
+    offset = 0
+    if fmt == CSC and (gene_lb != 0 or (gene_ub is not None and gene_ub != N)):
+        gene_ub = N if gene_ub is None else gene_ub
+        lo, hi = int(indptr[gene_lb]), int(indptr[gene_ub])
+        data, indices, indptr = data[lo:hi], indices[lo:hi], indptr[gene_lb:gene_ub + 1] - lo
+        N, offset = gene_ub - gene_lb, gene_lb
+    data = _uploadable(np.ascontiguousarray(data))
     with torch.cuda.device(device):
-        indptr = torch.from_numpy(np.ascontiguousarray(X.indptr, dtype=np.int64)).to(device, non_blocking=True)
-        data = torch.from_numpy(np.ascontiguousarray(X.data))
-        data = data.to(device, non_blocking=True)
-        raw = None
-        if data.dtype != torch.float32:
-            data, raw = _to_f32_or_wide(data)
-        indices = torch.from_numpy(np.ascontiguousarray(X.indices, dtype=np.int32)).to(device, non_blocking=True)
-    return DeviceMatrix(fmt, tuple(X.shape), data, indices, indptr, raw=raw)
+        d_indptr = torch.from_numpy(np.ascontiguousarray(indptr, dtype=np.int64)).to(device, non_blocking=True)
+        d_data = torch.empty(data.shape, dtype=_torch_dtype(data), device=device)
+        d_idx = torch.empty(indices.shape, dtype=torch.int32, device=device)
+        pend = [hostio.h2d_1d(d_data, data), hostio.h2d_1d(d_idx, np.ascontiguousarray(indices, dtype=np.int32))]
+    if d_data.dtype == torch.float32:
+        return DeviceMatrix(fmt, (n, N), d_data, d_idx, d_indptr, gene_offset=offset, pending=pend)
+    return DeviceMatrix(fmt, (n, N), None, d_idx, d_indptr, gene_offset=offset, pending=pend, unconverted=d_data)
 
 
 def _dense_block_f64(M: DeviceMatrix, lb: int, ub: int) -> torch.Tensor:

@@ -1,0 +1,257 @@
+"""Host <-> device transfers for host matrices (plumbing; the reference has no device boundary, this replaces its
+zero-copy ``InRAMDataHandler.fetch``, ``illico/utils/registry.py:97-100``).
+
+Three cases:
+  * pinned source (``torch.Tensor.pin_memory()`` behind the ndarray, or ``cudaHostRegister``-ed memory): one asynchronous
+    ``cudaMemcpy2DAsync`` straight from the user's buffer -- also for a column shard ``X[:, lb:ub]`` of a C-order matrix
+    (a strided source), which is how the genes are split across GPUs;
+  * pageable source (what ``adata.X`` normally is): worker threads copy row chunks into a ring of pinned staging
+    buffers (numpy releases the GIL in the copy loop) and enqueue each chunk's ``cudaMemcpyAsync`` on their own stream,
+    so that the host-side copies of several threads and the DMA of earlier chunks overlap; the caller keeps working on
+    the host meanwhile and joins with :meth:`Pending.finish`;
+  * results: each GPU writes its ``results[:, lb:ub, :]`` slab straight into ONE pinned ``[G, N, 3]`` host array with a
+    strided device-to-host copy.
+"""
+from __future__ import annotations
+
+import os
+import threading
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+
+CHUNK_BYTES = int(os.environ.get("ILLICO_STAGE_CHUNK_MB", "32")) << 20
+_rings: dict = {}
+_rings_lock = threading.Lock()
+
+
+def stage_threads() -> int:
+    env = os.environ.get("ILLICO_STAGE_THREADS")
+    if env:
+        return max(1, int(env))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, min(8, (os.cpu_count() or 8) // max(1, local_world)))
+
+
+def is_pinned(a: np.ndarray) -> bool:
+    """True when the array's memory is page-locked and known to CUDA (asynchronous DMA is possible from it)."""
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")          # read-only arrays: we only read
+            return bool(torch.from_numpy(a[:1] if a.ndim else a.reshape(1)).is_pinned())
+    except Exception:
+        return False
+
+
+# ---- NUMA placement ------------------------------------------------------------------------------------------------
+def numa_cpus_for_device(index: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None when unknown / single node."""
+    try:
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dev = torch.cuda.get_device_properties(index).pci_device_id
+        dom = torch.cuda.get_device_properties(index).pci_domain_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return cpus if cpus and cpus != allowed else None
+    except Exception:
+        return None
+
+
+def bind_thread_to_device_node(index: int) -> None:
+    """Runs the calling thread on the CPUs next to GPU ``index`` (first touch then places its pinned buffers there)."""
+    cpus = numa_cpus_for_device(index)
+    if cpus:
+        try:
+            os.sched_setaffinity(0, cpus)
+        except Exception:
+            pass
+
+
+# ---- strided copies through the C ABI (cudaMemcpy2DAsync) -------------------------------------------------------------
+def copy2d_async(dst_ptr: int, dpitch: int, src_ptr: int, spitch: int, width_bytes: int, height: int, kind: str, stream) -> None:
+    lib = _lib.load()
+    rc = lib.illico_memcpy2d_async(dst_ptr, dpitch, src_ptr, spitch, width_bytes, height, {"h2d": 1, "d2h": 2}[kind],
+                                   stream.cuda_stream)
+    _lib.check(rc, "illico_memcpy2d_async")
+
+
+class _Ring:
+    """Per (device, thread slot) pinned staging buffers, created once per process (page-locking 32 MB costs ~10 ms)."""
+
+    def __init__(self, device, n_threads):
+        self.device = device
+        self.bufs = [[None, None] for _ in range(n_threads)]
+        self.events = [[None, None] for _ in range(n_threads)]
+        self.streams = [None] * n_threads
+        self.busy = False
+
+    def slot(self, t, k):
+        if self.bufs[t][k] is None:
+            self.bufs[t][k] = torch.empty(CHUNK_BYTES, dtype=torch.uint8, pin_memory=True)
+        return self.bufs[t][k]
+
+    def stream(self, t):
+        if self.streams[t] is None:
+            self.streams[t] = torch.cuda.Stream(device=self.device)
+        return self.streams[t]
+
+
+def _acquire_ring(device, n_threads) -> _Ring:
+    """A free ring of the pool (a new one when every ring is in use: concurrent uploads never share staging buffers)."""
+    key = (str(device), n_threads)
+    with _rings_lock:
+        pool = _rings.setdefault(key, [])
+        for r in pool:
+            if not r.busy:
+                r.busy = True
+                return r
+        r = _Ring(device, n_threads)
+        r.busy = True
+        pool.append(r)
+        return r
+
+
+def _release_ring(ring) -> None:
+    with _rings_lock:
+        ring.busy = False
+
+
+class Pending:
+    """A host-to-device upload in flight.  :meth:`finish` joins the staging threads and makes the current stream of the
+    device wait for the copies; until then the destination must not be read."""
+
+    def __init__(self, device, threads=(), events=(), ring=None):
+        self.device, self.threads, self.events, self._ring = device, list(threads), list(events), ring
+        self.error = None
+        self._done = False
+
+    def finish(self):
+        if self._done:
+            return
+        for t in self.threads:
+            t.join()
+        if self._ring is not None:
+            _release_ring(self._ring)      # the buffers' events say when their last DMA is over
+            self._ring = None
+        self._done = True
+        if self.error is not None:
+            raise self.error
+        cur = torch.cuda.current_stream(self.device)
+        for ev in self.events:
+            if ev is not None:
+                cur.wait_event(ev)
+
+
+def h2d_2d(dst: torch.Tensor, src: np.ndarray, n_threads: int | None = None) -> Pending:
+    """Starts the copy of the 2-D host array ``src`` (any row stride, unit column stride) into the contiguous device
+    tensor ``dst`` of the same shape and dtype.  Returns at once; see :class:`Pending`."""
+    device = dst.device
+    n, b = src.shape
+    item = src.dtype.itemsize
+    assert dst.is_contiguous() and tuple(dst.shape) == (n, b) and dst.element_size() == item
+    if n == 0 or b == 0:
+        return Pending(device)
+    if src.strides[1] != item or src.strides[0] < 0:
+        src = np.ascontiguousarray(src)
+    cur = torch.cuda.current_stream(device)
+    if is_pinned(src):
+        copy2d_async(dst.data_ptr(), b * item, src.__array_interface__["data"][0], src.strides[0], b * item, n, "h2d", cur)
+        return Pending(device)
+    row_bytes = b * item
+    if n * row_bytes <= (4 << 20) or row_bytes > CHUNK_BYTES:   # small (or absurdly wide rows): the driver's own staged copy
+        dst.copy_(torch.from_numpy(np.ascontiguousarray(src)), non_blocking=True)
+        return Pending(device)
+    T = n_threads or stage_threads()
+    rows_per_chunk = max(1, CHUNK_BYTES // row_bytes)
+    n_chunks = -(-n // rows_per_chunk)
+    T = max(1, min(T, n_chunks))
+    ring = _acquire_ring(device, T)
+    counter = iter(range(n_chunks))
+    counter_lock = threading.Lock()
+    pending = Pending(device, ring=ring)
+    final_events = [None] * T
+    dst_bytes = dst.view(torch.uint8).view(n, row_bytes) if item != 1 else dst.view(n, row_bytes)
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    start_event = torch.cuda.Event()
+    start_event.record(cur)                   # the destination may still be in use by earlier work on this stream
+
+    def worker(t):
+        try:
+            bind_thread_to_device_node(dev_index)
+            with torch.cuda.device(device):
+                st = ring.stream(t)
+                st.wait_event(start_event)
+                k = 0
+                while True:
+                    with counter_lock:
+                        c = next(counter, None)
+                    if c is None:
+                        break
+                    r0 = c * rows_per_chunk
+                    r1 = min(n, r0 + rows_per_chunk)
+                    ev = ring.events[t][k]
+                    if ev is not None:
+                        ev.synchronize()          # the DMA out of this staging buffer has finished
+                    buf = ring.slot(t, k)
+                    view = buf[: (r1 - r0) * row_bytes]
+                    hv = view.numpy().view(src.dtype).reshape(r1 - r0, b)
+                    np.copyto(hv, src[r0:r1])     # GIL released inside; strided sources are gathered row by row
+                    with torch.cuda.stream(st):
+                        dst_bytes[r0:r1].copy_(view.view(r1 - r0, row_bytes), non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                    ring.events[t][k] = ev
+                    final_events[t] = ev
+                    k ^= 1
+        except BaseException as e:  # surfaced by finish()
+            pending.error = e
+
+    threads = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(T)]
+    pending.threads, pending.events = threads, final_events
+    for th in threads:
+        th.start()
+    return pending
+
+
+def h2d_1d(dst: torch.Tensor, src: np.ndarray, n_threads: int | None = None) -> Pending:
+    """1-D variant (the arrays of a sparse matrix)."""
+    src = np.ascontiguousarray(src).reshape(-1)
+    n = src.size
+    if n == 0:
+        return Pending(dst.device)
+    width = max(1, min(n, (CHUNK_BYTES // 4) // src.dtype.itemsize))
+    rows = n // width
+    if rows >= 1 and rows * width == n:
+        return h2d_2d(dst.view(rows, width), src.reshape(rows, width), n_threads)
+    # ragged tail: body as a 2-D copy, tail directly
+    body = rows * width
+    p = h2d_2d(dst[:body].view(rows, width), src[:body].reshape(rows, width), n_threads) if rows else Pending(dst.device)
+    dst[body:].copy_(torch.from_numpy(src[body:]), non_blocking=True)
+    return p
+
+
+def d2h_slab(host: torch.Tensor, dev_slab: torch.Tensor, gene_lb: int) -> None:
+    """Enqueues ``host[:, gene_lb:gene_lb + nb, :] = dev_slab`` (``host`` pinned ``[G, N, 3]`` float64, ``dev_slab``
+    contiguous ``[G, nb, 3]`` on a GPU) on the current stream of the slab's device: one strided device-to-host copy."""
+    G, N, three = host.shape
+    nb = dev_slab.shape[1]
+    assert three == 3 and dev_slab.shape[0] == G and dev_slab.is_contiguous() and host.is_contiguous()
+    if nb == 0:
+        return
+    cur = torch.cuda.current_stream(dev_slab.device)
+    copy2d_async(host.data_ptr() + gene_lb * 24, N * 24, dev_slab.data_ptr(), nb * 24, nb * 24, G, "d2h", cur)
+

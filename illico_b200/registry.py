@@ -90,8 +90,9 @@ class DataHandler(ABC):
 
 
 class InRAMDataHandler(DataHandler):
-    """Whole matrix is uploaded once; batches are column ranges of the resident copy
-    (reference ``InRAMDataHandler.fetch``, ``registry.py:97-100``)."""
+    """The matrix is in host (or device) memory; batches are column ranges of the resident copy
+    (reference ``InRAMDataHandler.fetch``, ``registry.py:97-100``).  ``upload_shard`` puts one GPU's gene shard in its
+    HBM: genes shard across GPUs with nothing exchanged between them."""
 
     _resident: DeviceMatrix | None = None
 
@@ -99,17 +100,21 @@ class InRAMDataHandler(DataHandler):
         return self.data, (lb, ub)
 
     def to_device(self, fetched, engine) -> DeviceMatrix:
-        """``engine`` may be an :class:`Engine` or just a device (the upload does not need the group plan,
-        so it can be started before the groups are encoded)."""
+        """Whole matrix on one device.  ``engine`` may be an :class:`Engine` or just a device."""
         if self._resident is None:
-            self._resident = self._upload(fetched, getattr(engine, "device", engine))
+            self._resident = self.upload_shard(0, self.data.shape[1], getattr(engine, "device", engine))[0]
         return self._resident
+
+    def upload_shard(self, lb: int, ub: int, device) -> tuple:
+        """``(DeviceMatrix, (lb', ub'))``: genes ``[lb, ub)`` on ``device`` and their bounds inside that matrix.
+        Returns as soon as the copies are started (``DeviceMatrix.ready()`` joins them)."""
+        raise NotImplementedError
 
 
 @data_handler_registry.register(np.ndarray)
 class DenseDataHandler(InRAMDataHandler):
-    def _upload(self, X, device):
-        return upload_dense(X, device)
+    def upload_shard(self, lb, ub, device):
+        return upload_dense(self.data, device, lb, ub), (0, ub - lb)
 
     def kernel_data_format(self):
         return KernelDataFormat.DENSE
@@ -120,8 +125,10 @@ class DenseDataHandler(InRAMDataHandler):
 
 @data_handler_registry.register(py_sparse.csr_matrix)
 class CSRDataHandler(InRAMDataHandler):
-    def _upload(self, X, device):
-        return upload_sparse(X, CSR, device)
+    def upload_shard(self, lb, ub, device):
+        # every CSR row holds all genes: the whole matrix goes to each GPU over its own link (1.9 GB at the K562 shape)
+        # and the kernels select the gene range
+        return upload_sparse(self.data, CSR, device), (lb, ub)
 
     def kernel_data_format(self):
         return KernelDataFormat.CSR
@@ -132,8 +139,8 @@ class CSRDataHandler(InRAMDataHandler):
 
 @data_handler_registry.register(py_sparse.csc_matrix)
 class CSCDataHandler(InRAMDataHandler):
-    def _upload(self, X, device):
-        return upload_sparse(X, CSC, device)
+    def upload_shard(self, lb, ub, device):
+        return upload_sparse(self.data, CSC, device, lb, ub), (0, ub - lb)
 
     def kernel_data_format(self):
         return KernelDataFormat.CSC
@@ -184,23 +191,29 @@ class TorchDenseDataHandler(InRAMDataHandler):
     """A 2-D ``torch.Tensor``: CUDA tensors are used where they are (no host round trip -- SURVEY section 8f.3), CPU
     tensors go through the ndarray path."""
 
-    def _upload(self, X, device):
+    def upload_shard(self, lb, ub, device):
         import torch
 
+        from .engine import _to_f32_or_wide
+
+        X = self.data
         if X.ndim != 2:
             raise ValueError("expression matrix must be two-dimensional")
-        if X.is_cuda:
-            from .engine import _to_f32_or_wide
-
-            want = torch.device(device)
-            if want.type == "cuda" and want.index is not None and X.device != want:
-                raise ValueError(f"expression tensor lives on {X.device} but the run was asked for {want}; move the tensor "
-                                 "or pass device=X.device (a kernel never reads another GPU's memory)")
+        if not X.is_cuda:
+            return upload_dense(X.numpy(), device, lb, ub), (0, ub - lb)
+        want = torch.device(device)
+        if want.type == "cuda" and want.index is None:
+            want = torch.device("cuda", torch.cuda.current_device())
+        if X.device == want:
             d, raw = (X, None) if X.dtype == torch.float32 else _to_f32_or_wide(X)
             if d is not None and d.stride(1) != 1:
                 d = d.contiguous()
-            return DeviceMatrix(DENSE, tuple(X.shape), d, raw=raw)
-        return upload_dense(X.numpy(), device)
+            return DeviceMatrix(DENSE, tuple(X.shape), d, raw=raw), (lb, ub)
+        # another GPU's shard of a device-resident matrix: peer copy of the columns (NVLink), never a remote read by a kernel
+        with torch.cuda.device(want):
+            shard = X[:, lb:ub].to(want, non_blocking=True).contiguous()
+        d, raw = (shard, None) if shard.dtype == torch.float32 else _to_f32_or_wide(shard)
+        return DeviceMatrix(DENSE, (X.shape[0], ub - lb), d, gene_offset=lb, raw=raw), (0, ub - lb)
 
     def kernel_data_format(self):
         return KernelDataFormat.DENSE
@@ -241,6 +254,13 @@ def _register_optional_backends() -> None:
         pass
 
 
+def _register_memmap() -> None:
+    from .backed import MemmapCSC, MemmapDense
+
+    data_handler_registry.register(MemmapDense)(BackedDenseDataHandler)
+    data_handler_registry.register(MemmapCSC)(BackedCSCDataHandler)
+
+
 def _register_torch() -> None:
     import torch
 
@@ -248,6 +268,7 @@ def _register_torch() -> None:
 
 
 _register_optional_backends()
+_register_memmap()
 _register_torch()
 
 from . import dispatch  # noqa: E402,F401  (registers the six GPU dispatchers)

@@ -119,6 +119,19 @@ int64_t illico_launch_count(void);
 /* with ILLICO_PROFILE=1 in the environment: duration (ms, CUDA events on the caller's stream) of the last
  * fused_pass_kernel launch of this thread, -1 if none (bench.py's roofline) */
 double illico_last_fused_ms(void);
+/* with ILLICO_PROFILE=1: every kernel this library launches is bracketed by CUDA events on the launching stream.  This
+ * call waits for the recorded launches, writes one line "kernel_name\ttotal_ms\tlaunches\n" per kernel (in first-launch
+ * order) into `out` (at most cap - 1 bytes + NUL), forgets them, and returns the full text length.  bench.py's roofline. */
+int64_t illico_profile_report(char* out, int64_t cap);
+
+/* ---- column shards in, result slabs out -------------------------------------------------------------
+ * Strided asynchronous copy (cudaMemcpy2DAsync) on `stream`: kind 1 = host to device, 2 = device to host.  The host side
+ * should be page-locked for the copy to be asynchronous.  This is how a GPU receives its gene shard X[:, lb:ub] of a
+ * C-order host matrix (height = n_cells rows of width_bytes = 4 (ub - lb), spitch = 4 n_genes) and how it delivers its
+ * slab results[:, lb:ub, :] into the one host array of the reference's layout (illico/asymptotic_wilcoxon.py:210,
+ * 241-244: the reference's threads write their batches into the same array). */
+int illico_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height,
+                          int kind, void* stream);
 
 /* ---- staging: input formats -> group-segmented non-zero lists ------------------------------- */
 
@@ -192,6 +205,21 @@ int illico_ovo_csc_f32(const float* data, const int32_t* indices, const int64_t*
                        int32_t n_genes_batch, const illico_plan_t* plan, const illico_flags_t* flags,
                        const illico_batch_buffers_t* buf, double* results, int64_t result_group_stride,
                        const illico_debug_t* dbg, void* stream);
+
+/* ---- next to the path and a test hook ------------------------------------------- */
+
+/* Benjamini-Hochberg adjusted p-values over the genes of each group (statsmodels multipletests(method="fdr_bh") /
+ * scanpy `pvals_adj`): p_values[g * group_stride + j * gene_stride] -> p_adj[g * n_genes + j].  Reads the p-value plane
+ * of the results array in place with group_stride = 3 * n_genes, gene_stride = 3. */
+size_t illico_bh_workspace_bytes(int32_t n_groups, int32_t n_genes);
+int illico_bh_adjust(const double* p_values, int64_t group_stride, int64_t gene_stride, int32_t n_groups, int32_t n_genes,
+                     double* p_adj, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The device epilogue's compute_pval (illico/utils/math.py:64-118) on arrays of arguments (device pointers): lets the
+ * known-answer vectors of the reference's primitive be checked against the GPU code itself. */
+int illico_compute_pval_batch(const int64_t* n_ref, const int64_t* n_tgt, const int64_t* n, const double* tie_sum,
+                              const double* U, const double* mu, const double* contin_corr, const int32_t* alternative,
+                              double* out, int64_t count, void* stream);
 
 #ifdef __cplusplus
 }

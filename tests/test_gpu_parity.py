@@ -622,7 +622,7 @@ def test_dispatcher_cache_sees_in_place_changes(fmt):
         Xf = C.to_format(Xd, fmt)
         return Xf if fmt == "dense" else dispatch.CSRMatrix(Xf.data, Xf.indices, Xf.indptr, Xf.shape)
 
-    Xf = host(X)
+    Xf = host(X.copy())
     first = fn(Xf, 0, 32, grpc, False, True, True, "two-sided")
     g, p, U, fc = oracle.run(X, labels, synth.CONTROL, is_log1p=False)
     ref_row = int(np.searchsorted(g, synth.CONTROL))
@@ -636,7 +636,7 @@ def test_dispatcher_cache_sees_in_place_changes(fmt):
     dispatch.clear_caches()
 
 
-def test_torch_tensor_on_another_device_is_refused():
+def test_torch_tensor_on_another_device_is_moved_not_read_remotely():
     import torch
 
     from illico_b200 import synth
@@ -645,6 +645,66 @@ def test_torch_tensor_on_another_device_is_refused():
     t = torch.from_numpy(X).cuda()
     groups, got = _run(t, labels, None, is_log1p=False)           # device defaults to the tensor's
     assert got[1].shape == (len(groups), 8)
-    if torch.cuda.device_count() > 1:
-        with pytest.raises(ValueError, match="lives on"):
-            _run(t, labels, None, is_log1p=False, device="cuda:1")
+    if torch.cuda.device_count() > 1:                             # the shard is peer-copied to the GPU that ranks it
+        _, other = _run(t, labels, None, is_log1p=False, device="cuda:1")
+        for a, b in zip(other, got):
+            np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("fmt", ["dense", "csr", "csc"])
+@pytest.mark.parametrize("test", ["ovo", "ovr"])
+def test_pageable_pinned_and_strided_uploads_agree(fmt, test):
+    """The three host-to-device routes of hostio (pinned 2-D copy, pageable input through the staging ring with several
+    worker threads and chunks, strided column shards) deliver the same matrix: results identical to the oracle's."""
+    import torch
+
+    from illico_b200 import hostio, synth
+
+    n, N = 70_000, 48                                             # 13 MB dense: above the direct-copy threshold
+    X, labels = synth.k562_like(seed=81, n_cells=n, n_genes=N, n_perts=12)
+    reference = synth.CONTROL if test == "ovo" else None
+    g, p, U, fc = oracle.run(X, labels, reference, is_log1p=False, n_threads=4)
+    ref_row = int(np.searchsorted(g, reference)) if reference is not None else None
+    old = hostio.CHUNK_BYTES
+    hostio.CHUNK_BYTES = 1 << 20                                  # many chunks per worker thread
+    try:
+        Xf = C.to_format(X, fmt)
+        _, got = _run(Xf, labels, reference, is_log1p=False)      # pageable: staged
+        assert_parity(got, (p, U, fc), ref_row=ref_row, what=f"pageable {fmt}")
+        if fmt == "dense":
+            pin = torch.from_numpy(X).pin_memory()
+            _, got = _run(pin.numpy(), labels, reference, is_log1p=False)
+            assert_parity(got, (p, U, fc), ref_row=ref_row, what="pinned dense")
+            wide = np.zeros((n, N + 16), dtype=np.float32)
+            wide[:, 8:8 + N] = X
+            _, got = _run(wide[:, 8:8 + N], labels, reference, is_log1p=False)   # strided pageable view
+            assert_parity(got, (p, U, fc), ref_row=ref_row, what="strided dense")
+            pw = torch.from_numpy(wide).pin_memory()
+            _, got = _run(pw.numpy()[:, 8:8 + N], labels, reference, is_log1p=False)   # strided pinned view: 2-D DMA
+            assert_parity(got, (p, U, fc), ref_row=ref_row, what="strided pinned dense")
+    finally:
+        hostio.CHUNK_BYTES = old
+
+
+@pytest.mark.parametrize("fmt", ["dense", "csr", "csc"])
+@pytest.mark.parametrize("test", ["ovo", "ovr"])
+def test_devices_argument_shards_genes(fmt, test):
+    """`devices=`: one host thread per GPU, contiguous gene shards, slabs delivered into one array -- identical to the
+    single-GPU call (with one GPU present the same device is used for a single shard; with more, for real)."""
+    import torch
+
+    from illico_b200 import asymptotic_wilcoxon, synth
+
+    X, labels = synth.k562_like(seed=82, n_cells=5000, n_genes=67, n_perts=9)
+    X[:, 11] = np.random.RandomState(2).poisson(25.0, X.shape[0])          # one gene for the general path
+    reference = synth.CONTROL if test == "ovo" else None
+    Xf = C.to_format(X, fmt)
+    _, want = _run(Xf, labels, reference, is_log1p=False)
+    n_dev = torch.cuda.device_count()
+    for devices in (["cuda:0"], "all", n_dev):
+        _, got = _run(Xf, labels, reference, is_log1p=False, devices=devices)
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+    with pytest.raises(ValueError):
+        asymptotic_wilcoxon(FakeAnnData(Xf, labels), is_log1p=False, group_keys="pert", reference=reference, device="cuda:0",
+                            devices="all")
