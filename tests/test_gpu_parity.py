@@ -708,3 +708,52 @@ def test_devices_argument_shards_genes(fmt, test):
     with pytest.raises(ValueError):
         asymptotic_wilcoxon(FakeAnnData(Xf, labels), is_log1p=False, group_keys="pert", reference=reference, device="cuda:0",
                             devices="all")
+
+
+def test_device_compute_pval_known_answers(golden_dir):
+    """the 1 300 known answers of the reference's `compute_pval` (illico/utils/math.py:64-118,
+    incl. huge z and the tie_corr cut-off) against the DEVICE epilogue code (epilogue.cuh), not only against the oracle."""
+    import torch
+
+    from illico_b200 import _lib
+
+    rows = np.load(os.path.join(golden_dir, "primitives.npz"))["pval_rows"]
+    n_ref, n_tgt = rows[:, 0].astype(np.int64), rows[:, 1].astype(np.int64)
+    alt_names = list(C.ALTERNATIVES)
+    alt = np.array([_lib.ALTERNATIVES[alt_names[int(a)]] for a in rows[:, 5]], dtype=np.int32)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    args = [t(n_ref), t(n_tgt), t(n_ref + n_tgt), t(rows[:, 2]), t(rows[:, 3]), t(n_ref * n_tgt / 2.0), t(rows[:, 4]), t(alt)]
+    out = torch.empty(rows.shape[0], dtype=torch.float64, device=dev)
+    lib = _lib.load()
+    rc = lib.illico_compute_pval_batch(*[a.data_ptr() for a in args], out.data_ptr(), rows.shape[0],
+                                       torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "illico_compute_pval_batch")
+    np.testing.assert_allclose(out.cpu().numpy(), rows[:, 6], rtol=1e-12, atol=2.3e-308)
+
+
+def test_optional_columns_p_adj_and_log2fc():
+    """Benjamini-Hochberg `p_adj` per group (statsmodels fdr_bh semantics, restated in numpy here) and
+    `log2_fold_change`; the default call returns the reference's three columns only."""
+    from illico_b200 import asymptotic_wilcoxon, synth
+
+    X, labels = synth.k562_like(seed=91, n_cells=4000, n_genes=700, n_perts=6)
+    X[:, :20] *= (np.asarray(labels) == "p0001")[:, None] * 3 + 1          # a few real effects
+    ad = FakeAnnData(X, labels)
+    base = asymptotic_wilcoxon(ad, is_log1p=False, group_keys="pert", reference=synth.CONTROL)
+    assert list(base.columns) == ["p_value", "statistic", "fold_change"]
+    df = asymptotic_wilcoxon(ad, is_log1p=False, group_keys="pert", reference=synth.CONTROL, p_adjust=True, log2_fold_change=True)
+    assert list(df.columns) == ["p_value", "statistic", "fold_change", "p_adj", "log2_fold_change"]
+    np.testing.assert_array_equal(df[["p_value", "statistic", "fold_change"]].to_numpy(), base.to_numpy())
+    G, N = len(set(labels)), X.shape[1]
+    p = df["p_value"].to_numpy().reshape(G, N)
+    want = np.empty_like(p)
+    for g in range(G):                                    # statsmodels.stats.multitest.multipletests(method="fdr_bh")
+        order = np.argsort(p[g], kind="stable")
+        raw = p[g][order] / (np.arange(1, N + 1) / float(N))
+        adj = np.minimum.accumulate(raw[::-1])[::-1]
+        adj[adj > 1] = 1
+        want[g, order] = adj
+    np.testing.assert_allclose(df["p_adj"].to_numpy().reshape(G, N), want, rtol=1e-15, atol=0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        np.testing.assert_array_equal(df["log2_fold_change"].to_numpy(), np.log2(df["fold_change"].to_numpy()))
