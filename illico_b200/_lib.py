@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libillico_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ALTERNATIVES = {"two-sided": 0, "less": 1, "greater": 2}
 TIES_DENSE, TIES_SPARSE = 0, 1
 
@@ -23,7 +23,7 @@ class Plan(C.Structure):
     _fields_ = [
         ("n_cells", _i32), ("n_groups", _i32), ("n_segments", _i32), ("ref_group", _i32),
         ("max_group_size", _i32), ("ref_group_size", _i32), ("ref_seg_begin", _i32), ("ref_seg_end", _i32),
-        ("slot_cap", _i32),
+        ("slot_cap", _i32), ("max_target_group_size", _i32),
         ("perm", _vp), ("cell_seg", _vp), ("seg_pos", _vp), ("seg_base", _vp), ("seg_group", _vp),
         ("group_seg", _vp), ("group_size", _vp),
     ]

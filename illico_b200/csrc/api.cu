@@ -76,7 +76,7 @@ int launch_ovo_csr_fused(const float*, const int32_t*, const long long*, int, in
                          const illico_batch_buffers_t*, double*, long long, const illico_debug_t*, cudaStream_t);
 int launch_ovr_csr_fused(const float*, const int32_t*, const long long*, int, int, const illico_plan_t*, const illico_flags_t*,
                          const illico_batch_buffers_t*, double*, long long, const illico_debug_t*, cudaStream_t);
-size_t ovo_fused_workspace_bytes(int);
+size_t ovo_fused_workspace_bytes(int, int);
 float ovo_fused_last_ms();
 size_t ovr_table_rec_bytes(const illico_plan_t*);
 
@@ -88,6 +88,7 @@ static int check_plan(const illico_plan_t* p) {
         return 1;
     }
     if (p->ref_group >= p->n_groups) { set_error("plan.ref_group out of range"); return 1; }
+    if (p->max_target_group_size < 0 || p->max_target_group_size > p->max_group_size) { set_error("plan.max_target_group_size out of range"); return 1; }
     if (p->ref_group >= 0 && (p->ref_seg_begin < 0 || p->ref_seg_end > p->n_segments || p->ref_seg_begin >= p->ref_seg_end)) {
         set_error("plan.ref_seg_* out of range");
         return 1;
@@ -207,7 +208,7 @@ size_t illico_rank_workspace_bytes(const illico_plan_t* plan, int32_t n_genes_ba
     if (plan->ref_group < 0) rank += 2 * ctas * ovr_table_rec_bytes(plan) + 256;  // table kernel: up to 8 CTAs per SM
     size_t stage = stage_csr_workspace_bytes(plan, n_genes_batch);  // CSR staging reuses the same scratch
     {                                                                // so do the fused paths' per-gene tables
-        const size_t fused = ovo_fused_workspace_bytes(n_genes_batch > 0 ? n_genes_batch : 1);
+        const size_t fused = ovo_fused_workspace_bytes(n_genes_batch > 0 ? n_genes_batch : 1, plan->n_groups);
         if (fused > stage) stage = fused;
     }
     return rank > stage ? rank : stage;

@@ -62,20 +62,25 @@ struct Gtab {
     uint32_t* wgt;             // [DCAP][bs]  OVO: 2 #{ref > v} + a; OVR: doubled mid-rank
     double* fval;              // [DCAP][bs]  f(value) for the fold change
     uint32_t* nnz;             // [bs]        OVO: control non-zeros; OVR: doubled mid-rank of the zero block
-    unsigned long long* tie;   // [bs]        OVO: sum over control runs of a^3 - a; OVR: f64 bits of the gene's tie sum
+    unsigned long long* tie;   // [bs]        OVO: sum over control runs of a^3 - a; OVR: f64 bits of the gene's tie correction
     double* sum;               // [bs]        OVO: sum of f(x) over the control; OVR: over all cells
     int* n_bad;                // [1]         genes flagged by the table kernel
     unsigned char* bad;        // [bs]        1 = the gene takes the general path
+    double* gc;                // [GC_N][Gs]  per-group constants of the p-value (fused_group_kernel)
+    int Gs;                    //             groups, padded to a multiple of 64
 };
+constexpr int GC_MU = 0, GC_NRNT = 1, GC_PROD12 = 2, GC_DENOM = 3, GC_INV_NT = 4, GC_N = 5;
 
-size_t gtab_bytes(int b) {
-    const size_t bs = (size_t)((b + 63) & ~63);
-    return bs * ((size_t)DCAP * 20 + 4 + 8 + 8 + 1) + 1024;
+size_t gtab_bytes(int b, int G) {
+    const size_t bs = (size_t)((b + 63) & ~63), Gs = (size_t)((G + 63) & ~63);
+    return bs * ((size_t)DCAP * 20 + 4 + 8 + 8 + 1) + Gs * 8 * GC_N + 1024;
 }
-Gtab gtab_carve(void* ws, int b) {
-    const size_t bs = (size_t)((b + 63) & ~63);
+Gtab gtab_carve(void* ws, int b, int G) {
+    const size_t bs = (size_t)((b + 63) & ~63), Gs = (size_t)((G + 63) & ~63);
     char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
     Gtab c;
+    c.Gs = (int)Gs;
+    c.gc = reinterpret_cast<double*>(p); p += Gs * 8 * GC_N;
     c.fval = reinterpret_cast<double*>(p); p += bs * 8 * DCAP;
     c.tie = reinterpret_cast<unsigned long long*>(p); p += bs * 8;
     c.sum = reinterpret_cast<double*>(p); p += bs * 8;
@@ -440,24 +445,55 @@ __global__ void __launch_bounds__(128) fused_gene_kernel(int b, const illico_pla
     }
     gt.nnz[j] = (uint32_t)(n0 + 1);                                              // doubled mid-rank of the zero block
     gt.sum[j] = total;
-    gt.tie[j] = (unsigned long long)__double_as_longlong(tie);
+    // the gene's tie correction, as compute_pval forms it (illico/utils/math.py:95): one division per gene, not per test
+    const double tie_corr = __dsub_rn(1.0, __ddiv_rn(fl.tie_correct ? tie : 0.0, (double)(n * (n - 1) * (n + 1))));
+    gt.tie[j] = (unsigned long long)__double_as_longlong(tie_corr);
     if (dbg_tie) dbg_tie[j] = tie;
     if (dbg_tie_exact) dbg_tie_exact[j] = (long long)(t_exact + zterm);
 }
 
-// ---- 3b. epilogue: 24-byte histogram -> (p, U, fold change), in place ---------------------------------------------------
+// ---- 3b. per-group constants of the p-value ------------------------------------------------------------------------
+// Everything in compute_pval (illico/utils/math.py:95-103) that depends on the group sizes only: evaluated once per group
+// with the reference's operations (int64 products, then float) instead of once per (group, gene).
+template <bool OVO>
+__global__ void __launch_bounds__(256) fused_group_kernel(const illico_plan_t pl, Gtab gt) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= pl.n_groups) return;
+    const long long n = pl.n_cells, n_t = pl.group_size[g];
+    const long long n_r = OVO ? (long long)pl.group_size[pl.ref_group] : n - n_t;
+    const long long nn = n_r + n_t;
+    gt.gc[GC_MU * gt.Gs + g] = (double)(n_r * n_t) / 2.0;
+    gt.gc[GC_NRNT * gt.Gs + g] = (double)(n_r * n_t);
+    gt.gc[GC_PROD12 * gt.Gs + g] = __ddiv_rn((double)(n_r * n_t * (n_r + n_t + 1)), 12.0);
+    gt.gc[GC_DENOM * gt.Gs + g] = (double)(nn * (nn - 1) * (nn + 1));
+    gt.gc[GC_INV_NT * gt.Gs + g] = 1.0 / (double)n_t;
+}
+
+// ---- 3c. epilogue: 24-byte histogram -> (p, U, fold change), in place ---------------------------------------------------
 // Thread = gene, looping over a slice of the groups: the gene's table (weights, multiplicities, f(value)) and scalars
 // stay in registers, so the unrolled 12-slot fold has no loads and no address arithmetic; records of adjacent genes
-// are adjacent, so every warp access is a contiguous 768-byte run.
+// are adjacent, so every warp access is a contiguous 768-byte run.  The fold change is a ratio of means compared at 1e-10:
+// its divisions by the group sizes are multiplications by precomputed reciprocals; everything that feeds the p-value
+// keeps the reference's IEEE operations.
 constexpr int EPI_GROUPS = 16;   // groups per thread
 template <bool OVO>
 __global__ void __launch_bounds__(256, 3) fused_epilogue_kernel(int b, const illico_plan_t pl, const illico_flags_t fl, Gtab gt,
                                                              int bs, double* __restrict__ results, long long gstride,
                                                              long long* dbg_u2, double* dbg_tie, long long* dbg_tie_exact) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= b || gt.bad[j]) return;
+    __shared__ double gcs[GC_N][EPI_GROUPS];
+    __shared__ int nts[EPI_GROUPS];
     const int G = pl.n_groups, ref = pl.ref_group;
     const int ga = blockIdx.y * EPI_GROUPS, gb = min(G, ga + EPI_GROUPS);
+    if (threadIdx.x < GC_N * EPI_GROUPS) {
+        const int c = threadIdx.x / EPI_GROUPS, k = threadIdx.x % EPI_GROUPS;
+        if (ga + k < gb) gcs[c][k] = gt.gc[c * gt.Gs + ga + k];
+    } else if (threadIdx.x < GC_N * EPI_GROUPS + EPI_GROUPS) {
+        const int k = threadIdx.x - GC_N * EPI_GROUPS;
+        if (ga + k < gb) nts[k] = pl.group_size[ga + k];
+    }
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= b || gt.bad[j]) return;
     uint32_t wgt[DCAP], mult[OVO ? DCAP : 1];
     double fval[DCAP];
 #pragma unroll
@@ -469,20 +505,23 @@ __global__ void __launch_bounds__(256, 3) fused_epilogue_kernel(int b, const ill
     const long long n = pl.n_cells;
     const double cc = fl.use_continuity ? 0.5 : 0.0;
     const long long g_nnz = gt.nnz[j];                       // OVO: control non-zeros; OVR: doubled mid-rank of the zero block
-    const unsigned long long g_tie = gt.tie[j];              // OVO: control tie term; OVR: f64 bits of the gene's tie sum
+    const unsigned long long g_tie = gt.tie[j];              // OVO: control tie term; OVR: f64 bits of the gene's tie correction
     const double g_sum = gt.sum[j];                          // OVO: control sum; OVR: whole-gene sum
     const long long n_ref = OVO ? (long long)pl.group_size[ref] : 0;
+    const double ovr_tie_corr = __longlong_as_double((long long)g_tie);
+    // OVO: the control's mean is a per-gene constant
+    const double ovo_rsum = OVO ? (fl.group_sums ? fl.group_sums[(long long)ref * b + j] : g_sum) : 0.0;
+    const double ovo_mean_r = OVO ? ovo_rsum / (double)n_ref : 0.0;
+    const double ovo_inv_mean_r = 1.0 / ovo_mean_r;
     for (int g = ga; g < gb; ++g) {
-        const long long n_t = pl.group_size[g];
+        const int k = g - ga;
+        const long long n_t = nts[k];
         const long long n_r = OVO ? n_ref : n - n_t;         // the sample U is reported for
-        const double mu = (double)(n_r * n_t) / 2.0;
         double* o = results + (long long)g * gstride + (long long)j * 3;
         const long long di = (long long)g * b + j;
         if (OVO && g == ref) {
             // control row: (1, -1, fold change of the control against itself), as ovo_kernel writes it
-            const double rsum = fl.group_sums ? fl.group_sums[(long long)ref * b + j] : g_sum;
-            const double mean_r = rsum / (double)n_r;
-            o[0] = 1.0; o[1] = -1.0; o[2] = (mean_r == 0.0) ? INFINITY : mean_r / mean_r;
+            o[0] = 1.0; o[1] = -1.0; o[2] = (ovo_mean_r == 0.0) ? INFINITY : ovo_mean_r / ovo_mean_r;
             if (dbg_u2) dbg_u2[di] = -2;
             if (dbg_tie) dbg_tie[di] = 0.0;
             if (dbg_tie_exact) dbg_tie_exact[di] = 0;
@@ -511,29 +550,27 @@ __global__ void __launch_bounds__(256, 3) fused_epilogue_kernel(int b, const ill
         if (OVO) {
             const long long zeros_r = n_r - g_nnz;           // every control value is positive
             if (fl.group_sums) sum = fl.group_sums[(long long)g * b + j];
-            const double rsum = fl.group_sums ? fl.group_sums[(long long)ref * b + j] : g_sum;
             const long long Z = zeros_r + z_t;
             const unsigned long long u2 = acc + (unsigned long long)(z_t * (2ll * g_nnz + zeros_r));
             const unsigned long long tie_exact = g_tie + tie_nz + (unsigned long long)cube_minus(Z);
             const double tie = (double)tie_exact;            // < 2^53: pairs of at most 208 063 cells
-            U = (double)u2 / 2.0;
-            p = compute_pval(n_r, n_t, n_r + n_t, fl.tie_correct ? tie : 0.0, U, mu, cc, fl.alternative);
-            const double mean_t = sum / (double)n_t, mean_r = rsum / (double)n_r;
-            fc = (mean_r == 0.0) ? INFINITY : mean_t / mean_r;
+            U = (double)u2 * 0.5;
+            const double tie_corr = __dsub_rn(1.0, __ddiv_rn(fl.tie_correct ? tie : 0.0, gcs[GC_DENOM][k]));
+            p = pval_core(gcs[GC_NRNT][k], gcs[GC_MU][k], gcs[GC_PROD12][k], tie_corr, U, cc, fl.alternative);
+            fc = (ovo_mean_r == 0.0) ? INFINITY : (sum * gcs[GC_INV_NT][k]) * ovo_inv_mean_r;
             if (dbg_u2) dbg_u2[di] = (long long)u2;
             if (dbg_tie) dbg_tie[di] = tie;
             if (dbg_tie_exact) dbg_tie_exact[di] = (long long)tie_exact;
         } else {
             const unsigned long long R2 = acc + (unsigned long long)z_t * (unsigned long long)g_nnz;
             const long long u2 = 2 * n_r * n_t + n_t * (n_t + 1) - (long long)R2;
-            const double tie = __longlong_as_double((long long)g_tie);
-            U = (double)u2 / 2.0;
-            p = compute_pval(n_r, n_t, n, fl.tie_correct ? tie : 0.0, U, mu, cc, fl.alternative);
+            U = (double)u2 * 0.5;
+            p = pval_core(gcs[GC_NRNT][k], gcs[GC_MU][k], gcs[GC_PROD12][k], ovr_tie_corr, U, cc, fl.alternative);
             // rest-of-cells mean: exactly zero when this group holds every non-zero of the gene (the reference's total is
             // the sum of the per-group sums, so its `total - sum` is an exact 0 there; a total accumulated in another
             // order could leave an ulp and turn the +inf fold change into 1e16)
             const bool all_here = (long long)m == n - (g_nnz - 1);
-            const double mu_t = sum / (double)n_t, mu_r = all_here ? 0.0 : (g_sum - sum) / (double)(n - n_t);
+            const double mu_t = sum * gcs[GC_INV_NT][k], mu_r = all_here ? 0.0 : (g_sum - sum) / (double)(n - n_t);
             fc = (mu_r == 0.0) ? INFINITY : mu_t / mu_r;
             if (dbg_u2) dbg_u2[di] = u2;
         }
@@ -814,12 +851,13 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
               cudaStream_t stream) {
     if (env_int(OVO ? "ILLICO_OVO_FUSED" : "ILLICO_OVR_FUSED", 1) == 0 || b <= 0) return -1;
     if (!stage_dense_tma_ok(X, ld, gene_lb, b, plan)) return -1;
-    if (plan->max_group_size >= 65536 || plan->n_groups < 2 || plan->n_groups > 65535) return -1;   // u16 counters, grid.y
-    if (OVO && (long long)plan->ref_group_size + plan->max_group_size > PAIR_MAX) return -1;        // tie sums below 2^53
+    // u16 counters hold the groups that are ranked (the control's rows are skipped; its histogram is the u32 table)
+    if (plan->max_target_group_size >= 65536 || plan->n_groups < 2 || plan->n_groups > 65535) return -1;   // + grid.y
+    if (OVO && (long long)plan->ref_group_size + plan->max_target_group_size > PAIR_MAX) return -1;  // tie sums below 2^53
     if (!OVO && flags->group_sums) return -1;
-    if (buf->workspace_bytes < gtab_bytes(b)) return -1;
+    if (buf->workspace_bytes < gtab_bytes(b, plan->n_groups)) return -1;
     const int bs = (b + 63) & ~63;
-    Gtab gt = gtab_carve(buf->workspace, b);
+    Gtab gt = gtab_carve(buf->workspace, b, plan->n_groups);
 
     // 1. table segments: the control group (OVO) or a sample of about 16k cells (OVR: the first segments)
     int seg_lo = plan->ref_seg_begin, seg_hi = plan->ref_seg_end;
@@ -876,6 +914,7 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
     if (timed) ILLICO_CUDA_OK(cudaEventRecord(e1, stream));
 
     // 3. per-gene weights, then the epilogue
+    ILLICO_LAUNCH("fused_group_kernel", stream, fused_group_kernel<OVO><<<(plan->n_groups + 255) / 256, 256, 0, stream>>>(*plan, gt));
     ILLICO_LAUNCH("fused_gene_kernel", stream, fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, (dbg && !OVO) ? dbg->tie_sum : nullptr,
                                                                 (dbg && !OVO) ? (long long*)dbg->tie_exact : nullptr));
     ILLICO_CUDA_OK(cudaGetLastError());
@@ -940,7 +979,7 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
 
 float ovo_fused_last_ms() { return g_last_fused_ms; }
 
-size_t ovo_fused_workspace_bytes(int b) { return gtab_bytes(b); }
+size_t ovo_fused_workspace_bytes(int b, int n_groups) { return gtab_bytes(b, n_groups); }
 
 int launch_ovo_dense_fused(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan,
                            const illico_flags_t* flags, const illico_batch_buffers_t* buf, double* results, long long gstride,
@@ -966,12 +1005,12 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
                   const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf, double* results,
                   long long gstride, const illico_debug_t* dbg, cudaStream_t stream) {
     if (env_int(OVO ? "ILLICO_OVO_FUSED" : "ILLICO_OVR_FUSED", 1) == 0 || env_int("ILLICO_CSR_FUSED", 1) == 0 || b <= 0) return -1;
-    if (plan->max_group_size >= 65536 || plan->n_groups < 2 || plan->n_groups > 65535 || plan->n_segments > 65535) return -1;
-    if (OVO && (long long)plan->ref_group_size + plan->max_group_size > PAIR_MAX) return -1;
+    if (plan->max_target_group_size >= 65536 || plan->n_groups < 2 || plan->n_groups > 65535 || plan->n_segments > 65535) return -1;
+    if (OVO && (long long)plan->ref_group_size + plan->max_target_group_size > PAIR_MAX) return -1;
     if (!OVO && flags->group_sums) return -1;
-    if (buf->workspace_bytes < gtab_bytes(b)) return -1;
+    if (buf->workspace_bytes < gtab_bytes(b, plan->n_groups)) return -1;
     const int bs = (b + 63) & ~63;
-    Gtab gt = gtab_carve(buf->workspace, b);
+    Gtab gt = gtab_carve(buf->workspace, b, plan->n_groups);
     unsigned long long* rec = reinterpret_cast<unsigned long long*>(results);
     const int G = plan->n_groups;
 
@@ -1017,6 +1056,7 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
         ILLICO_LAUNCH("fused_hist_sum_kernel", stream, fused_hist_sum_kernel<<<dim3((unsigned)((b + 255) / 256), (unsigned)((G + gpb - 1) / gpb)), 256, 0, stream>>>(b, G, gpb, gt, bs, rec,
                                                                                                                  gstride));
     }
+    ILLICO_LAUNCH("fused_group_kernel", stream, fused_group_kernel<OVO><<<(plan->n_groups + 255) / 256, 256, 0, stream>>>(*plan, gt));
     ILLICO_LAUNCH("fused_gene_kernel", stream, fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, (dbg && !OVO) ? dbg->tie_sum : nullptr,
                                                                 (dbg && !OVO) ? (long long*)dbg->tie_exact : nullptr));
     {

@@ -81,7 +81,7 @@ class Engine:
         self.plan = _lib.Plan(
             n_cells=hp.n_cells, n_groups=hp.n_groups, n_segments=hp.n_segments, ref_group=hp.ref_group,
             max_group_size=hp.max_group_size, ref_group_size=hp.ref_group_size, ref_seg_begin=hp.ref_seg_begin,
-            ref_seg_end=hp.ref_seg_end, slot_cap=hp.slot_cap,
+            ref_seg_end=hp.ref_seg_end, slot_cap=hp.slot_cap, max_target_group_size=hp.max_target_group_size,
             **{k: self._tables[k].data_ptr() for k in HostPlan.TABLES})
         self._buf_genes = 0
         self._ir_vals = self._ir_cnt = self._ws = None

@@ -137,6 +137,8 @@ class HostPlan:
         self.n_segments = S
         self.max_group_size = int(counts.max())
         self.ref_group_size = int(counts[self.ref_group]) if self.ref_group >= 0 else 0
+        others = np.delete(counts, self.ref_group) if self.ref_group >= 0 else counts
+        self.max_target_group_size = int(others.max()) if others.size else 0
         self.slot_cap = int(seg_base[-1])
         self.ref_seg_begin = int(group_seg[self.ref_group]) if self.ref_group >= 0 else 0
         self.ref_seg_end = int(group_seg[self.ref_group + 1]) if self.ref_group >= 0 else 0

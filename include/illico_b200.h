@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define ILLICO_ABI_VERSION 1
+#define ILLICO_ABI_VERSION 2
 
 enum illico_alternative { ILLICO_TWO_SIDED = 0, ILLICO_LESS = 1, ILLICO_GREATER = 2 };
 
@@ -83,6 +83,7 @@ typedef struct illico_plan {
     int32_t ref_seg_begin;      /* segments [ref_seg_begin, ref_seg_end) belong to the reference group */
     int32_t ref_seg_end;
     int32_t slot_cap;           /* floats per gene in ir_vals (= seg_base[n_segments]) */
+    int32_t max_target_group_size; /* largest group other than the reference group (= max_group_size without one) */
     const int32_t* perm;        /* [n_cells]     perm[pos] = cell (row) index, groups contiguous, stable */
     const int32_t* cell_seg;    /* [n_cells]     segment of each cell (row -> segment) */
     const int32_t* seg_pos;     /* [n_segments+1] positions (into perm) covered by each segment */

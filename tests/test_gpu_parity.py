@@ -344,8 +344,11 @@ def test_dense_staging_tma_and_plain_paths_agree(monkeypatch, n_genes, batch, te
     groups, tma = _run(X, labels, ref, is_log1p=False, batch_size=batch)
     monkeypatch.setenv("ILLICO_STAGE_TMA", "0")
     _, plain = _run(X, labels, ref, is_log1p=False, batch_size=batch)
-    for a, b in zip(tma, plain):
-        np.testing.assert_array_equal(a, b)
+    # p and U bit for bit; the fold change to rounding (the fused path, which only TMA-capable batches take, multiplies
+    # by reciprocals of the group sizes where the general path divides)
+    np.testing.assert_array_equal(tma[0], plain[0])
+    np.testing.assert_array_equal(tma[1], plain[1])
+    np.testing.assert_allclose(tma[2], plain[2], rtol=1e-14, atol=0)
     g, p, U, fc = oracle.run(X, labels, ref, is_log1p=False)
     ref_row = int(np.searchsorted(groups, ref)) if ref is not None else None
     assert_parity(tma, (p, U, fc), ref_row=ref_row, what=f"tma staging {n_genes}/{batch}/{test}")
