@@ -12,10 +12,18 @@
 // pair (zeros are never stored: they are one analytic tie block, for dense input too).  Everything is
 // exact integer arithmetic; the f64 epilogue follows illico/utils/math.py:95-118 operation by operation.
 //
-// One CTA per gene (persistent, grid-strided).  Perturbations are processed in three tiers by their
-// number of non-zeros m:  m <= small_cap  one THREAD per group (insertion sort in a private shared
-// column), m <= WARP_CAP one WARP per group (bitonic sort in shared memory), larger groups one at a time
-// by the whole CTA (radix sort in the CTA's global slab).
+// One CTA per gene (persistent; genes are handed out by an atomic counter, so that a few expensive genes do not
+// leave their CTAs behind).  Per gene, in order of preference:
+//   table path   the control has at most DT_CAP distinct values (raw counts, also dense high-count genes): one THREAD
+//                per group, private histogram over the control's values (two 16-bit bins per shared-memory word), no
+//                sort, no search;
+//   stream tier  any other gene, groups of at most STREAM_MAX non-zeros: one THREAD per group streams its values once:
+//                each is ranked against the control by one binary search and contributes 2 #{ref > v} + a and the tie
+//                term 3 a (a + 1) on the spot (a = its multiplicity in the control).  That is only exact while the
+//                group's own values are pairwise different, which a private 32-slot key hash checks; a group with a
+//                repeated value is redone by the warp tier;
+//   warp tier    one WARP per group (bitonic sort in shared memory, runs, binary searches), up to WARP_CAP non-zeros;
+//   block tier   larger groups one at a time by the whole CTA (radix sort in the CTA's global slab).
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "sort.cuh"
@@ -24,12 +32,16 @@
 
 namespace illico {
 
-constexpr int WARP_CAP = 1024;   // keys per warp buffer in the warp tier
+constexpr int WARP_CAP = 1024;     // keys per warp buffer in the warp tier
 constexpr int GROUP_CHUNK = 2048;  // groups handled per sweep (bounds the deferred lists)
-constexpr int DT_CAP = 22;         // distinct control values for the table fast path (<= small_cap)
-constexpr int DT_HASH = 64;        // slots of the key -> table-index hash (load factor <= 1/3)
-constexpr int ST_CAP = 1024;      // distinct control values kept in the shared-memory search table
-constexpr int FAST_MAX = 96;       // largest group (non-zeros) a single thread streams through the table path
+constexpr int DT_CAP = 64;         // distinct control values for the table path
+constexpr int DT_HASH = 256;       // slots of the value -> table-index hash (load factor <= 1/4)
+constexpr int NE_CAP = 4;          // table path: distinct values of a group that the control does not have
+constexpr int ST_CAP = 1024;       // distinct control values kept in the shared-memory search table
+constexpr int STREAM_MAX = 28;     // stream tier: most non-zeros per group (32-slot duplicate hash)
+constexpr int STREAM_SLOTS = 32;
+constexpr int REF_CAP = 1536;      // control keys sorted in shared memory (larger controls: the CTA's global slab)
+constexpr int GCN = 5;             // per-group constants of the p-value (see ovo_group_consts_kernel)
 
 struct OvoParams {
     const float* ir_vals;
@@ -41,10 +53,12 @@ struct OvoParams {
     long long gstride;
     uint32_t* slab;          // global scratch, slab_words per CTA
     long long slab_words;
-    int ref_cap;             // capacity (keys) of each of the two control buffers
-    int small_cap;           // thread-tier capacity (keys per thread)
     int scratch_words;       // shared scratch (control ping-pong partner, later the tier buffers)
-    int use_search_table;    // ILLICO_OVO_SEARCH_TABLE
+    int* gene_counter;       // next gene to hand out (zeroed before the launch)
+    const int* n_genes_dev;  // optional: number of genes decided on the device (a hand-back list), else n_genes
+    const int* gene_map;     // optional: results of gene j go to column gene_map[j] (compacted hand-back)
+    const double* gc;        // [GCN][Gs] per-group constants (ovo_group_consts_kernel)
+    int Gs;
     long long* dbg_u2;
     double* dbg_tie;
     long long* dbg_tie_exact;
@@ -54,23 +68,28 @@ struct RefInfo {
     const uint32_t* keys;  // sorted non-zero control keys
     int nnz;               // how many
     int npos;              // control values > 0
-    long long zeros;       // control zeros
+    int zeros;             // control zeros
     long long n_ref;
     unsigned long long tie;  // sum over control non-zero runs of a^3 - a
     double sum;              // sum of f(x) over the control
-    // search table (optional, st_n >= 0): the control's distinct keys ascending and the position of each one's first
+    double mean;             // sum / n_ref
+    double inv_mean;
+    // search table (st_n >= 0): the control's distinct keys ascending and the position of each one's first
     // occurrence in `keys` (st_lo[st_n] = nnz).  A rank then costs a binary search over <= 1024 shared-memory entries
-    // instead of one over the whole sorted control, which lives in the CTA's global slab when it is large: measured
-    // 25 ms per dense high-count gene without it (every probe a dependent L2 load).
+    // instead of one over the whole sorted control, which lives in the CTA's global slab when it is large.
     const uint32_t* st_key;
     const int* st_lo;
     int st_n;
 };
 
-// contribution of one distinct perturbation value (key, multiplicity b)
-__device__ __forceinline__ void rank_value(const RefInfo& R, uint32_t key, long long b, unsigned long long& u2,
-                                           unsigned long long& tie) {
-    int lo, hi;
+template <bool LOG1P>
+__device__ __forceinline__ double fc_val(float v) {
+    if (LOG1P) return expm1((double)v);
+    return (double)v;
+}
+
+// position of `key` in the sorted control: [lo, hi) = its run (empty when the control does not have the value)
+__device__ __forceinline__ void rank_pos(const RefInfo& R, uint32_t key, int& lo, int& hi) {
     if (R.st_n >= 0) {
         const int t = lower_bound_u32(R.st_key, R.st_n, key);
         lo = R.st_lo[t];
@@ -80,11 +99,18 @@ __device__ __forceinline__ void rank_value(const RefInfo& R, uint32_t key, long 
         hi = lo;
         if (lo < R.nnz && R.keys[lo] == key) hi = upper_bound_u32(R.keys, R.nnz, key);
     }
-    long long a = hi - lo;
-    long long gt = (long long)(R.nnz - hi) + ((key < KEY_ZERO) ? R.zeros : 0);
-    u2 += (unsigned long long)(b * (2 * gt + a));
-    long long t = a + b;
-    tie += (unsigned long long)(cube_minus(t) - cube_minus(a));
+}
+
+// contribution of one distinct perturbation value (key, multiplicity b)
+__device__ __forceinline__ void rank_value(const RefInfo& R, uint32_t key, uint32_t b, unsigned long long& u2,
+                                           unsigned long long& tie) {
+    int lo, hi;
+    rank_pos(R, key, lo, hi);
+    const uint32_t a = (uint32_t)(hi - lo);
+    const uint32_t gt = (uint32_t)(R.nnz - hi) + ((key < KEY_ZERO) ? (uint32_t)R.zeros : 0u);
+    u2 += (unsigned long long)b * (unsigned long long)(2u * gt + a);             // 2 gt + a <= 2 n_ref < 2^32
+    // (a+b)^3 - (a+b) - (a^3 - a) = b (3 a (a + b) + b^2 - 1)
+    if (a | (b - 1u)) tie += (unsigned long long)b * (3ull * a * ((unsigned long long)a + b) + (unsigned long long)b * b - 1ull);
 }
 
 // The reference's sequential f64 tie accumulation for ONE pair (illico/utils/ranking.py:52-158 for the dense
@@ -119,7 +145,7 @@ __device__ __forceinline__ void finalize_group(const OvoParams& P, const RefInfo
     const long long n_t = P.plan.group_size[g];
     const long long z_t = n_t - m;
     if (P.flags.group_sums) sum = P.flags.group_sums[(long long)g * P.n_genes + j];
-    const long long Z = R.zeros + z_t;
+    const long long Z = (long long)R.zeros + z_t;
     u2 += (unsigned long long)(z_t * (2ll * R.npos + R.zeros));
     const unsigned long long tie_exact = R.tie + tie_nz + (unsigned long long)cube_minus(Z);
     // Every partial sum of the reference's sequential f64 accumulation is an exact integer while the
@@ -128,15 +154,15 @@ __device__ __forceinline__ void finalize_group(const OvoParams& P, const RefInfo
     double tie = (double)tie_exact;
     if (tie >= TWO53 && gkeys != nullptr)
         tie = ordered_pair_tie(R.keys, R.nnz, gkeys, gstride, (int)m, Z, P.flags.tie_order == ILLICO_TIES_SPARSE);
-    const double U = (double)u2 / 2.0;
-    const double mu = (double)(R.n_ref * n_t) / 2.0;
+    const double U = (double)u2 * 0.5;
     const double cc = P.flags.use_continuity ? 0.5 : 0.0;
-    const double p = compute_pval(R.n_ref, n_t, R.n_ref + n_t, P.flags.tie_correct ? tie : 0.0, U, mu, cc,
-                                  P.flags.alternative);
-    const double mean_t = sum / (double)n_t;
-    const double mean_r = R.sum / (double)R.n_ref;
-    const double fc = (mean_r == 0.0) ? INFINITY : mean_t / mean_r;
-    double* o = P.results + (long long)g * P.gstride + (long long)j * 3;
+    // per-group constants of compute_pval (illico/utils/math.py:95-103) from the table: same operations, once per group
+    const double* gc = P.gc + g;
+    const double tie_corr = __dsub_rn(1.0, __ddiv_rn(P.flags.tie_correct ? tie : 0.0, gc[3 * P.Gs]));
+    const double p = pval_core(gc[1 * P.Gs], gc[0], gc[2 * P.Gs], tie_corr, U, cc, P.flags.alternative);
+    const double fc = (R.mean == 0.0) ? INFINITY : (sum * gc[4 * P.Gs]) * R.inv_mean;
+    const int jo = P.gene_map ? P.gene_map[j] : j;
+    double* o = P.results + (long long)g * P.gstride + (long long)jo * 3;
     o[0] = p; o[1] = U; o[2] = fc;
     const long long di = (long long)g * P.n_genes + j;
     if (P.dbg_u2) P.dbg_u2[di] = (long long)u2;
@@ -144,8 +170,22 @@ __device__ __forceinline__ void finalize_group(const OvoParams& P, const RefInfo
     if (P.dbg_tie_exact) P.dbg_tie_exact[di] = (long long)tie_exact;
 }
 
-template <int OVO_THREADS, int MIN_CTAS>
+// Everything in compute_pval that depends on the group sizes only: [0] mu = n_r n_t / 2, [1] float(n_r n_t),
+// [2] float(n_r n_t (n_r + n_t + 1)) / 12, [3] float(n (n-1) (n+1)) with n = n_r + n_t, [4] 1 / n_t.
+__global__ void __launch_bounds__(256) ovo_group_consts_kernel(const illico_plan_t pl, double* gc, int Gs) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= pl.n_groups) return;
+    const long long n_t = pl.group_size[g], n_r = pl.group_size[pl.ref_group], nn = n_r + n_t;
+    gc[0 * Gs + g] = (double)(n_r * n_t) / 2.0;
+    gc[1 * Gs + g] = (double)(n_r * n_t);
+    gc[2 * Gs + g] = __ddiv_rn((double)(n_r * n_t * (n_r + n_t + 1)), 12.0);
+    gc[3 * Gs + g] = (double)(nn * (nn - 1) * (nn + 1));
+    gc[4 * Gs + g] = 1.0 / (double)n_t;
+}
+
+template <int OVO_THREADS, int MIN_CTAS, bool LOG1P>
 __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoParams P) {
+    constexpr int NT = OVO_THREADS;
     constexpr int OVO_NW = OVO_THREADS / 32;
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -153,22 +193,18 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
     const int S = pl.n_segments, G = pl.n_groups, ref = pl.ref_group;
 
     // ---- shared carve-up
-    uint32_t* refA = smem;                                  // [ref_cap]
-    uint32_t* scratch = refA + P.ref_cap;                   // [scratch_words] (>= ref_cap)
+    uint32_t* refA = smem;                                  // [REF_CAP]
+    uint32_t* scratch = refA + REF_CAP;                     // [scratch_words] (>= REF_CAP)
     uint32_t* hist = scratch + P.scratch_words;             // [OVO_NW * 256]
     uint32_t* aux = hist + OVO_NW * 256;                    // [RADIX_AUX_WORDS]
     uint16_t* mlist = (uint16_t*)(aux + RADIX_AUX_WORDS);   // [GROUP_CHUNK] group index inside the chunk
     uint16_t* blist = mlist + GROUP_CHUNK;                  // [GROUP_CHUNK]
-    int* counters = (int*)(blist + GROUP_CHUNK);            // [8] three rotating {medium, big} list counters + table counter
+    int* counters = (int*)(blist + GROUP_CHUNK);            // [8] three rotating {medium, big} list counters, [7] next gene
     double* redd = (double*)(counters + 8);                 // [32]
     unsigned long long* redu = (unsigned long long*)(redd + 32);  // [32]
     double* dval = (double*)(redu + 32);                    // [DT_CAP]   f(x) of each distinct control value
-    unsigned long long* dw = (unsigned long long*)(dval + DT_CAP);  // [DT_CAP] 2 #{ref > v} + a
-    unsigned long long* dA3 = dw + DT_CAP;                  // [DT_CAP]   3 a^2 - 1
-    uint2* hkv = (uint2*)(dA3 + DT_CAP);                    // [DT_HASH]  open-addressed {float bits, byte offset of the bin}
-    uint32_t* dkey = (uint32_t*)(hkv + DT_HASH);            // [DT_CAP]   distinct control keys, ascending
-    int* dlo = (int*)(dkey + DT_CAP);                       // [DT_CAP+1] first position of each in the sorted control
-    uint32_t* st_key = (uint32_t*)(dlo + DT_CAP + 1);       // [ST_CAP]   search table: distinct control keys, ascending
+    uint2* hkv = (uint2*)(dval + DT_CAP);                   // [DT_HASH]  open-addressed {float bits, table index}
+    uint32_t* st_key = (uint32_t*)(hkv + DT_HASH);          // [ST_CAP]   search table: distinct control keys, ascending
     int* st_lo = (int*)(st_key + ST_CAP);                   // [ST_CAP+1] first position of each
 
     uint32_t* slab = P.slab + (long long)blockIdx.x * P.slab_words;
@@ -181,9 +217,15 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
     if (tid < 8) counters[tid] = 0;
     if (tid < 3) mmax3[tid] = 0;
     int cc = 0;  // chunk counter: chunk c uses counter set c % 3 and clears set (c + 1) % 3 for the next chunk
+    const int n_genes = P.n_genes_dev ? *P.n_genes_dev : P.n_genes;
+    const uint32_t hkv_s = (uint32_t)__cvta_generic_to_shared(hkv);
     __syncthreads();
 
-    for (int j = blockIdx.x; j < P.n_genes; j += gridDim.x) {
+    for (;;) {
+        if (tid == 0) counters[7] = atomicAdd(P.gene_counter, 1);
+        __syncthreads();
+        const int j = counters[7];
+        if (j >= n_genes) break;
         const uint32_t* cnt = P.ir_cnt + (long long)j * S;
         const float* vals = P.ir_vals + (long long)j * pl.slot_cap;
 
@@ -197,7 +239,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
         __syncthreads();
         const int nref_nz = (int)hist[ref_s1 - ref_s0];
         // control keys live in shared memory when they fit, else in this CTA's global slab
-        const bool ref_smem = nref_nz <= P.ref_cap;
+        const bool ref_smem = nref_nz <= REF_CAP;
         uint32_t* rA = ref_smem ? refA : slab + 2ll * maxg;
         uint32_t* rB = ref_smem ? scratch : slab + 3ll * maxg;
         double rsum = 0.0;
@@ -208,7 +250,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
             for (int i = lane; i < c; i += 32) {
                 float v = src[i];
                 rA[off + i] = f2key(v);
-                rsum += fc_value(v, P.flags.is_log1p);
+                rsum += fc_val<LOG1P>(v);
             }
         }
         __syncthreads();
@@ -222,37 +264,18 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
         R.keys = rA;
         R.nnz = nref_nz;
         R.n_ref = pl.group_size[ref];
-        R.zeros = R.n_ref - nref_nz;
+        R.zeros = (int)(R.n_ref - nref_nz);
         R.npos = nref_nz - upper_bound_u32(rA, nref_nz, KEY_ZERO);
         R.sum = P.flags.group_sums ? P.flags.group_sums[(long long)ref * P.n_genes + j] : rsum;
-        {
-            unsigned long long t = 0;
-            for (int i = tid; i < nref_nz; i += OVO_THREADS) {
-                uint32_t k = rA[i];
-                if (i == 0 || rA[i - 1] != k) {
-                    long long a = upper_bound_u32(rA, nref_nz, k) - i;
-                    t += (unsigned long long)cube_minus(a);
-                }
-            }
-            R.tie = block_sum<unsigned long long>(t, redu);
-        }
-        // ---- distinct-value table of the control (raw counts have a handful of distinct values): groups whose
-        // values all occur in it are ranked by a private histogram over the table, without sorting or searching
-        if (tid == 0) counters[6] = 0;
-        __syncthreads();
-        for (int i = tid; i < nref_nz; i += OVO_THREADS) {
-            const uint32_t k = rA[i];
-            if (i == 0 || rA[i - 1] != k) {
-                const int slot = atomicAdd(&counters[6], 1);
-                if (slot < DT_CAP) { dkey[slot] = k; dlo[slot] = i; }
-            }
-        }
-        __syncthreads();
-        const int D = counters[6];
-        const bool table = D <= DT_CAP;
-        // ---- search table for controls with more distinct values than the histogram path takes (D counts them all)
+        R.mean = R.sum / (double)R.n_ref;
+        R.inv_mean = 1.0 / R.mean;
+        // ---- distinct control values: how many, then (when they fit) the ordered search table
+        int heads = 0;
+        for (int i = tid; i < nref_nz; i += OVO_THREADS) heads += (i == 0 || rA[i - 1] != rA[i]) ? 1 : 0;
+        const int D = (int)block_sum<unsigned long long>((unsigned long long)heads, redu);
         R.st_key = st_key; R.st_lo = st_lo; R.st_n = -1;
-        if (!table && D <= ST_CAP && P.use_search_table) {
+        unsigned long long tsum = 0;
+        if (D <= ST_CAP) {
             // ordered compaction of the run starts of rA: chunks of OVO_THREADS elements, ballot + warp totals
             int base = 0;
             for (int i0 = 0; i0 < nref_nz; i0 += OVO_THREADS) {
@@ -274,33 +297,29 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
             if (tid == 0) st_lo[D] = nref_nz;
             R.st_n = D;
             __syncthreads();
-        }
-        if (table && tid == 0) {
-            for (int a = 1; a < D; ++a) {  // order the <= 22 entries by position (= by key)
-                const uint32_t k = dkey[a];
-                const int l = dlo[a];
-                int q = a - 1;
-                while (q >= 0 && dlo[q] > l) { dlo[q + 1] = dlo[q]; dkey[q + 1] = dkey[q]; --q; }
-                dlo[q + 1] = l; dkey[q + 1] = k;
+            for (int a = tid; a < D; a += OVO_THREADS) tsum += (unsigned long long)cube_minus((long long)(st_lo[a + 1] - st_lo[a]));
+        } else {
+            for (int i = tid; i < nref_nz; i += OVO_THREADS) {
+                const uint32_t k = rA[i];
+                if (i == 0 || rA[i - 1] != k) tsum += (unsigned long long)cube_minus((long long)(upper_bound_u32(rA, nref_nz, k) - i));
             }
-            dlo[D] = nref_nz;
-            for (int a = 0; a < DT_HASH; ++a) hkv[a] = make_uint2(0u, 0u);  // +0.0f is never staged
-            for (int a = 0; a < D; ++a) {
-                const float v = key2f(dkey[a]);
-                dval[a] = fc_value(v, P.flags.is_log1p);
-                const unsigned long long mult = (unsigned long long)(dlo[a + 1] - dlo[a]);
-                const unsigned long long gt = (unsigned long long)(nref_nz - dlo[a + 1]) +
-                                              ((dkey[a] < KEY_ZERO) ? (unsigned long long)R.zeros : 0ull);
-                dw[a] = 2ull * gt + mult;
-                dA3[a] = 3ull * mult * mult - 1ull;
+        }
+        R.tie = block_sum<unsigned long long>(tsum, redu);
+        // ---- table path set-up: value -> table index hash, f(value) per entry (the weights come from st_lo)
+        const bool table = D <= DT_CAP;
+        if (table) {
+            for (int a = tid; a < DT_HASH; a += OVO_THREADS) hkv[a] = make_uint2(0u, 0u);  // +0.0f is never staged
+            __syncthreads();
+            for (int a = tid; a < D; a += OVO_THREADS) {
+                const float v = key2f(st_key[a]);
+                dval[a] = fc_val<LOG1P>(v);
                 const uint32_t bits = __float_as_uint(v);
-                uint32_t h = (bits * 2654435761u) >> 26;
-                while (hkv[h].x != 0u) h = (h + 1) & (DT_HASH - 1);
-                hkv[h] = make_uint2(bits, (uint32_t)(a * OVO_THREADS * 4));
+                uint32_t h = (bits * 2654435761u) >> 24;
+                while (atomicCAS(&hkv[h].x, 0u, bits) != 0u) h = (h + 1) & (DT_HASH - 1);
+                hkv[h].y = (uint32_t)a;
             }
         }
         __syncthreads();
-        const uint32_t hkv_s = (uint32_t)__cvta_generic_to_shared(hkv);
 
         // ================= phase 2: perturbations, in chunks of GROUP_CHUNK groups =================
         for (int g0 = 0; g0 < G; g0 += GROUP_CHUNK) {
@@ -309,14 +328,14 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
             int* m_max = mmax3 + (cc % 3);             // largest non-zero count among the chunk's warp-tier groups
             if (tid == 0) { const int nx = (cc + 1) % 3; counters[2 * nx] = 0; counters[2 * nx + 1] = 0; mmax3[nx] = 0; }
             ++cc;
-            // ---- thread tier
+            // ---- one thread per group
             for (int g = g0 + tid; g < g1; g += OVO_THREADS) {
                 if (g == ref) {
                     // control row: the sparse kernels' convention (ovo/sparse_ovo.py:140-143); fold change of the
                     // control against itself (utils/math.py:191-192)
-                    double* o = P.results + (long long)g * P.gstride + (long long)j * 3;
-                    double mean_r = R.sum / (double)R.n_ref;
-                    o[0] = 1.0; o[1] = -1.0; o[2] = (mean_r == 0.0) ? INFINITY : mean_r / mean_r;
+                    const int jo = P.gene_map ? P.gene_map[j] : j;
+                    double* o = P.results + (long long)g * P.gstride + (long long)jo * 3;
+                    o[0] = 1.0; o[1] = -1.0; o[2] = (R.mean == 0.0) ? INFINITY : R.mean / R.mean;
                     const long long di = (long long)g * P.n_genes + j;
                     if (P.dbg_u2) P.dbg_u2[di] = -2;
                     if (P.dbg_tie) P.dbg_tie[di] = 0.0;
@@ -326,43 +345,47 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
                 int m = 0;
                 for (int s = s0; s < s1; ++s) m += (int)cnt[s];
-                uint32_t* col = scratch + tid;  // private column: element k at col[k * OVO_THREADS]
                 const bool big_pair = R.n_ref + (long long)pl.group_size[g] > 208063;  // tie sum may pass 2^53
-                if (table && m <= FAST_MAX && !big_pair) {
-                    // ---- table path: private histogram over the control's distinct values
-                    for (int t = 0; t < D; ++t) col[t * OVO_THREADS] = 0;
+                bool done = false;
+                if (table && !big_pair && pl.group_size[g] < 65536) {
+                    // ---- table path: private histogram over the control's distinct values, two 16-bit bins per word
+                    // (word q of the thread at scratch[q * NT + tid]: conflict-free whatever the values are)
+                    uint32_t* bins = scratch + tid;
+                    uint32_t* ex = scratch + (DT_CAP / 2) * NT + tid;   // values the control lacks: (bits, count) pairs
+                    const int nwords = (D + 1) >> 1;
+                    for (int q = 0; q < nwords; ++q) bins[q * NT] = 0u;
                     bool ok = true;
-                    int ne = 0;                                   // values the control does not have: (bits, count)
-                    const int ne_cap = (P.small_cap - D) >> 1;    // pairs kept after the D histogram bins
-                    const uint32_t col_s = (uint32_t)__cvta_generic_to_shared(col);
+                    int ne = 0;
+                    const uint32_t bins_s = (uint32_t)__cvta_generic_to_shared(bins);
                     // one stored value: hash probe (one 64-bit shared load on a hit) + bump of the private bin
                     auto bump = [&](float v) {
                         const uint32_t bits = __float_as_uint(v);
-                        uint32_t h = (bits * 2654435761u) >> 26;
-                        uint32_t k, off;
-                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(k), "=r"(off) : "r"(hkv_s + h * 8u));
+                        uint32_t h = (bits * 2654435761u) >> 24;
+                        uint32_t k, t;
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(k), "=r"(t) : "r"(hkv_s + h * 8u));
                         if (k != bits) {  // collision chain, or a value the control does not have (rare)
                             while (k != bits && k != 0u) {
                                 h = (h + 1) & (DT_HASH - 1);
-                                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(k), "=r"(off) : "r"(hkv_s + h * 8u));
+                                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(k), "=r"(t) : "r"(hkv_s + h * 8u));
                             }
                             if (k == 0u) {
                                 int x = 0;
-                                while (x < ne && col[(D + 2 * x) * OVO_THREADS] != bits) ++x;
-                                if (x < ne) col[(D + 2 * x + 1) * OVO_THREADS] += 1;
-                                else if (ne < ne_cap) {
-                                    col[(D + 2 * ne) * OVO_THREADS] = bits;
-                                    col[(D + 2 * ne + 1) * OVO_THREADS] = 1;
+                                while (x < ne && ex[(2 * x) * NT] != bits) ++x;
+                                if (x < ne) ex[(2 * x + 1) * NT] += 1;
+                                else if (ne < NE_CAP) {
+                                    ex[(2 * ne) * NT] = bits;
+                                    ex[(2 * ne + 1) * NT] = 1;
                                     ++ne;
                                 } else ok = false;
                                 return;
                             }
                         }
+                        const uint32_t addr = bins_s + (t >> 1) * (NT * 4u);
                         uint32_t r;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(col_s + off) : "memory");
-                        asm volatile("st.shared.u32 [%0], %1;" :: "r"(col_s + off), "r"(r + 1u) : "memory");
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+                        asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(r + (1u << ((t & 1u) << 4))) : "memory");
                     };
-                    for (int s = s0; s < s1; ++s) {
+                    for (int s = s0; s < s1 && ok; ++s) {
                         const int c = (int)cnt[s];
                         const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);  // 32-byte aligned slot
                         const int nfull = c >> 2;
@@ -381,70 +404,82 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                         unsigned long long u2 = 0, tie = 0;
                         double sum = 0.0;
                         for (int t = 0; t < D; ++t) {
-                            const uint32_t bq = col[t * OVO_THREADS];
+                            const uint32_t bq = (bins[(t >> 1) * NT] >> ((t & 1) << 4)) & 0xffffu;
                             if (bq) {
-                                // b (2 gt + a)  and  (a+b)^3 - (a+b) - (a^3 - a) = b (3a^2 - 1 + b (3a + b))
-                                const uint32_t a3 = 3u * (uint32_t)(dlo[t + 1] - dlo[t]);
-                                u2 += (unsigned long long)bq * dw[t];
-                                tie += (unsigned long long)bq * (dA3[t] + (unsigned long long)bq * (unsigned long long)(a3 + bq));
+                                // b (2 gt + a)  and  (a+b)^3 - (a+b) - (a^3 - a) = b (3 a (a + b) + b^2 - 1)
+                                const uint32_t a = (uint32_t)(st_lo[t + 1] - st_lo[t]);
+                                const uint32_t gt = (uint32_t)(nref_nz - st_lo[t + 1]) + ((st_key[t] < KEY_ZERO) ? (uint32_t)R.zeros : 0u);
+                                u2 += (unsigned long long)bq * (unsigned long long)(2u * gt + a);
+                                tie += (unsigned long long)bq * (3ull * a * ((unsigned long long)a + bq) + (unsigned long long)bq * bq - 1ull);
                                 sum += (double)bq * dval[t];
                             }
                         }
                         for (int x = 0; x < ne; ++x) {  // absent from the control: a = 0, position by binary search
-                            const uint32_t key = f2key(__uint_as_float(col[(D + 2 * x) * OVO_THREADS]));
-                            const long long bq = col[(D + 2 * x + 1) * OVO_THREADS];
-                            const long long gt = (long long)(nref_nz - lower_bound_u32(rA, nref_nz, key)) +
-                                                 ((key < KEY_ZERO) ? R.zeros : 0);
-                            u2 += (unsigned long long)(bq * 2 * gt);
-                            tie += (unsigned long long)cube_minus(bq);
-                            sum += (double)bq * fc_value(key2f(key), P.flags.is_log1p);
+                            const float v = __uint_as_float(ex[(2 * x) * NT]);
+                            const uint32_t bq = ex[(2 * x + 1) * NT];
+                            rank_value(R, f2key(v), bq, u2, tie);
+                            sum += (double)bq * fc_val<LOG1P>(v);
                         }
                         finalize_group(P, R, j, g, m, u2, tie, sum);
-                        continue;
+                        done = true;
                     }
-                    // too many values the control does not have: a whole warp ranks this group (general path)
-                    mlist[atomicAdd(&cnt_m[0], 1)] = (uint16_t)(g - g0);
-                    atomicMax(m_max, m);
-                    continue;
-                }
-                if (m > P.small_cap) {
-                    mlist[atomicAdd(&cnt_m[0], 1)] = (uint16_t)(g - g0);
-                    atomicMax(m_max, m);
-                    continue;
-                }
-                double sum = 0.0;
-                int k = 0;
-                for (int s = s0; s < s1; ++s) {
-                    const int c = (int)cnt[s];
-                    const float* src = vals + pl.seg_base[s];
-                    for (int i = 0; i < c; ++i) {
-                        float v = src[i];
+                } else if (!table && !big_pair && m <= STREAM_MAX) {
+                    // ---- stream tier: every value ranked on arrival; exact as long as the group's values are pairwise
+                    // different (private key hash: slot q of the thread at scratch[q * NT + tid])
+                    uint32_t* hs = scratch + tid;
+#pragma unroll
+                    for (int q = 0; q < STREAM_SLOTS; ++q) hs[q * NT] = 0u;
+                    unsigned long long u2 = 0, tie = 0;
+                    double sum = 0.0;
+                    bool dup = false;
+                    auto take = [&](float v) {
                         uint32_t key = f2key(v);
-                        // insertion sort, ascending
-                        int q = k - 1;
-                        while (q >= 0 && col[q * OVO_THREADS] > key) { col[(q + 1) * OVO_THREADS] = col[q * OVO_THREADS]; --q; }
-                        col[(q + 1) * OVO_THREADS] = key;
-                        ++k;
+                        if (key == 0u) key = 1u;                                   // (only a NaN payload maps to 0)
+                        int lo, hi;
+                        rank_pos(R, key, lo, hi);
+                        const uint32_t a = (uint32_t)(hi - lo);
+                        const uint32_t gt = (uint32_t)(R.nnz - hi) + ((key < KEY_ZERO) ? (uint32_t)R.zeros : 0u);
+                        u2 += (unsigned long long)(2u * gt + a);
+                        if (a) tie += 3ull * a * ((unsigned long long)a + 1ull);    // (a+1)^3 - (a+1) - (a^3 - a)
+                        sum += fc_val<LOG1P>(v);
+                        uint32_t h = (key * 2654435761u) >> 27;
+                        for (;;) {
+                            const uint32_t kk = hs[h * NT];
+                            if (kk == 0u) { hs[h * NT] = key; break; }
+                            if (kk == key) { dup = true; break; }
+                            h = (h + 1) & (STREAM_SLOTS - 1);
+                        }
+                    };
+                    for (int s = s0; s < s1; ++s) {
+                        const int c = (int)cnt[s];
+                        const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);
+                        const int nfull = c >> 2;
+                        float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int i4 = 0; i4 < nfull; ++i4) {
+                            const float4 q4 = nxt;
+                            if (4 * i4 + 4 < c) nxt = src4[i4 + 1];
+                            take(q4.x); take(q4.y); take(q4.z); take(q4.w);
+                        }
+                        const int rem = c & 3;
+                        if (rem > 0) take(nxt.x);
+                        if (rem > 1) take(nxt.y);
+                        if (rem > 2) take(nxt.z);
+                    }
+                    if (!dup) {
+                        finalize_group(P, R, j, g, m, u2, tie, sum);
+                        done = true;
                     }
                 }
-                unsigned long long u2 = 0, tie = 0;
-                int i = 0;
-                while (i < m) {
-                    uint32_t key = col[i * OVO_THREADS];
-                    int r = i + 1;
-                    while (r < m && col[r * OVO_THREADS] == key) ++r;
-                    rank_value(R, key, r - i, u2, tie);
-                    sum += (double)(r - i) * fc_value(key2f(key), P.flags.is_log1p);
-                    i = r;
+                if (!done) {  // a whole warp (or the CTA) ranks this group by sorting it
+                    mlist[atomicAdd(&cnt_m[0], 1)] = (uint16_t)(g - g0);
+                    atomicMax(m_max, m);
                 }
-                finalize_group(P, R, j, g, m, u2, tie, sum, col, OVO_THREADS);
             }
             __syncthreads();
             // ---- warp tier (usually empty: then this barrier is the only one of the chunk)
             const int nm = cnt_m[0];
             if (nm == 0) continue;
-            // warp-tier buffers: 512 keys each when every group of the chunk fits (all 8 warps then own one; with 1024-key
-            // buffers only 5 do -- a dense high-count gene has all its 2000 groups here, and its CTA is the kernel's tail)
+            // warp-tier buffers: 512 keys each when every group of the chunk fits (more warps then own one)
             const int wcap = (*m_max <= WARP_CAP / 2) ? WARP_CAP / 2 : WARP_CAP;
             const int nwb = min(OVO_NW, P.scratch_words / wcap);
             for (int e = w; e < nm && w < nwb; e += nwb) {
@@ -471,10 +506,10 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 unsigned long long u2 = 0, tie = 0;
                 double sum = 0.0;
                 for (int i = lane; i < m; i += 32) {
-                    uint32_t key = buf[i];
-                    sum += fc_value(key2f(key), P.flags.is_log1p);
+                    const uint32_t key = buf[i];
+                    sum += fc_val<LOG1P>(key2f(key));
                     if (i == 0 || buf[i - 1] != key) {
-                        long long b = upper_bound_u32(buf, m, key) - i;
+                        const uint32_t b = (i + 1 < m && buf[i + 1] == key) ? (uint32_t)(upper_bound_u32(buf, m, key) - i) : 1u;
                         rank_value(R, key, b, u2, tie);
                     }
                 }
@@ -502,10 +537,10 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 unsigned long long u2 = 0, tie = 0;
                 double sum = 0.0;
                 for (int i = tid; i < m; i += OVO_THREADS) {
-                    uint32_t key = gk[i];
-                    sum += fc_value(key2f(key), P.flags.is_log1p);
+                    const uint32_t key = gk[i];
+                    sum += fc_val<LOG1P>(key2f(key));
                     if (i == 0 || gk[i - 1] != key) {
-                        long long b = upper_bound_u32(gk, m, key) - i;
+                        const uint32_t b = (i + 1 < m && gk[i + 1] == key) ? (uint32_t)(upper_bound_u32(gk, m, key) - i) : 1u;
                         rank_value(R, key, b, u2, tie);
                     }
                 }
@@ -520,73 +555,69 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
     }
 }
 
-// max over the batch's genes of the control group's non-zero count: sizes the shared control buffer
-__global__ void max_ref_nnz_kernel(const uint32_t* __restrict__ ir_cnt, int n_genes, int S, int s0, int s1, int* out) {
-    int m = 0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_genes; j += gridDim.x * blockDim.x) {
-        int c = 0;
-        for (int s = s0; s < s1; ++s) c += (int)ir_cnt[(long long)j * S + s];
-        m = max(m, c);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
-}
-
 // ------------------------------------------------------------------------------------------------------
+// workspace: [gene counter | per-group constants | per-CTA slabs]
+static size_t ovo_head_bytes(const illico_plan_t* plan) {
+    const size_t Gs = (size_t)((plan->n_groups + 63) & ~63);
+    return 256 + Gs * GCN * sizeof(double);
+}
 size_t ovo_workspace_bytes(const illico_plan_t* plan, int n_ctas) {
-    return (size_t)n_ctas * 4 * (size_t)plan->max_group_size * sizeof(uint32_t);
+    return ovo_head_bytes(plan) + (size_t)n_ctas * 4 * (size_t)plan->max_group_size * sizeof(uint32_t);
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
-
-template <int NT, int MIN_CTAS>
+template <int NT, int MIN_CTAS, bool LOG1P>
 static int launch_ovo_t(OvoParams& P, const illico_plan_t* plan, void* workspace, size_t workspace_bytes, int sms,
                         int max_smem, cudaStream_t stream) {
     constexpr int NW = NT / 32;
-    // shared memory: fixed part + control buffer + scratch.  Genes whose control has more non-zeros than ref_cap
+    // shared memory: control buffer + scratch + fixed part.  Genes whose control has more non-zeros than REF_CAP
     // keep the control in the CTA's global slab.
-    const size_t fixed = (size_t)(NW * 256 + RADIX_AUX_WORDS + GROUP_CHUNK + 8) * 4 + 32 * 8 * 2 + 3 * DT_CAP * 8 +
-                         (2 * DT_CAP + 1) * 4 + DT_HASH * 8 + 64 + (2 * ST_CAP + 1) * 4;
-    const int small_cap = DT_CAP;
-    int scratch_words = small_cap * NT;               // thread tier: small_cap keys per thread
+    const size_t fixed = (size_t)(NW * 256 + RADIX_AUX_WORDS + GROUP_CHUNK + 8) * 4 + 32 * 8 * 2 + DT_CAP * 8 + DT_HASH * 8 +
+                         (2 * ST_CAP + 1) * 4 + 64;
+    int scratch_words = (DT_CAP / 2 + 2 * NE_CAP) * NT;              // table path: bins + extras per thread
+    if (scratch_words < STREAM_SLOTS * NT) scratch_words = STREAM_SLOTS * NT;
     if (scratch_words < 2 * WARP_CAP) scratch_words = 2 * WARP_CAP;  // at least two warp-tier buffers
-    // The control buffer is sized to what this batch needs (P.ref_cap holds the measured maximum): shared memory
-    // that is not carved out stays L1 cache for the scattered reads of the group slots.
-    int ref_cap = (P.ref_cap + 3) & ~3;
-    if (ref_cap < 4) ref_cap = 4;
-    const int ref_cap_max = env_int("ILLICO_OVO_REF_CAP", scratch_words);
-    if (ref_cap > ref_cap_max) ref_cap = ref_cap_max;
-    if (ref_cap > scratch_words) ref_cap = scratch_words;  // the ping-pong partner is the scratch area
-    const size_t need = fixed + (size_t)(ref_cap + scratch_words) * 4;
+    const size_t need = fixed + (size_t)(REF_CAP + scratch_words) * 4;
     if (need > (size_t)max_smem) { set_error("ovo_kernel needs %zu bytes of shared memory", need); return 1; }
-    P.ref_cap = ref_cap; P.small_cap = small_cap; P.scratch_words = scratch_words;
-    P.use_search_table = env_int("ILLICO_OVO_SEARCH_TABLE", 1);
-    auto kern = ovo_kernel<NT, MIN_CTAS>;
+    P.scratch_words = scratch_words;
+    auto kern = ovo_kernel<NT, MIN_CTAS, LOG1P>;
     ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     int occ = 0;
     ILLICO_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, need));
     if (occ < 1) { set_error("ovo_kernel does not fit: %zu bytes of shared memory", need); return 1; }
     int grid = sms * occ;
     if (grid > P.n_genes) grid = P.n_genes;
+    const size_t head = ovo_head_bytes(plan);
+    if (workspace_bytes < head) { set_error("rank workspace too small: %zu bytes", workspace_bytes); return 1; }
     const size_t slab_words = 4 * (size_t)plan->max_group_size;
-    if ((size_t)grid * slab_words * 4 > workspace_bytes) {
-        grid = (int)(workspace_bytes / (slab_words * 4));
+    if ((size_t)grid * slab_words * 4 > workspace_bytes - head) {
+        grid = (int)((workspace_bytes - head) / (slab_words * 4));
         if (grid < 1) { set_error("rank workspace too small: %zu bytes", workspace_bytes); return 1; }
     }
-    P.slab = (uint32_t*)workspace; P.slab_words = (long long)slab_words;
+    char* ws = reinterpret_cast<char*>(workspace);
+    P.gene_counter = reinterpret_cast<int*>(ws);
+    P.Gs = (plan->n_groups + 63) & ~63;
+    double* gc = reinterpret_cast<double*>(ws + 256);
+    P.gc = gc;
+    P.slab = reinterpret_cast<uint32_t*>(ws + head); P.slab_words = (long long)slab_words;
+    ILLICO_CUDA_OK(cudaMemsetAsync(P.gene_counter, 0, sizeof(int), stream));
+    ILLICO_LAUNCH("ovo_group_consts_kernel", stream,
+                  ovo_group_consts_kernel<<<(plan->n_groups + 255) / 256, 256, 0, stream>>>(*plan, gc, P.Gs));
     ILLICO_LAUNCH("ovo_kernel", stream, kern<<<grid, NT, need, stream>>>(P));
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int launch_ovo(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const illico_plan_t* plan,
-               const illico_flags_t* flags, double* results, long long gstride, void* workspace,
-               size_t workspace_bytes, const illico_debug_t* dbg, cudaStream_t stream) {
+// n_genes_dev / gene_map: see OvoParams (both may be NULL)
+int launch_ovo_mapped(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const int* n_genes_dev, const int* gene_map,
+                      const illico_plan_t* plan, const illico_flags_t* flags, double* results, long long gstride,
+                      void* workspace, size_t workspace_bytes, const illico_debug_t* dbg, cudaStream_t stream) {
     if (n_genes <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+        const size_t adj = 256 - (reinterpret_cast<uintptr_t>(workspace) & 255);
+        if (workspace_bytes <= adj) { set_error("rank workspace too small"); return 1; }
+        workspace = reinterpret_cast<char*>(workspace) + adj;
+        workspace_bytes -= adj;
+    }
     int dev = 0, sms = 0, max_smem = 0;
     ILLICO_CUDA_OK(cudaGetDevice(&dev));
     ILLICO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -595,24 +626,18 @@ int launch_ovo(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const 
     OvoParams P;
     P.ir_vals = ir_vals; P.ir_cnt = ir_cnt; P.n_genes = n_genes; P.plan = *plan; P.flags = *flags;
     P.results = results; P.gstride = gstride;
+    P.n_genes_dev = n_genes_dev; P.gene_map = gene_map;
     P.dbg_u2 = dbg ? (long long*)dbg->u2 : nullptr; P.dbg_tie = dbg ? dbg->tie_sum : nullptr;
     P.dbg_tie_exact = dbg ? (long long*)dbg->tie_exact : nullptr;
-    // measured control size (one tiny kernel + a 4-byte read-back; the staging kernel is already in flight)
-    {
-        int* d_max = reinterpret_cast<int*>(workspace);
-        int h_max = 0;
-        ILLICO_CUDA_OK(cudaMemsetAsync(d_max, 0, sizeof(int), stream));
-        ILLICO_LAUNCH("max_ref_nnz_kernel", stream, max_ref_nnz_kernel<<<(n_genes + 255) / 256, 256, 0, stream>>>(ir_cnt, n_genes, plan->n_segments, plan->ref_seg_begin,
-                                                                      plan->ref_seg_end, d_max));
-        ILLICO_CUDA_OK(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
-        P.ref_cap = h_max;
-        workspace = reinterpret_cast<char*>(workspace) + 256;
-        workspace_bytes -= 256;
-    }
-    if (env_int("ILLICO_OVO_THREADS", 256) == 256)
-        return launch_ovo_t<256, 4>(P, plan, workspace, workspace_bytes, sms, max_smem, stream);
-    return launch_ovo_t<512, 2>(P, plan, workspace, workspace_bytes, sms, max_smem, stream);
+    if (flags->is_log1p) return launch_ovo_t<256, 3, true>(P, plan, workspace, workspace_bytes, sms, max_smem, stream);
+    return launch_ovo_t<256, 3, false>(P, plan, workspace, workspace_bytes, sms, max_smem, stream);
+}
+
+int launch_ovo(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const illico_plan_t* plan,
+               const illico_flags_t* flags, double* results, long long gstride, void* workspace,
+               size_t workspace_bytes, const illico_debug_t* dbg, cudaStream_t stream) {
+    return launch_ovo_mapped(ir_vals, ir_cnt, n_genes, nullptr, nullptr, plan, flags, results, gstride, workspace, workspace_bytes,
+                             dbg, stream);
 }
 
 }  // namespace illico
