@@ -19,9 +19,8 @@
 //                sort, no search;
 //   stream tier  any other gene, groups of at most STREAM_MAX non-zeros: one THREAD per group streams its values once:
 //                each is ranked against the control by one binary search and contributes 2 #{ref > v} + a and the tie
-//                term 3 a (a + 1) on the spot (a = its multiplicity in the control).  That is only exact while the
-//                group's own values are pairwise different, which a private 32-slot key hash checks; a group with a
-//                repeated value is redone by the warp tier;
+//                terms of its run on the spot (a private 32-slot hash counts the occurrences of a value inside the
+//                group; the per-element terms telescope to the per-run formulas above) -- no sort;
 //   warp tier    one WARP per group (bitonic sort in shared memory, runs, binary searches), up to WARP_CAP non-zeros;
 //   block tier   larger groups one at a time by the whole CTA (radix sort in the CTA's global slab).
 #include "common.cuh"
@@ -33,13 +32,15 @@
 namespace illico {
 
 constexpr int WARP_CAP = 1024;     // keys per warp buffer in the warp tier
-constexpr int GROUP_CHUNK = 2048;  // groups handled per sweep (bounds the deferred lists)
+constexpr int GROUP_CHUNK = 1024;  // groups handled per sweep (bounds the per-chunk lists)
 constexpr int DT_CAP = 64;         // distinct control values for the table path
 constexpr int DT_HASH = 256;       // slots of the value -> table-index hash (load factor <= 1/4)
 constexpr int NE_CAP = 4;          // table path: distinct values of a group that the control does not have
 constexpr int ST_CAP = 1024;       // distinct control values kept in the shared-memory search table
-constexpr int STREAM_MAX = 28;     // stream tier: most non-zeros per group (32-slot duplicate hash)
+constexpr int STREAM_MAX = 28;     // stream tier: most non-zeros per group (16 buckets x 2 slots of the occurrence hash)
 constexpr int STREAM_SLOTS = 32;
+constexpr int MBINS = 64;          // groups of a chunk are handed to the threads in order of their non-zero count (bins)
+constexpr int HCAP = 4096;         // slots of the hash that finds the distinct values of a large control
 constexpr int REF_CAP = 1536;      // control keys sorted in shared memory (larger controls: the CTA's global slab)
 constexpr int GCN = 5;             // per-group constants of the p-value (see ovo_group_consts_kernel)
 
@@ -65,7 +66,8 @@ struct OvoParams {
 };
 
 struct RefInfo {
-    const uint32_t* keys;  // sorted non-zero control keys
+    const uint32_t* keys;  // sorted non-zero control keys (NULL when only the table below was built)
+    uint32_t keys_s;       // their shared-memory address, 0 when they live in the CTA's global slab
     int nnz;               // how many
     int npos;              // control values > 0
     int zeros;             // control zeros
@@ -75,12 +77,39 @@ struct RefInfo {
     double mean;             // sum / n_ref
     double inv_mean;
     // search table (st_n >= 0): the control's distinct keys ascending and the position of each one's first
-    // occurrence in `keys` (st_lo[st_n] = nnz).  A rank then costs a binary search over <= 1024 shared-memory entries
-    // instead of one over the whole sorted control, which lives in the CTA's global slab when it is large.
-    const uint32_t* st_key;
-    const int* st_lo;
+    // occurrence in the sorted control (st_lo[st_n] = nnz), in shared memory.  A rank then costs a binary search over
+    // <= 1024 shared-memory entries whatever the size of the control.
+    uint32_t st_key_s, st_lo_s;   // shared-memory addresses
     int st_n;
 };
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+// lower / upper bound over a sorted shared-memory array (32-bit shared addresses, branch-free body; the trip count
+// only depends on n, so a warp stays converged)
+__device__ __forceinline__ int lb_shared(uint32_t base_s, int n, uint32_t key) {
+    int lo = 0, len = n;
+    while (len > 1) {
+        const int half = len >> 1;
+        lo += (lds_u32(base_s + (uint32_t)(lo + half - 1) * 4u) < key) ? half : 0;
+        len -= half;
+    }
+    if (len == 1) lo += (lds_u32(base_s + (uint32_t)lo * 4u) < key) ? 1 : 0;
+    return lo;
+}
+__device__ __forceinline__ int ub_shared(uint32_t base_s, int n, uint32_t key) {
+    int lo = 0, len = n;
+    while (len > 1) {
+        const int half = len >> 1;
+        lo += (lds_u32(base_s + (uint32_t)(lo + half - 1) * 4u) <= key) ? half : 0;
+        len -= half;
+    }
+    if (len == 1) lo += (lds_u32(base_s + (uint32_t)lo * 4u) <= key) ? 1 : 0;
+    return lo;
+}
 
 template <bool LOG1P>
 __device__ __forceinline__ double fc_val(float v) {
@@ -91,9 +120,13 @@ __device__ __forceinline__ double fc_val(float v) {
 // position of `key` in the sorted control: [lo, hi) = its run (empty when the control does not have the value)
 __device__ __forceinline__ void rank_pos(const RefInfo& R, uint32_t key, int& lo, int& hi) {
     if (R.st_n >= 0) {
-        const int t = lower_bound_u32(R.st_key, R.st_n, key);
-        lo = R.st_lo[t];
-        hi = (t < R.st_n && R.st_key[t] == key) ? R.st_lo[t + 1] : lo;
+        const int t = lb_shared(R.st_key_s, R.st_n, key);
+        lo = (int)lds_u32(R.st_lo_s + (uint32_t)t * 4u);
+        hi = (t < R.st_n && lds_u32(R.st_key_s + (uint32_t)t * 4u) == key) ? (int)lds_u32(R.st_lo_s + (uint32_t)(t + 1) * 4u) : lo;
+    } else if (R.keys_s) {
+        lo = lb_shared(R.keys_s, R.nnz, key);
+        hi = lo;
+        if (lo < R.nnz && lds_u32(R.keys_s + (uint32_t)lo * 4u) == key) hi = ub_shared(R.keys_s, R.nnz, key);
     } else {
         lo = lower_bound_u32(R.keys, R.nnz, key);
         hi = lo;
@@ -194,16 +227,21 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
 
     // ---- shared carve-up
     uint32_t* refA = smem;                                  // [REF_CAP]
-    uint32_t* scratch = refA + REF_CAP;                     // [scratch_words] (>= REF_CAP)
+    uint32_t* scratch = refA + REF_CAP;                     // [scratch_words] (>= REF_CAP, >= 2 * HCAP)
     uint32_t* hist = scratch + P.scratch_words;             // [OVO_NW * 256]
     uint32_t* aux = hist + OVO_NW * 256;                    // [RADIX_AUX_WORDS]
-    uint16_t* mlist = (uint16_t*)(aux + RADIX_AUX_WORDS);   // [GROUP_CHUNK] group index inside the chunk
-    uint16_t* blist = mlist + GROUP_CHUNK;                  // [GROUP_CHUNK]
-    int* counters = (int*)(blist + GROUP_CHUNK);            // [8] three rotating {medium, big} list counters, [7] next gene
-    double* redd = (double*)(counters + 8);                 // [32]
+    uint16_t* mlist = (uint16_t*)(aux + RADIX_AUX_WORDS);   // [GROUP_CHUNK] groups left to the warp tier (index inside the chunk)
+    uint16_t* blist = mlist + GROUP_CHUNK;                  // [GROUP_CHUNK] ... to the block tier
+    uint16_t* order = blist + GROUP_CHUNK;                  // [GROUP_CHUNK] the chunk's groups by non-zero count
+    uint16_t* marr = order + GROUP_CHUNK;                   // [GROUP_CHUNK] non-zero count of each group (capped)
+    int* counters = (int*)(marr + GROUP_CHUNK);             // [8] rotating {medium, big} list counters, [6] scratch, [7] next gene
+    int* mh = counters + 8;                                 // [MBINS] histogram / cursors of the non-zero counts
+    double* redd = (double*)(mh + MBINS);                   // [32]
     unsigned long long* redu = (unsigned long long*)(redd + 32);  // [32]
     double* dval = (double*)(redu + 32);                    // [DT_CAP]   f(x) of each distinct control value
-    uint2* hkv = (uint2*)(dval + DT_CAP);                   // [DT_HASH]  open-addressed {float bits, table index}
+    uint32_t* dwt = (uint32_t*)(dval + DT_CAP);             // [DT_CAP]   2 #{ref > v} + a
+    uint32_t* dmult = dwt + DT_CAP;                         // [DT_CAP]   a = multiplicity in the control
+    uint2* hkv = (uint2*)(dmult + DT_CAP);                  // [DT_HASH]  open-addressed {float bits, table index}
     uint32_t* st_key = (uint32_t*)(hkv + DT_HASH);          // [ST_CAP]   search table: distinct control keys, ascending
     int* st_lo = (int*)(st_key + ST_CAP);                   // [ST_CAP+1] first position of each
 
@@ -219,6 +257,9 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
     int cc = 0;  // chunk counter: chunk c uses counter set c % 3 and clears set (c + 1) % 3 for the next chunk
     const int n_genes = P.n_genes_dev ? *P.n_genes_dev : P.n_genes;
     const uint32_t hkv_s = (uint32_t)__cvta_generic_to_shared(hkv);
+    const long long n_ref_cells = pl.group_size[ref];
+    // pairs above 208 063 cells replay the reference's ordered tie sum from the SORTED control: no hashing then
+    const bool may_hash = n_ref_cells + (long long)pl.max_target_group_size <= 208063;
     __syncthreads();
 
     for (;;) {
@@ -229,83 +270,168 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
         const uint32_t* cnt = P.ir_cnt + (long long)j * S;
         const float* vals = P.ir_vals + (long long)j * pl.slot_cap;
 
-        // ================= phase 1: control keys, sorted once per gene =================
+        // ================= phase 1: the control, once per gene =================
         // offsets of the control's segments (few): serial prefix by thread 0 into hist[] (free now)
         if (tid == 0) {
             uint32_t acc = 0;
             for (int s = ref_s0; s < ref_s1; ++s) { hist[s - ref_s0] = acc; acc += cnt[s]; }
             hist[ref_s1 - ref_s0] = acc;
+            counters[6] = 0;
         }
         __syncthreads();
         const int nref_nz = (int)hist[ref_s1 - ref_s0];
-        // control keys live in shared memory when they fit, else in this CTA's global slab
         const bool ref_smem = nref_nz <= REF_CAP;
-        uint32_t* rA = ref_smem ? refA : slab + 2ll * maxg;
-        uint32_t* rB = ref_smem ? scratch : slab + 3ll * maxg;
+        RefInfo R;
+        R.nnz = nref_nz;
+        R.n_ref = n_ref_cells;
+        R.zeros = (int)(R.n_ref - nref_nz);
+        R.st_key_s = (uint32_t)__cvta_generic_to_shared(st_key);
+        R.st_lo_s = (uint32_t)__cvta_generic_to_shared(st_lo);
+        R.st_n = -1;
+        R.keys = nullptr; R.keys_s = 0u;
         double rsum = 0.0;
-        for (int s = ref_s0 + w; s < ref_s1; s += OVO_NW) {
-            const uint32_t off = hist[s - ref_s0];
-            const int c = (int)cnt[s];
-            const float* src = vals + pl.seg_base[s];
-            for (int i = lane; i < c; i += 32) {
-                float v = src[i];
-                rA[off + i] = f2key(v);
-                rsum += fc_val<LOG1P>(v);
+        int D = 0;
+        bool hashed = false;
+        if (!ref_smem && may_hash) {
+            // ---- a large control (a dense gene).  Count data has a handful of distinct values whatever the size: find
+            // them with a shared-memory hash (value -> multiplicity) instead of sorting 10k keys through the global slab.
+            uint32_t* hk = scratch;
+            uint32_t* hc = scratch + HCAP;
+            for (int i = tid; i < 2 * HCAP; i += OVO_THREADS) scratch[i] = 0u;
+            __syncthreads();
+            for (int s = ref_s0 + w; s < ref_s1; s += OVO_NW) {
+                const int c = (int)cnt[s];
+                const float* src = vals + pl.seg_base[s];
+                for (int i = lane; i < c; i += 32) {
+                    const float v = src[i];
+                    rsum += fc_val<LOG1P>(v);
+                    uint32_t key = f2key(v);
+                    if (key == 0u) key = 1u;
+                    if (*(volatile int*)&counters[6] > ST_CAP) continue;      // not count-like: the sort path takes over
+                    uint32_t h = (key * 2654435761u) >> 20;
+                    for (;;) {
+                        const uint32_t prev = atomicCAS(&hk[h], 0u, key);
+                        if (prev == 0u) atomicAdd(&counters[6], 1);
+                        if (prev == 0u || prev == key) { atomicAdd(&hc[h], 1u); break; }
+                        h = (h + 1) & (HCAP - 1);
+                    }
+                }
+            }
+            __syncthreads();
+            D = counters[6];
+            __syncthreads();
+            if (D <= ST_CAP) {
+                // distinct (key, multiplicity) pairs -> sorted by key -> first positions by an exclusive scan
+                if (tid == 0) counters[6] = 0;
+                __syncthreads();
+                for (int t = tid; t < HCAP; t += OVO_THREADS)
+                    if (hk[t] != 0u) {
+                        const int idx = atomicAdd(&counters[6], 1);
+                        st_key[idx] = hk[t];
+                        st_lo[idx] = (int)hc[t];
+                    }
+                const int Pd = max(2, next_pow2(D));
+                for (int i = D + tid; i < Pd; i += OVO_THREADS) { st_key[i] = 0xffffffffu; st_lo[i] = 0; }
+                __syncthreads();
+                block_bitonic_sort_pairs(st_key, (uint32_t*)st_lo, Pd);
+                // exclusive prefix of the multiplicities: ST_CAP / OVO_THREADS consecutive entries per thread
+                constexpr int PER = (ST_CAP + OVO_THREADS - 1) / OVO_THREADS;
+                uint32_t cv[PER], loc = 0;
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    const int i = tid * PER + q;
+                    cv[q] = (i < D) ? (uint32_t)st_lo[i] : 0u;
+                    loc += cv[q];
+                }
+                const uint32_t incl = warp_incl_scan(loc, lane);
+                if (lane == 31) aux[w] = incl;
+                __syncthreads();
+                uint32_t basev = incl - loc;
+                for (int ww = 0; ww < w; ++ww) basev += aux[ww];
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    const int i = tid * PER + q;
+                    if (i < D) st_lo[i] = (int)basev;
+                    basev += cv[q];
+                }
+                if (tid == 0) st_lo[D] = nref_nz;
+                __syncthreads();
+                hashed = true;
+                R.st_n = D;
+            } else {
+                rsum = 0.0;   // recomputed by the sort path below
             }
         }
-        __syncthreads();
-        rsum = block_sum<double>(rsum, redd);
-        const uint32_t* rk = block_radix_sort(rA, rB, nref_nz, hist, aux);
-        if (rk != rA) {  // keep the sorted keys in rA: rB is recycled as tier scratch
-            for (int i = tid; i < nref_nz; i += OVO_THREADS) rA[i] = rB[i];
+        if (!hashed) {
+            // ---- sort path: control keys in shared memory when they fit, else in this CTA's global slab
+            uint32_t* rA = ref_smem ? refA : slab + 2ll * maxg;
+            uint32_t* rB = ref_smem ? scratch : slab + 3ll * maxg;
+            for (int s = ref_s0 + w; s < ref_s1; s += OVO_NW) {
+                const uint32_t off = hist[s - ref_s0];
+                const int c = (int)cnt[s];
+                const float* src = vals + pl.seg_base[s];
+                for (int i = lane; i < c; i += 32) {
+                    const float v = src[i];
+                    uint32_t key = f2key(v);
+                    if (key == 0u) key = 1u;
+                    rA[off + i] = key;
+                    rsum += fc_val<LOG1P>(v);
+                }
+            }
             __syncthreads();
+            const uint32_t* rk = block_radix_sort(rA, rB, nref_nz, hist, aux);
+            if (rk != rA) {  // keep the sorted keys in rA: rB is recycled as tier scratch
+                for (int i = tid; i < nref_nz; i += OVO_THREADS) rA[i] = rB[i];
+                __syncthreads();
+            }
+            R.keys = rA;
+            R.keys_s = ref_smem ? (uint32_t)__cvta_generic_to_shared(rA) : 0u;
+            // distinct control values: how many, then (when they fit) the ordered search table
+            int heads = 0;
+            for (int i = tid; i < nref_nz; i += OVO_THREADS) heads += (i == 0 || rA[i - 1] != rA[i]) ? 1 : 0;
+            D = (int)block_sum<unsigned long long>((unsigned long long)heads, redu);
+            if (D <= ST_CAP) {
+                // ordered compaction of the run starts of rA: chunks of OVO_THREADS elements, ballot + warp totals
+                int base = 0;
+                for (int i0 = 0; i0 < nref_nz; i0 += OVO_THREADS) {
+                    const int i = i0 + tid;
+                    const bool head = i < nref_nz && (i == 0 || rA[i - 1] != rA[i]);
+                    const unsigned bal = __ballot_sync(FULL, head);
+                    if (lane == 0) hist[w] = (uint32_t)__popc(bal);
+                    __syncthreads();
+                    int before = 0, total = 0;
+                    for (int ww = 0; ww < OVO_NW; ++ww) { const int c = (int)hist[ww]; if (ww < w) before += c; total += c; }
+                    if (head) {
+                        const int slot = base + before + __popc(bal & ((1u << lane) - 1u));
+                        st_key[slot] = rA[i];
+                        st_lo[slot] = i;
+                    }
+                    base += total;
+                    __syncthreads();
+                }
+                if (tid == 0) st_lo[D] = nref_nz;
+                R.st_n = D;
+                __syncthreads();
+            }
         }
-        RefInfo R;
-        R.keys = rA;
-        R.nnz = nref_nz;
-        R.n_ref = pl.group_size[ref];
-        R.zeros = (int)(R.n_ref - nref_nz);
-        R.npos = nref_nz - upper_bound_u32(rA, nref_nz, KEY_ZERO);
+        rsum = block_sum<double>(rsum, redd);
         R.sum = P.flags.group_sums ? P.flags.group_sums[(long long)ref * P.n_genes + j] : rsum;
         R.mean = R.sum / (double)R.n_ref;
         R.inv_mean = 1.0 / R.mean;
-        // ---- distinct control values: how many, then (when they fit) the ordered search table
-        int heads = 0;
-        for (int i = tid; i < nref_nz; i += OVO_THREADS) heads += (i == 0 || rA[i - 1] != rA[i]) ? 1 : 0;
-        const int D = (int)block_sum<unsigned long long>((unsigned long long)heads, redu);
-        R.st_key = st_key; R.st_lo = st_lo; R.st_n = -1;
         unsigned long long tsum = 0;
-        if (D <= ST_CAP) {
-            // ordered compaction of the run starts of rA: chunks of OVO_THREADS elements, ballot + warp totals
-            int base = 0;
-            for (int i0 = 0; i0 < nref_nz; i0 += OVO_THREADS) {
-                const int i = i0 + tid;
-                const bool head = i < nref_nz && (i == 0 || rA[i - 1] != rA[i]);
-                const unsigned bal = __ballot_sync(FULL, head);
-                if (lane == 0) hist[w] = (uint32_t)__popc(bal);
-                __syncthreads();
-                int before = 0, total = 0;
-                for (int ww = 0; ww < OVO_NW; ++ww) { const int c = (int)hist[ww]; if (ww < w) before += c; total += c; }
-                if (head) {
-                    const int slot = base + before + __popc(bal & ((1u << lane) - 1u));
-                    st_key[slot] = rA[i];
-                    st_lo[slot] = i;
-                }
-                base += total;
-                __syncthreads();
-            }
-            if (tid == 0) st_lo[D] = nref_nz;
-            R.st_n = D;
-            __syncthreads();
+        if (R.st_n >= 0) {
             for (int a = tid; a < D; a += OVO_THREADS) tsum += (unsigned long long)cube_minus((long long)(st_lo[a + 1] - st_lo[a]));
+            R.npos = nref_nz - st_lo[lb_shared(R.st_key_s, D, KEY_ZERO + 1u)];
         } else {
+            const uint32_t* rA = R.keys;
             for (int i = tid; i < nref_nz; i += OVO_THREADS) {
                 const uint32_t k = rA[i];
                 if (i == 0 || rA[i - 1] != k) tsum += (unsigned long long)cube_minus((long long)(upper_bound_u32(rA, nref_nz, k) - i));
             }
+            R.npos = nref_nz - upper_bound_u32(rA, nref_nz, KEY_ZERO);
         }
         R.tie = block_sum<unsigned long long>(tsum, redu);
-        // ---- table path set-up: value -> table index hash, f(value) per entry (the weights come from st_lo)
+        // ---- table path set-up: value -> table index hash, per-entry weights and f(value)
         const bool table = D <= DT_CAP;
         if (table) {
             for (int a = tid; a < DT_HASH; a += OVO_THREADS) hkv[a] = make_uint2(0u, 0u);  // +0.0f is never staged
@@ -313,6 +439,10 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
             for (int a = tid; a < D; a += OVO_THREADS) {
                 const float v = key2f(st_key[a]);
                 dval[a] = fc_val<LOG1P>(v);
+                const uint32_t mult = (uint32_t)(st_lo[a + 1] - st_lo[a]);
+                const uint32_t gt = (uint32_t)(nref_nz - st_lo[a + 1]) + ((st_key[a] < KEY_ZERO) ? (uint32_t)R.zeros : 0u);
+                dwt[a] = 2u * gt + mult;
+                dmult[a] = mult;
                 const uint32_t bits = __float_as_uint(v);
                 uint32_t h = (bits * 2654435761u) >> 24;
                 while (atomicCAS(&hkv[h].x, 0u, bits) != 0u) h = (h + 1) & (DT_HASH - 1);
@@ -323,13 +453,35 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
 
         // ================= phase 2: perturbations, in chunks of GROUP_CHUNK groups =================
         for (int g0 = 0; g0 < G; g0 += GROUP_CHUNK) {
-            const int g1 = min(G, g0 + GROUP_CHUNK);
+            const int g1 = min(G, g0 + GROUP_CHUNK), ng = g1 - g0;
             int* cnt_m = counters + 2 * (cc % 3);      // [0] medium list length, [1] big list length
             int* m_max = mmax3 + (cc % 3);             // largest non-zero count among the chunk's warp-tier groups
             if (tid == 0) { const int nx = (cc + 1) % 3; counters[2 * nx] = 0; counters[2 * nx + 1] = 0; mmax3[nx] = 0; }
             ++cc;
+            // ---- the chunk's groups in order of their non-zero count (counting sort over MBINS bins): the 32 groups a
+            // warp works on at a time then have about the same length, so its lanes finish together
+            for (int i = tid; i < MBINS; i += OVO_THREADS) mh[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < ng; i += OVO_THREADS) {
+                const int g = g0 + i;
+                int m = 0;
+                for (int s = pl.group_seg[g]; s < pl.group_seg[g + 1]; ++s) m += (int)cnt[s];
+                marr[i] = (uint16_t)min(m, 65535);
+                atomicAdd(&mh[min(m, MBINS - 1)], 1);
+            }
+            __syncthreads();
+            if (w == 0) {   // exclusive scan of the MBINS counts
+                const int c0 = mh[2 * lane], c1 = mh[2 * lane + 1];
+                const uint32_t incl = warp_incl_scan((uint32_t)(c0 + c1), lane);
+                mh[2 * lane] = (int)incl - c0 - c1;
+                mh[2 * lane + 1] = (int)incl - c1;
+            }
+            __syncthreads();
+            for (int i = tid; i < ng; i += OVO_THREADS) order[atomicAdd(&mh[min((int)marr[i], MBINS - 1)], 1)] = (uint16_t)i;
+            __syncthreads();
             // ---- one thread per group
-            for (int g = g0 + tid; g < g1; g += OVO_THREADS) {
+            for (int i = tid; i < ng; i += OVO_THREADS) {
+                const int gi = order[i], g = g0 + gi;
                 if (g == ref) {
                     // control row: the sparse kernels' convention (ovo/sparse_ovo.py:140-143); fold change of the
                     // control against itself (utils/math.py:191-192)
@@ -343,8 +495,8 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                     continue;
                 }
                 const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
-                int m = 0;
-                for (int s = s0; s < s1; ++s) m += (int)cnt[s];
+                int m = marr[gi];
+                if (m == 65535) { m = 0; for (int s = s0; s < s1; ++s) m += (int)cnt[s]; }
                 const bool big_pair = R.n_ref + (long long)pl.group_size[g] > 208063;  // tie sum may pass 2^53
                 bool done = false;
                 if (table && !big_pair && pl.group_size[g] < 65536) {
@@ -387,31 +539,39 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                     };
                     for (int s = s0; s < s1 && ok; ++s) {
                         const int c = (int)cnt[s];
-                        const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);  // 32-byte aligned slot
-                        const int nfull = c >> 2;
-                        float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int i4 = 0; i4 < nfull; ++i4) {
-                            const float4 q4 = nxt;
-                            if (4 * i4 + 4 < c) nxt = src4[i4 + 1];  // next 16 bytes are in flight while these are ranked
-                            bump(q4.x); bump(q4.y); bump(q4.z); bump(q4.w);
+                        const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);  // 32-byte aligned, padded slot
+                        const int n4 = (c + 3) >> 2;
+                        // two 16-byte loads (one 32-byte sector) in flight ahead of the values being counted
+                        float4 q0 = (n4 > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 q1 = (n4 > 1) ? src4[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int i4 = 0; i4 < n4; i4 += 2) {
+                            const float4 a4 = q0, b4 = q1;
+                            if (i4 + 2 < n4) q0 = src4[i4 + 2];
+                            if (i4 + 3 < n4) q1 = src4[i4 + 3];
+                            const float q[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+                            const int left = c - 4 * i4;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (e < left) bump(q[e]);
                         }
-                        const int rem = c & 3;
-                        if (rem > 0) bump(nxt.x);
-                        if (rem > 1) bump(nxt.y);
-                        if (rem > 2) bump(nxt.z);
                     }
                     if (ok) {
                         unsigned long long u2 = 0, tie = 0;
                         double sum = 0.0;
-                        for (int t = 0; t < D; ++t) {
-                            const uint32_t bq = (bins[(t >> 1) * NT] >> ((t & 1) << 4)) & 0xffffu;
-                            if (bq) {
-                                // b (2 gt + a)  and  (a+b)^3 - (a+b) - (a^3 - a) = b (3 a (a + b) + b^2 - 1)
-                                const uint32_t a = (uint32_t)(st_lo[t + 1] - st_lo[t]);
-                                const uint32_t gt = (uint32_t)(nref_nz - st_lo[t + 1]) + ((st_key[t] < KEY_ZERO) ? (uint32_t)R.zeros : 0u);
-                                u2 += (unsigned long long)bq * (unsigned long long)(2u * gt + a);
-                                tie += (unsigned long long)bq * (3ull * a * ((unsigned long long)a + bq) + (unsigned long long)bq * bq - 1ull);
-                                sum += (double)bq * dval[t];
+                        for (int q = 0; q < nwords; ++q) {
+                            const uint32_t wd = bins[q * NT];
+                            if (wd == 0u) continue;
+#pragma unroll
+                            for (int hsel = 0; hsel < 2; ++hsel) {
+                                const uint32_t bq = hsel ? (wd >> 16) : (wd & 0xffffu);
+                                if (bq) {
+                                    // b (2 gt + a)  and  (a+b)^3 - (a+b) - (a^3 - a) = b (3 a (a + b) + b^2 - 1)
+                                    const int t = 2 * q + hsel;
+                                    const uint32_t a = dmult[t];
+                                    u2 += (unsigned long long)bq * (unsigned long long)dwt[t];
+                                    tie += (unsigned long long)bq * (3ull * a * ((unsigned long long)a + bq) + (unsigned long long)bq * bq - 1ull);
+                                    sum += (double)bq * dval[t];
+                                }
                             }
                         }
                         for (int x = 0; x < ne; ++x) {  // absent from the control: a = 0, position by binary search
@@ -424,14 +584,19 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                         done = true;
                     }
                 } else if (!table && !big_pair && m <= STREAM_MAX) {
-                    // ---- stream tier: every value ranked on arrival; exact as long as the group's values are pairwise
-                    // different (private key hash: slot q of the thread at scratch[q * NT + tid])
+                    // ---- stream tier: every value is ranked on arrival.  The k-th occurrence of a value inside the group
+                    // (a = its multiplicity in the control) adds 2 gt + a to 2U and (a+k)^3 - (a+k) - ((a+k-1)^3 - (a+k-1)) =
+                    // 3 (a+k) (a+k-1) to the tie term -- the sums telescope to the per-run formulas, so no sort is needed;
+                    // k comes from a private hash of 16 buckets x 2 key slots (slot q of the thread at
+                    // scratch[q * NT + tid]) with the occurrence count of slot q in byte q of the words behind them
+                    // (log-normalised counts repeat values often: small integer counts over integer library sizes).
                     uint32_t* hs = scratch + tid;
+                    const uint32_t hs_s = (uint32_t)__cvta_generic_to_shared(hs);
+                    const uint32_t hc_s = hs_s + STREAM_SLOTS * (NT * 4u);
 #pragma unroll
-                    for (int q = 0; q < STREAM_SLOTS; ++q) hs[q * NT] = 0u;
+                    for (int q = 0; q < STREAM_SLOTS + STREAM_SLOTS / 4; ++q) hs[q * NT] = 0u;
                     unsigned long long u2 = 0, tie = 0;
                     double sum = 0.0;
-                    bool dup = false;
                     auto take = [&](float v) {
                         uint32_t key = f2key(v);
                         if (key == 0u) key = 1u;                                   // (only a NaN payload maps to 0)
@@ -440,38 +605,43 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                         const uint32_t a = (uint32_t)(hi - lo);
                         const uint32_t gt = (uint32_t)(R.nnz - hi) + ((key < KEY_ZERO) ? (uint32_t)R.zeros : 0u);
                         u2 += (unsigned long long)(2u * gt + a);
-                        if (a) tie += 3ull * a * ((unsigned long long)a + 1ull);    // (a+1)^3 - (a+1) - (a^3 - a)
                         sum += fc_val<LOG1P>(v);
-                        uint32_t h = (key * 2654435761u) >> 27;
+                        uint32_t bkt = (key * 2654435761u) >> 28, slot;
                         for (;;) {
-                            const uint32_t kk = hs[h * NT];
-                            if (kk == 0u) { hs[h * NT] = key; break; }
-                            if (kk == key) { dup = true; break; }
-                            h = (h + 1) & (STREAM_SLOTS - 1);
+                            const uint32_t a0 = hs_s + (2u * bkt) * (NT * 4u), a1 = a0 + NT * 4u;
+                            const uint32_t k0 = lds_u32(a0), k1 = lds_u32(a1);
+                            if (k0 == key) { slot = 2u * bkt; break; }
+                            if (k1 == key) { slot = 2u * bkt + 1u; break; }
+                            if (k0 == 0u) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a0), "r"(key) : "memory"); slot = 2u * bkt; break; }
+                            if (k1 == 0u) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a1), "r"(key) : "memory"); slot = 2u * bkt + 1u; break; }
+                            bkt = (bkt + 1u) & 15u;
                         }
+                        const uint32_t ca = hc_s + (slot >> 2) * (NT * 4u) + (slot & 3u);
+                        uint32_t k;
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(k) : "r"(ca) : "memory");
+                        k += 1u;
+                        asm volatile("st.shared.u8 [%0], %1;" :: "r"(ca), "r"(k) : "memory");
+                        const unsigned long long t = (unsigned long long)a + k;
+                        if (t > 1ull) tie += 3ull * t * (t - 1ull);
                     };
                     for (int s = s0; s < s1; ++s) {
                         const int c = (int)cnt[s];
                         const float4* src4 = reinterpret_cast<const float4*>(vals + pl.seg_base[s]);
-                        const int nfull = c >> 2;
                         float4 nxt = (c > 0) ? src4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int i4 = 0; i4 < nfull; ++i4) {
+                        for (int i4 = 0; 4 * i4 < c; ++i4) {
                             const float4 q4 = nxt;
                             if (4 * i4 + 4 < c) nxt = src4[i4 + 1];
-                            take(q4.x); take(q4.y); take(q4.z); take(q4.w);
+                            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (4 * i4 + e < c) take(q[e]);
                         }
-                        const int rem = c & 3;
-                        if (rem > 0) take(nxt.x);
-                        if (rem > 1) take(nxt.y);
-                        if (rem > 2) take(nxt.z);
                     }
-                    if (!dup) {
-                        finalize_group(P, R, j, g, m, u2, tie, sum);
-                        done = true;
-                    }
+                    finalize_group(P, R, j, g, m, u2, tie, sum);
+                    done = true;
                 }
                 if (!done) {  // a whole warp (or the CTA) ranks this group by sorting it
-                    mlist[atomicAdd(&cnt_m[0], 1)] = (uint16_t)(g - g0);
+                    mlist[atomicAdd(&cnt_m[0], 1)] = (uint16_t)gi;
                     atomicMax(m_max, m);
                 }
             }
@@ -487,7 +657,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
                 int m = 0;
                 for (int s = s0; s < s1; ++s) m += (int)cnt[s];
-                if (m > WARP_CAP) {
+                if (m > WARP_CAP || (R.keys == nullptr && R.n_ref + (long long)pl.group_size[g] > 208063)) {
                     if (lane == 0) blist[atomicAdd(&cnt_m[1], 1)] = (uint16_t)(g - g0);
                     continue;
                 }
@@ -496,7 +666,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 for (int s = s0; s < s1; ++s) {
                     const int c = (int)cnt[s];
                     const float* src = vals + pl.seg_base[s];
-                    for (int i = lane; i < c; i += 32) buf[k + i] = f2key(src[i]);
+                    for (int i = lane; i < c; i += 32) { uint32_t key = f2key(src[i]); buf[k + i] = key ? key : 1u; }
                     k += c;
                 }
                 const int Pw = next_pow2(m);
@@ -529,7 +699,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 for (int s = s0; s < s1; ++s) {
                     const int c = (int)cnt[s];
                     const float* src = vals + pl.seg_base[s];
-                    for (int i = tid; i < c; i += OVO_THREADS) gA[m + i] = f2key(src[i]);
+                    for (int i = tid; i < c; i += OVO_THREADS) { uint32_t key = f2key(src[i]); gA[m + i] = key ? key : 1u; }
                     m += c;
                 }
                 __syncthreads();
@@ -571,10 +741,11 @@ static int launch_ovo_t(OvoParams& P, const illico_plan_t* plan, void* workspace
     constexpr int NW = NT / 32;
     // shared memory: control buffer + scratch + fixed part.  Genes whose control has more non-zeros than REF_CAP
     // keep the control in the CTA's global slab.
-    const size_t fixed = (size_t)(NW * 256 + RADIX_AUX_WORDS + GROUP_CHUNK + 8) * 4 + 32 * 8 * 2 + DT_CAP * 8 + DT_HASH * 8 +
+    const size_t fixed = (size_t)(NW * 256 + RADIX_AUX_WORDS + 2 * GROUP_CHUNK + 8 + MBINS) * 4 + 32 * 8 * 2 + DT_CAP * 16 + DT_HASH * 8 +
                          (2 * ST_CAP + 1) * 4 + 64;
     int scratch_words = (DT_CAP / 2 + 2 * NE_CAP) * NT;              // table path: bins + extras per thread
-    if (scratch_words < STREAM_SLOTS * NT) scratch_words = STREAM_SLOTS * NT;
+    if (scratch_words < (STREAM_SLOTS + STREAM_SLOTS / 4) * NT) scratch_words = (STREAM_SLOTS + STREAM_SLOTS / 4) * NT;
+    if (scratch_words < 2 * HCAP) scratch_words = 2 * HCAP;          // distinct-value hash of a large control
     if (scratch_words < 2 * WARP_CAP) scratch_words = 2 * WARP_CAP;  // at least two warp-tier buffers
     const size_t need = fixed + (size_t)(REF_CAP + scratch_words) * 4;
     if (need > (size_t)max_smem) { set_error("ovo_kernel needs %zu bytes of shared memory", need); return 1; }

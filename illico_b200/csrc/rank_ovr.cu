@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
             double* o = P.results + (long long)g * P.gstride + (long long)j * 3;
             const double sum = o[2];
             const long long n_t = pl.group_size[g];
-            const double mu_t = sum / (double)n_t;
+            const double mu_t = sum * (1.0 / (double)n_t);   // (the fused epilogue's form: every path gives the same bits)
             const double mu_r = (total - sum) / (double)(n - n_t);
             o[2] = (mu_r == 0.0) ? INFINITY : mu_t / mu_r;
         }
@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
             const double U = (double)u2 / 2.0;
             const double mu = (double)(n_r * n_t) / 2.0;
             const double p = compute_pval(n_r, n_t, n, P.flags.tie_correct ? tie : 0.0, U, mu, cc, P.flags.alternative);
-            const double mu_t = sum / (double)n_t;
+            const double mu_t = sum * (1.0 / (double)n_t);   // (the fused epilogue's form: every path gives the same bits)
             // exactly zero when the group holds every non-zero of the gene (see fused_epilogue_kernel)
             const double mu_r = (nnz_g == nnz) ? 0.0 : (total - sum) / (double)(n - n_t);
             double* o = P.results + (long long)g * P.gstride + (long long)j * 3;

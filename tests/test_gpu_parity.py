@@ -760,3 +760,43 @@ def test_optional_columns_p_adj_and_log2fc():
     np.testing.assert_allclose(df["p_adj"].to_numpy().reshape(G, N), want, rtol=1e-15, atol=0)
     with np.errstate(divide="ignore", invalid="ignore"):
         np.testing.assert_array_equal(df["log2_fold_change"].to_numpy(), np.log2(df["fold_change"].to_numpy()))
+
+
+@pytest.mark.parametrize("fmt", ["dense", "csr"])
+@pytest.mark.parametrize("log1p", [False, True])
+def test_ovo_stream_tier_with_repeated_values(fmt, log1p):
+    """ovo_kernel's stream tier (control with more than 64 distinct values, groups of at most 28 non-zeros): values that
+    repeat inside a group and values shared with the control -- the telescoped per-element tie terms and the private
+    occurrence hash against the oracle (U and tie sums bit-exact)."""
+    import torch
+
+    from illico_b200 import dispatch, synth
+    from illico_b200.groups import encode_and_count_groups
+
+    rng = np.random.RandomState(77)
+    n, N = 9000, 40
+    labels, _ = synth.perturbation_labels(rng, n, 110, p_control=0.25)
+    X = (np.round(rng.gamma(2.0, 2.0, size=(n, N)) * 8) / 8).astype(np.float32)      # ~150 distinct values per gene
+    X[rng.rand(n, N) < 0.7] = 0
+    X[:, 3] = np.where(rng.rand(n) < 0.3, rng.gamma(2.0, 2.0, n), 0).astype(np.float32)   # no repeats at all
+    if fmt == "dense":
+        X[:, 4] = -X[:, 4]                 # negative values (dense only: the sparse kernels assume stored values > 0)
+    if log1p:
+        X = np.log1p(np.abs(X)).astype(np.float32)
+    Xf = C.to_format(X, fmt)
+    groups, got = _run(Xf, labels, synth.CONTROL, is_log1p=log1p)
+    g, p, U, fc = oracle.run(Xf, labels, synth.CONTROL, is_log1p=log1p)
+    ref_row = int(np.searchsorted(groups, synth.CONTROL))
+    assert_parity(got, (p, U, fc), ref_row=ref_row, fc_rtol=FC_RTOL_LOG1P_F32 if log1p else FC_RTOL, what="stream tier")
+    # exact integers and tie sums through the dispatcher's debug outputs
+    uniq, grpc = encode_and_count_groups(labels, synth.CONTROL)
+    fn = getattr(dispatch, f"{fmt}_ovo_mwu_kernel_over_contiguous_col_chunk")
+    Xd = Xf if fmt == "dense" else dispatch.CSRMatrix(Xf.data, Xf.indices, Xf.indptr, Xf.shape)
+    dbg = {}
+    fn(Xd, 0, N, grpc, log1p, True, True, "two-sided", debug=dbg)
+    _, _, _, _, ties = oracle.run(Xf, labels, synth.CONTROL, is_log1p=log1p, want_ties=True)
+    rows = np.arange(len(groups)) != ref_row
+    np.testing.assert_array_equal(dbg["tie_sum"].cpu().numpy()[rows], ties[rows])
+    np.testing.assert_array_equal(dbg["u2"].cpu().numpy()[rows], (2 * U[rows]).astype(np.int64))
+    dispatch.clear_caches()
+    assert torch.cuda.is_available()
