@@ -65,6 +65,17 @@ struct OvoParams {
     long long* dbg_tie_exact;
 };
 
+// Sorted shared-memory array of n >= 1 keys, described once per gene: p = largest power of two <= n.
+struct SortedS {
+    uint32_t base;   // shared address
+    int n, p;
+};
+__device__ __forceinline__ SortedS sorted_s(uint32_t base, int n) {
+    SortedS a;
+    a.base = base; a.n = n; a.p = (n > 0) ? (1 << (31 - __clz(n))) : 0;
+    return a;
+}
+
 struct RefInfo {
     const uint32_t* keys;  // sorted non-zero control keys (NULL when only the table below was built)
     uint32_t keys_s;       // their shared-memory address, 0 when they live in the CTA's global slab
@@ -81,35 +92,8 @@ struct RefInfo {
     // <= 1024 shared-memory entries whatever the size of the control.
     uint32_t st_key_s, st_lo_s;   // shared-memory addresses
     int st_n;
+    SortedS st, ks;        // search descriptors of the table / of the keys when they are in shared memory
 };
-
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-// lower / upper bound over a sorted shared-memory array (32-bit shared addresses, branch-free body; the trip count
-// only depends on n, so a warp stays converged)
-__device__ __forceinline__ int lb_shared(uint32_t base_s, int n, uint32_t key) {
-    int lo = 0, len = n;
-    while (len > 1) {
-        const int half = len >> 1;
-        lo += (lds_u32(base_s + (uint32_t)(lo + half - 1) * 4u) < key) ? half : 0;
-        len -= half;
-    }
-    if (len == 1) lo += (lds_u32(base_s + (uint32_t)lo * 4u) < key) ? 1 : 0;
-    return lo;
-}
-__device__ __forceinline__ int ub_shared(uint32_t base_s, int n, uint32_t key) {
-    int lo = 0, len = n;
-    while (len > 1) {
-        const int half = len >> 1;
-        lo += (lds_u32(base_s + (uint32_t)(lo + half - 1) * 4u) <= key) ? half : 0;
-        len -= half;
-    }
-    if (len == 1) lo += (lds_u32(base_s + (uint32_t)lo * 4u) <= key) ? 1 : 0;
-    return lo;
-}
 
 template <bool LOG1P>
 __device__ __forceinline__ double fc_val(float v) {
@@ -117,21 +101,91 @@ __device__ __forceinline__ double fc_val(float v) {
     return (double)v;
 }
 
-// position of `key` in the sorted control: [lo, hi) = its run (empty when the control does not have the value)
-__device__ __forceinline__ void rank_pos(const RefInfo& R, uint32_t key, int& lo, int& hi) {
-    if (R.st_n >= 0) {
-        const int t = lb_shared(R.st_key_s, R.st_n, key);
-        lo = (int)lds_u32(R.st_lo_s + (uint32_t)t * 4u);
-        hi = (t < R.st_n && lds_u32(R.st_key_s + (uint32_t)t * 4u) == key) ? (int)lds_u32(R.st_lo_s + (uint32_t)(t + 1) * 4u) : lo;
-    } else if (R.keys_s) {
-        lo = lb_shared(R.keys_s, R.nnz, key);
-        hi = lo;
-        if (lo < R.nnz && lds_u32(R.keys_s + (uint32_t)lo * 4u) == key) hi = ub_shared(R.keys_s, R.nnz, key);
-    } else {
-        lo = lower_bound_u32(R.keys, R.nnz, key);
-        hi = lo;
-        if (lo < R.nnz && R.keys[lo] == key) hi = upper_bound_u32(R.keys, R.nnz, key);
+// shared-memory loads through 32-bit shared addresses.  lds_ro: tables that are constant while they are read (the
+// compiler may schedule these freely, which is what lets several searches overlap); lds_u32: private, read-modify-write
+// data (ordered with the stores)
+__device__ __forceinline__ uint32_t lds_ro(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+// NK lower bounds at once (UPPER: upper bounds): NK independent dependent-load chains in flight per thread.  The trip
+// count only depends on n, so a warp stays converged.  First probe at p - 1 moves the window to [n - p, n) when the answer
+// lies beyond p; the window then halves p -> 1 (the answer stays inside [start, start + width]).
+template <int NK, bool UPPER>
+__device__ __forceinline__ void bound_shared(const SortedS& A, const uint32_t (&key)[NK], int (&out)[NK]) {
+    if (A.n <= 0) {
+#pragma unroll
+        for (int e = 0; e < NK; ++e) out[e] = 0;
+        return;
     }
+    uint32_t a[NK];
+    const uint32_t first = A.base + (uint32_t)(A.p - 1) * 4u, jump = (uint32_t)(A.n - A.p) * 4u;
+#pragma unroll
+    for (int e = 0; e < NK; ++e) {
+        const uint32_t k = lds_ro(first);
+        a[e] = A.base + ((UPPER ? (k <= key[e]) : (k < key[e])) ? jump : 0u);
+    }
+    for (uint32_t step = (uint32_t)A.p * 2u; step >= 4u; step >>= 1) {   // byte steps: p/2 ... 1 elements
+        uint32_t k[NK];
+#pragma unroll
+        for (int e = 0; e < NK; ++e) k[e] = lds_ro(a[e] + step - 4u);
+#pragma unroll
+        for (int e = 0; e < NK; ++e) a[e] += (UPPER ? (k[e] <= key[e]) : (k[e] < key[e])) ? step : 0u;
+    }
+#pragma unroll
+    for (int e = 0; e < NK; ++e) {
+        const uint32_t k = lds_ro(a[e]);
+        out[e] = (int)((a[e] - A.base) >> 2) + ((UPPER ? (k <= key[e]) : (k < key[e])) ? 1 : 0);
+    }
+}
+__device__ __forceinline__ int lb_shared(uint32_t base_s, int n, uint32_t key) {
+    const uint32_t k1[1] = {key};
+    int o[1];
+    bound_shared<1, false>(sorted_s(base_s, n), k1, o);
+    return o[0];
+}
+
+// position of NK keys in the sorted control: [lo, hi) = the key's run (empty when the control does not have the value)
+template <int NK>
+__device__ __forceinline__ void rank_pos_n(const RefInfo& R, const uint32_t (&key)[NK], int (&lo)[NK], int (&hi)[NK]) {
+    if (R.st_n >= 0) {
+        int t[NK];
+        bound_shared<NK, false>(R.st, key, t);
+#pragma unroll
+        for (int e = 0; e < NK; ++e) {
+            lo[e] = (int)lds_ro(R.st_lo_s + (uint32_t)t[e] * 4u);
+            const bool eq = t[e] < R.st_n && lds_ro(R.st_key_s + (uint32_t)t[e] * 4u) == key[e];
+            hi[e] = eq ? (int)lds_ro(R.st_lo_s + (uint32_t)(t[e] + 1) * 4u) : lo[e];
+        }
+    } else if (R.keys_s) {
+        bound_shared<NK, false>(R.ks, key, lo);
+        bool any_eq = false;
+#pragma unroll
+        for (int e = 0; e < NK; ++e) {
+            hi[e] = lo[e];
+            any_eq |= lo[e] < R.nnz && lds_ro(R.keys_s + (uint32_t)lo[e] * 4u) == key[e];
+        }
+        if (any_eq) bound_shared<NK, true>(R.ks, key, hi);
+    } else {
+#pragma unroll
+        for (int e = 0; e < NK; ++e) {
+            lo[e] = lower_bound_u32(R.keys, R.nnz, key[e]);
+            hi[e] = lo[e];
+            if (lo[e] < R.nnz && R.keys[lo[e]] == key[e]) hi[e] = upper_bound_u32(R.keys, R.nnz, key[e]);
+        }
+    }
+}
+__device__ __forceinline__ void rank_pos(const RefInfo& R, uint32_t key, int& lo, int& hi) {
+    const uint32_t k1[1] = {key};
+    int l[1], h[1];
+    rank_pos_n<1>(R, k1, l, h);
+    lo = l[0]; hi = h[0];
 }
 
 // contribution of one distinct perturbation value (key, multiplicity b)
@@ -288,7 +342,9 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
         R.st_key_s = (uint32_t)__cvta_generic_to_shared(st_key);
         R.st_lo_s = (uint32_t)__cvta_generic_to_shared(st_lo);
         R.st_n = -1;
+        R.st = sorted_s(R.st_key_s, 0);
         R.keys = nullptr; R.keys_s = 0u;
+        R.ks = sorted_s(0u, 0);
         double rsum = 0.0;
         int D = 0;
         bool hashed = false;
@@ -358,6 +414,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 __syncthreads();
                 hashed = true;
                 R.st_n = D;
+                R.st = sorted_s(R.st_key_s, D);
             } else {
                 rsum = 0.0;   // recomputed by the sort path below
             }
@@ -386,6 +443,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
             }
             R.keys = rA;
             R.keys_s = ref_smem ? (uint32_t)__cvta_generic_to_shared(rA) : 0u;
+            R.ks = sorted_s(R.keys_s, ref_smem ? nref_nz : 0);
             // distinct control values: how many, then (when they fit) the ordered search table
             int heads = 0;
             for (int i = tid; i < nref_nz; i += OVO_THREADS) heads += (i == 0 || rA[i - 1] != rA[i]) ? 1 : 0;
@@ -411,6 +469,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 }
                 if (tid == 0) st_lo[D] = nref_nz;
                 R.st_n = D;
+                R.st = sorted_s(R.st_key_s, D);
                 __syncthreads();
             }
         }
@@ -597,32 +656,44 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                     for (int q = 0; q < STREAM_SLOTS + STREAM_SLOTS / 4; ++q) hs[q * NT] = 0u;
                     unsigned long long u2 = 0, tie = 0;
                     double sum = 0.0;
-                    auto take = [&](float v) {
-                        uint32_t key = f2key(v);
-                        if (key == 0u) key = 1u;                                   // (only a NaN payload maps to 0)
-                        int lo, hi;
-                        rank_pos(R, key, lo, hi);
-                        const uint32_t a = (uint32_t)(hi - lo);
-                        const uint32_t gt = (uint32_t)(R.nnz - hi) + ((key < KEY_ZERO) ? (uint32_t)R.zeros : 0u);
-                        u2 += (unsigned long long)(2u * gt + a);
-                        sum += fc_val<LOG1P>(v);
-                        uint32_t bkt = (key * 2654435761u) >> 28, slot;
-                        for (;;) {
-                            const uint32_t a0 = hs_s + (2u * bkt) * (NT * 4u), a1 = a0 + NT * 4u;
-                            const uint32_t k0 = lds_u32(a0), k1 = lds_u32(a1);
-                            if (k0 == key) { slot = 2u * bkt; break; }
-                            if (k1 == key) { slot = 2u * bkt + 1u; break; }
-                            if (k0 == 0u) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a0), "r"(key) : "memory"); slot = 2u * bkt; break; }
-                            if (k1 == 0u) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a1), "r"(key) : "memory"); slot = 2u * bkt + 1u; break; }
-                            bkt = (bkt + 1u) & 15u;
+                    // four values at a time: their searches are independent load chains and overlap; the occurrence hash
+                    // is updated one value after the other
+                    auto take4 = [&](const float4 q4, int nv) {
+                        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+                        uint32_t key[4];
+                        int lo[4], hi[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            key[e] = (e < nv) ? f2key(q[e]) : 0xffffffffu;
+                            if (key[e] == 0u) key[e] = 1u;                         // (only a NaN payload maps to 0)
                         }
-                        const uint32_t ca = hc_s + (slot >> 2) * (NT * 4u) + (slot & 3u);
-                        uint32_t k;
-                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(k) : "r"(ca) : "memory");
-                        k += 1u;
-                        asm volatile("st.shared.u8 [%0], %1;" :: "r"(ca), "r"(k) : "memory");
-                        const unsigned long long t = (unsigned long long)a + k;
-                        if (t > 1ull) tie += 3ull * t * (t - 1ull);
+                        rank_pos_n<4>(R, key, lo, hi);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (e < nv) {
+                                const uint32_t a = (uint32_t)(hi[e] - lo[e]);
+                                const uint32_t gt = (uint32_t)(R.nnz - hi[e]) + ((key[e] < KEY_ZERO) ? (uint32_t)R.zeros : 0u);
+                                u2 += (unsigned long long)(2u * gt + a);
+                                sum += fc_val<LOG1P>(q[e]);
+                                uint32_t bkt = (key[e] * 2654435761u) >> 28, slot;
+                                for (;;) {
+                                    const uint32_t a0 = hs_s + (2u * bkt) * (NT * 4u), a1 = a0 + NT * 4u;
+                                    const uint32_t k0 = lds_u32(a0), k1 = lds_u32(a1);
+                                    if (k0 == key[e]) { slot = 2u * bkt; break; }
+                                    if (k1 == key[e]) { slot = 2u * bkt + 1u; break; }
+                                    if (k0 == 0u) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a0), "r"(key[e]) : "memory"); slot = 2u * bkt; break; }
+                                    if (k1 == 0u) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a1), "r"(key[e]) : "memory"); slot = 2u * bkt + 1u; break; }
+                                    bkt = (bkt + 1u) & 15u;
+                                }
+                                const uint32_t ca = hc_s + (slot >> 2) * (NT * 4u) + (slot & 3u);
+                                uint32_t k;
+                                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(k) : "r"(ca) : "memory");
+                                k += 1u;
+                                asm volatile("st.shared.u8 [%0], %1;" :: "r"(ca), "r"(k) : "memory");
+                                const unsigned long long t = (unsigned long long)a + k;
+                                if (t > 1ull) tie += 3ull * t * (t - 1ull);
+                            }
+                        }
                     };
                     for (int s = s0; s < s1; ++s) {
                         const int c = (int)cnt[s];
@@ -631,10 +702,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                         for (int i4 = 0; 4 * i4 < c; ++i4) {
                             const float4 q4 = nxt;
                             if (4 * i4 + 4 < c) nxt = src4[i4 + 1];
-                            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (4 * i4 + e < c) take(q[e]);
+                            take4(q4, min(4, c - 4 * i4));
                         }
                     }
                     finalize_group(P, R, j, g, m, u2, tie, sum);
