@@ -668,6 +668,18 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                             if (key[e] == 0u) key[e] = 1u;                         // (only a NaN payload maps to 0)
                         }
                         rank_pos_n<4>(R, key, lo, hi);
+                        // occurrence hash: the four buckets are probed together (eight loads in flight); a value is then
+                        // resolved against what it loaded unless an earlier value of this quadruple wrote to its bucket.
+                        // The count byte of a slot is only touched from the second occurrence on (0 = seen once).
+                        uint32_t bk[4], k0[4], k1[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            bk[e] = (key[e] * 2654435761u) >> 28;
+                            const uint32_t a0 = hs_s + (2u * bk[e]) * (NT * 4u);
+                            k0[e] = lds_u32(a0);
+                            k1[e] = lds_u32(a0 + NT * 4u);
+                        }
+                        uint32_t dirty = 0u;                                      // buckets written by this quadruple
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             if (e < nv) {
@@ -675,21 +687,29 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                                 const uint32_t gt = (uint32_t)(R.nnz - hi[e]) + ((key[e] < KEY_ZERO) ? (uint32_t)R.zeros : 0u);
                                 u2 += (unsigned long long)(2u * gt + a);
                                 sum += fc_val<LOG1P>(q[e]);
-                                uint32_t bkt = (key[e] * 2654435761u) >> 28, slot;
+                                uint32_t bkt = bk[e], c0 = k0[e], c1 = k1[e], k = 1u;
+                                bool fresh = ((dirty >> bkt) & 1u) == 0u;
                                 for (;;) {
                                     const uint32_t a0 = hs_s + (2u * bkt) * (NT * 4u), a1 = a0 + NT * 4u;
-                                    const uint32_t k0 = lds_u32(a0), k1 = lds_u32(a1);
-                                    if (k0 == key[e]) { slot = 2u * bkt; break; }
-                                    if (k1 == key[e]) { slot = 2u * bkt + 1u; break; }
-                                    if (k0 == 0u) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a0), "r"(key[e]) : "memory"); slot = 2u * bkt; break; }
-                                    if (k1 == 0u) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a1), "r"(key[e]) : "memory"); slot = 2u * bkt + 1u; break; }
-                                    bkt = (bkt + 1u) & 15u;
+                                    if (!fresh) { c0 = lds_u32(a0); c1 = lds_u32(a1); }
+                                    const bool hit0 = c0 == key[e], hit1 = c1 == key[e];
+                                    if (hit0 || hit1) {                                   // seen before: k-th occurrence
+                                        const uint32_t slot = 2u * bkt + (hit0 ? 0u : 1u);
+                                        const uint32_t ca = hc_s + (slot >> 2) * (NT * 4u) + (slot & 3u);
+                                        uint32_t cnt8;
+                                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cnt8) : "r"(ca) : "memory");
+                                        k = cnt8 + 2u;
+                                        asm volatile("st.shared.u8 [%0], %1;" :: "r"(ca), "r"(cnt8 + 1u) : "memory");
+                                        break;
+                                    }
+                                    if (c0 == 0u || c1 == 0u) {
+                                        asm volatile("st.shared.u32 [%0], %1;" :: "r"(c0 == 0u ? a0 : a1), "r"(key[e]) : "memory");
+                                        dirty |= 1u << bkt;
+                                        break;
+                                    }
+                                    bkt = (bkt + 1u) & 15u;                               // bucket full of other values
+                                    fresh = false;
                                 }
-                                const uint32_t ca = hc_s + (slot >> 2) * (NT * 4u) + (slot & 3u);
-                                uint32_t k;
-                                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(k) : "r"(ca) : "memory");
-                                k += 1u;
-                                asm volatile("st.shared.u8 [%0], %1;" :: "r"(ca), "r"(k) : "memory");
                                 const unsigned long long t = (unsigned long long)a + k;
                                 if (t > 1ull) tie += 3ull * t * (t - 1ull);
                             }
@@ -793,6 +813,11 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
     }
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // workspace: [gene counter | per-group constants | per-CTA slabs]
 static size_t ovo_head_bytes(const illico_plan_t* plan) {
@@ -868,6 +893,11 @@ int launch_ovo_mapped(const float* ir_vals, const uint32_t* ir_cnt, int n_genes,
     P.n_genes_dev = n_genes_dev; P.gene_map = gene_map;
     P.dbg_u2 = dbg ? (long long*)dbg->u2 : nullptr; P.dbg_tie = dbg ? dbg->tie_sum : nullptr;
     P.dbg_tie_exact = dbg ? (long long*)dbg->tie_exact : nullptr;
+    static const int nt = env_int("ILLICO_OVO_THREADS", 256);
+    if (nt == 512) {
+        if (flags->is_log1p) return launch_ovo_t<512, 2, true>(P, plan, workspace, workspace_bytes, sms, max_smem, stream);
+        return launch_ovo_t<512, 2, false>(P, plan, workspace, workspace_bytes, sms, max_smem, stream);
+    }
     if (flags->is_log1p) return launch_ovo_t<256, 3, true>(P, plan, workspace, workspace_bytes, sms, max_smem, stream);
     return launch_ovo_t<256, 3, false>(P, plan, workspace, workspace_bytes, sms, max_smem, stream);
 }
