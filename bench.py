@@ -529,6 +529,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from illico_b200 import hostio
+
+        hostio.bind_thread_to_device_node(local)   # pinned host buffers are then first-touched next to this rank's GPU
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- headline workload: weak scaling, every rank owns a full-size gene shard

@@ -169,7 +169,12 @@ def h2d_2d(dst: torch.Tensor, src: np.ndarray, n_threads: int | None = None) -> 
         src = np.ascontiguousarray(src)
     cur = torch.cuda.current_stream(device)
     if is_pinned(src):
-        copy2d_async(dst.data_ptr(), b * item, src.__array_interface__["data"][0], src.strides[0], b * item, n, "h2d", cur)
+        if src.strides[0] == b * item:      # contiguous: one linear asynchronous copy
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                dst.copy_(torch.from_numpy(src), non_blocking=True)
+        else:                               # a column shard of a wider matrix: strided DMA
+            copy2d_async(dst.data_ptr(), b * item, src.__array_interface__["data"][0], src.strides[0], b * item, n, "h2d", cur)
         return Pending(device)
     row_bytes = b * item
     if n * row_bytes <= (4 << 20) or row_bytes > CHUNK_BYTES:   # small (or absurdly wide rows): the driver's own staged copy
