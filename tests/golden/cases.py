@@ -106,6 +106,35 @@ def _highcount():
     return X, labels, "g7"
 
 
+def _c4_clusters():
+    """BASELINE config 4 structure: one-versus-rest over 50 clusters, every cluster (1 200-1 400 cells) cut into several
+    plan segments (multi-segment groups on the fused paths, multi-segment records of the table kernels)."""
+    rng = np.random.RandomState(17)
+    n, N = 65_000, 20
+    X = (rng.poisson(1.0, size=(n, N)) * (rng.rand(n, N) >= 0.85)).astype(np.float32)
+    X[:, 4] = rng.poisson(20.0, n) * (rng.rand(n) >= 0.3)                  # a high-count gene: general path
+    X[:, 9] = np.where(rng.rand(n) < 0.1, rng.gamma(2.0, 2.0, n), 0.0)      # continuous non-zeros
+    labels = synth.cluster_labels(18, n, 50)
+    return X, labels, labels[0]
+
+
+def _c5_many_groups():
+    """BASELINE config 5 structure: 10 000 perturbations + control (10 001 groups of ~12 cells, a control of 5 000 cut
+    into ten segments), CSR."""
+    rng = np.random.RandomState(19)
+    n_perts, per, n_ctrl, N = 10_000, 12, 5_000, 10
+    width = len(str(n_perts - 1))
+    codes = np.concatenate([np.repeat(np.arange(n_perts), per), np.full(n_ctrl, n_perts)])
+    rng.shuffle(codes)
+    names = np.array([f"p{i:0{width}d}" for i in range(n_perts)] + [synth.CONTROL])
+    labels = names[codes].tolist()
+    n = codes.size
+    X = (rng.poisson(1.0, size=(n, N)) * (rng.rand(n, N) >= 0.9)).astype(np.float32)
+    X[:, 3] = np.where(rng.rand(n) < 0.1, np.round(rng.gamma(2.0, 2.0, n) * 4) / 4, 0.0)   # ~60 distinct values
+    X[:, 7] = rng.poisson(15.0, n) * (rng.rand(n) >= 0.5)
+    return X, labels, synth.CONTROL
+
+
 def _grid(fmts, tests, ccs=(True,), tcs=(True,), alts=("two-sided",), log1p=(False,)):
     return list(itertools.product(fmts, tests, ccs, tcs, alts, log1p))
 
@@ -125,6 +154,8 @@ CASES = {
     "log1p64": (_log1p64, _grid(ALL_FMT, BOTH, log1p=(True,)), 10),
     "batched": (_batched, _grid(ALL_FMT, BOTH), 128),
     "highcount": (_highcount, _grid(ALL_FMT, BOTH, alts=("two-sided", "greater")), 16),
+    "c4_clusters": (_c4_clusters, _grid(("csc", "dense", "csr"), ("ovr",)) + _grid(("csc",), ("ovo",)), 8),
+    "c5_many_groups": (_c5_many_groups, _grid(("csr", "dense"), ("ovo",)) + _grid(("csr",), ("ovr",)), 5),
 }
 
 
