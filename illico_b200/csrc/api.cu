@@ -207,12 +207,10 @@ size_t illico_rank_workspace_bytes(const illico_plan_t* plan, int32_t n_genes_ba
     size_t rank = ctas * per_cta + 256 + (((size_t)(n_genes_batch > 0 ? n_genes_batch : 1) + 64) * sizeof(int) + 255);
     if (plan->ref_group < 0) rank += 2 * ctas * ovr_table_rec_bytes(plan) + 256;  // table kernel: up to 8 CTAs per SM
     else rank += 1024 + ((size_t)plan->n_groups + 64) * 5 * sizeof(double);       // gene counter + per-group constants
-    size_t stage = stage_csr_workspace_bytes(plan, n_genes_batch);  // CSR staging reuses the same scratch
-    {                                                                // so do the fused paths' per-gene tables
-        const size_t fused = ovo_fused_workspace_bytes(n_genes_batch > 0 ? n_genes_batch : 1, plan->n_groups);
-        if (fused > stage) stage = fused;
-    }
-    return rank > stage ? rank : stage;
+    const size_t stage = stage_csr_workspace_bytes(plan, n_genes_batch);  // CSR staging reuses the rank kernels' scratch
+    // the fused paths keep their per-gene tables in front of that scratch until the handed-back genes have been ranked
+    const size_t fused = (ovo_fused_workspace_bytes(n_genes_batch > 0 ? n_genes_batch : 1, plan->n_groups) + 511) & ~(size_t)255;
+    return fused + (rank > stage ? rank : stage);
 }
 
 int illico_rank_ovr(const float* ir_vals, const uint32_t* ir_cnt, int32_t n_genes_batch, const illico_plan_t* plan,

@@ -33,16 +33,19 @@
 
 #include <stdlib.h>
 
-#include <vector>
-
 namespace illico {
 
 // general path (stage.cu, rank_ovo.cu, rank_ovr.cu) for the genes the fused path hands back
-int launch_stage_dense(const float*, long long, int, int, const illico_plan_t*, float*, uint32_t*, cudaStream_t);
-int launch_ovo(const float*, const uint32_t*, int, const illico_plan_t*, const illico_flags_t*, double*, long long, void*,
-               size_t, const illico_debug_t*, cudaStream_t);
-int launch_ovr(const float*, const uint32_t*, int, const illico_plan_t*, const illico_flags_t*, double*, long long, void*,
-               size_t, const illico_debug_t*, cudaStream_t);
+int launch_stage_dense_list(const float* X, long long ld, int gene_lb, const int* list, const int* n_list_dev,
+                            const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, cudaStream_t stream);
+int launch_stage_csr_if(const float*, const int32_t*, const long long*, int, int, const illico_plan_t*, float*, uint32_t*, void*, size_t,
+                        const int*, int, cudaStream_t);
+int launch_stage_csr_list(const float*, const int32_t*, const long long*, int, int, const int*, const int*, int, int,
+                          const illico_plan_t*, float*, uint32_t*, cudaStream_t);
+int launch_ovo_mapped(const float*, const uint32_t*, int, const int*, const int*, int, const illico_plan_t*, const illico_flags_t*, double*,
+                      long long, void*, size_t, const illico_debug_t*, cudaStream_t);
+int launch_ovr_mapped(const float*, const uint32_t*, int, const int*, const int*, int, const illico_plan_t*, const illico_flags_t*, double*,
+                      long long, void*, size_t, const illico_debug_t*, cudaStream_t);
 bool stage_dense_tma_ok(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan);
 int launch_stage_dense_tma(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
                            uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream, int segs_per_cta = 0);
@@ -64,16 +67,19 @@ struct Gtab {
     uint32_t* nnz;             // [bs]        OVO: control non-zeros; OVR: doubled mid-rank of the zero block
     unsigned long long* tie;   // [bs]        OVO: sum over control runs of a^3 - a; OVR: f64 bits of the gene's tie correction
     double* sum;               // [bs]        OVO: sum of f(x) over the control; OVR: over all cells
-    int* n_bad;                // [1]         genes flagged by the table kernel
+    int* n_bad;                // [16]        control block: [0] genes flagged so far, [1] length of `list`, [2] hand-back mode
+    int* list;                 // [bs]        the genes handed back to the general path (built on the device after the pass)
+    int* cmap;                 // [bs]        CSR hand-back: position of a gene in `list`, -1 when it is not on it
     unsigned char* bad;        // [bs]        1 = the gene takes the general path
     double* gc;                // [GC_N][Gs]  per-group constants of the p-value (fused_group_kernel)
     int Gs;                    //             groups, padded to a multiple of 64
 };
+constexpr int HB_NONE = 0, HB_LIST = 1, HB_ALL = 2;   // hand-back modes (control block [2])
 constexpr int GC_MU = 0, GC_NRNT = 1, GC_PROD12 = 2, GC_DENOM = 3, GC_INV_NT = 4, GC_N = 5;
 
 size_t gtab_bytes(int b, int G) {
     const size_t bs = (size_t)((b + 63) & ~63), Gs = (size_t)((G + 63) & ~63);
-    return bs * ((size_t)DCAP * 20 + 4 + 8 + 8 + 1) + Gs * 8 * GC_N + 1024;
+    return bs * ((size_t)DCAP * 20 + 4 + 8 + 8 + 1 + 8) + Gs * 8 * GC_N + 1024;
 }
 Gtab gtab_carve(void* ws, int b, int G) {
     const size_t bs = (size_t)((b + 63) & ~63), Gs = (size_t)((G + 63) & ~63);
@@ -89,6 +95,8 @@ Gtab gtab_carve(void* ws, int b, int G) {
     c.wgt = reinterpret_cast<uint32_t*>(p); p += bs * 4 * DCAP;
     c.nnz = reinterpret_cast<uint32_t*>(p); p += bs * 4;
     c.n_bad = reinterpret_cast<int*>(p); p += 64;
+    c.list = reinterpret_cast<int*>(p); p += bs * 4;
+    c.cmap = reinterpret_cast<int*>(p); p += bs * 4;
     c.bad = reinterpret_cast<unsigned char*>(p);
     return c;
 }
@@ -189,6 +197,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const f
     const int g0 = blockIdx.x * FUSED_LANES;
     const uint32_t row_bytes = (uint32_t)min(FUSED_LANES, (b - g0 + 3) & ~3) * 4u;
     if (nv <= 0) return;
+    // every gene of this CTA was already handed back by the table step (continuous data: all of them): nothing to stream.
+    // The decision is the CTA's own, taken on the device: the host enqueues the pass without knowing.
+    if (__syncthreads_and(t >= FUSED_LANES || g0 + t >= b || gt.bad[g0 + t] != 0)) return;
 
     if (t == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -748,27 +759,43 @@ __global__ void __launch_bounds__(256) fused_hist_sum_kernel(int b, int G, int g
         if (acc[q]) atomicAdd(gt.mult + (long long)q * bs + j, acc[q]);
 }
 
-// ---- compacted hand-back (dense): the flagged genes' columns are gathered into a small row-major matrix, the general
-// path runs on it, and its results are scattered back -- cost follows the number of flagged genes (a scattered fraction f
-// of the genes costs about 8 f of one pass over the matrix: every 4-byte element drags its 32-byte sector along).
-__global__ void __launch_bounds__(256) gather_genes_kernel(const float* __restrict__ X, long long ld, int gene_lb,
-                                                           const int* __restrict__ list, int nb, int nbp, int n,
-                                                           float* __restrict__ Xc) {
-    const long long total = (long long)n * nbp;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / nbp;
-        const int k = (int)(i - r * nbp);
-        Xc[i] = (k < nb) ? __ldg(X + r * ld + gene_lb + list[k]) : 0.0f;
+// ---- hand-back, decided on the device -----------------------------------------------------------------------------------
+// After the epilogue: the genes flagged during the table step or the pass, in ascending order, become `list` (and, for the
+// CSR staging, cmap[gene] = position in the list).  Few of them (<= b * num / den): HB_LIST, only those are staged and ranked
+// by the general path; more: HB_ALL, the list is the whole batch (the fused results are simply overwritten); none: HB_NONE,
+// the kernels enqueued behind this one find an empty list and leave.  One CTA: the flags are a few kilobytes.
+__global__ void __launch_bounds__(1024) fused_list_kernel(int b, Gtab gt, int num, int den, int force_all) {
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) base_s = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < b; j0 += 1024) {
+        const int j = j0 + t;
+        const bool flag = j < b && gt.bad[j] != 0;
+        const unsigned bal = __ballot_sync(FULL, flag);
+        if (lane == 0) wsum[w] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int ww = 0; ww < 32; ++ww) { const int c = wsum[ww]; if (ww < w) before += c; total += c; }
+        const int base = base_s;
+        if (j < b) {
+            const int k = base + before + __popc(bal & ((1u << lane) - 1u));
+            if (flag) gt.list[k] = j;
+            gt.cmap[j] = flag ? k : -1;
+        }
+        __syncthreads();
+        if (t == 0) base_s = base + total;
+        __syncthreads();
     }
-}
-__global__ void __launch_bounds__(256) scatter_results_kernel(const double* __restrict__ tmp, int nb, int nbp,
-                                                              const int* __restrict__ list, int G,
-                                                              double* __restrict__ results, long long gstride) {
-    const long long total = (long long)G * nb * 3;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long g = i / (3ll * nb);
-        const int rem = (int)(i - g * 3ll * nb), k = rem / 3, c = rem - 3 * k;
-        results[g * gstride + 3ll * list[k] + c] = tmp[(g * nbp + k) * 3 + c];
+    const int n = base_s;
+    const bool all = force_all || (long long)n * den > (long long)b * num;
+    if (all && n > 0) {
+        for (int j = t; j < b; j += 1024) { gt.list[j] = j; gt.cmap[j] = j; }
+    }
+    if (t == 0) {
+        gt.n_bad[1] = (n == 0) ? 0 : (all ? b : n);
+        gt.n_bad[2] = (n == 0) ? HB_NONE : (all ? HB_ALL : HB_LIST);
     }
 }
 
@@ -776,60 +803,14 @@ int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
 }
-
-// Genes handed back by a fused pass go through the general path in merged runs: a launch costs about as much as
-// ILLICO_FUSED_GAP genes, so runs closer than that are joined (good genes inside a run are simply recomputed).
-// Returns 0 = done, 1 = error, -1 = redo the whole batch through the general path.
-// fraction of the batch the merged runs of handed-back genes would cover (what the general path would redo)
-double hand_back_coverage(const std::vector<unsigned char>& bad, int b) {
-    const int gap = env_int("ILLICO_FUSED_GAP", 128);
-    long long covered = 0;
-    int j = 0;
-    while (j < b) {
-        if (!bad[j]) { ++j; continue; }
-        int ub = j + 1, k = j + 1;
-        while (k < b) {
-            if (bad[k]) { ub = k + 1; ++k; }
-            else if (k - ub < gap) ++k;
-            else break;
-        }
-        covered += ub - j;
-        j = ub;
-    }
-    return b > 0 ? (double)covered / (double)b : 0.0;
-}
-// The fused pass only pays off while few genes are handed back: scattered ones drag their neighbours into the merged
-// runs.  Above this coverage the general path does the whole batch (measured costs at the K562 shape: fused 2.3 ms,
-// general 3.4 ms per full batch).
-double max_hand_back() {
-    const char* v = getenv("ILLICO_FUSED_MAX_HANDBACK");
-    return v ? atof(v) : 0.3;
+// largest share of a batch (in 1/1024) that is handed back gene by gene; above it the general path redoes the batch
+int list_share_1024() {
+    const char* v = getenv("ILLICO_FUSED_LIST_SHARE");
+    const double f = v ? atof(v) : 0.125;
+    return (int)(f * 1024.0 + 0.5);
 }
 
-template <typename F>
-int hand_back(const std::vector<unsigned char>& bad, int b, bool side_arrays, F general) {
-    int first = -1, last = -1;
-    for (int j = 0; j < b; ++j)
-        if (bad[j]) { if (first < 0) first = j; last = j; }
-    if (first < 0) return 0;
-    if (side_arrays) return -1;   // debug / group-sum arrays are indexed by the whole batch
-    const int gap = env_int("ILLICO_FUSED_GAP", 128);
-    int lb = first;
-    while (lb <= last) {
-        int ub = lb + 1, j = lb + 1;
-        while (j <= last) {
-            if (bad[j]) { ub = j + 1; ++j; }
-            else if (j - ub < gap) ++j;
-            else break;
-        }
-        if (general(lb, ub)) return 1;
-        lb = ub;
-        while (lb <= last && !bad[lb]) ++lb;
-    }
-    return 0;
-}
-
-thread_local float g_last_fused_ms = -1.0f;
+thread_local float g_last_fused_ms = -1.0f;   // >= 0: the last dispatcher call of this thread enqueued a fused pass
 
 template <int ROWS, int STAGES, int BUF, int MINB, bool OVO>
 int launch_pass_t(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, int gpc, Gtab gt, int bs,
@@ -844,17 +825,20 @@ int launch_pass_t(const float* X, long long ld, int gene_lb, int b, const illico
     return 0;
 }
 
-// The whole fused path for one gene batch.  0 = done, 1 = error, -1 = not applicable (the caller runs the general path).
+// The whole fused path for one gene batch, enqueued without a single host read-back.
+// 0 = enqueued, 1 = error, -1 = not applicable (the caller runs the general path).
 template <bool OVO>
 int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, const illico_flags_t* flags,
               const illico_batch_buffers_t* buf, double* results, long long gstride, const illico_debug_t* dbg,
               cudaStream_t stream) {
+    g_last_fused_ms = -1.0f;
     if (env_int(OVO ? "ILLICO_OVO_FUSED" : "ILLICO_OVR_FUSED", 1) == 0 || b <= 0) return -1;
     if (!stage_dense_tma_ok(X, ld, gene_lb, b, plan)) return -1;
     // u16 counters hold the groups that are ranked (the control's rows are skipped; its histogram is the u32 table)
     if (plan->max_target_group_size >= 65536 || plan->n_groups < 2 || plan->n_groups > 65535) return -1;   // + grid.y
     if (OVO && (long long)plan->ref_group_size + plan->max_target_group_size > PAIR_MAX) return -1;  // tie sums below 2^53
     if (!OVO && flags->group_sums) return -1;
+    if (dbg) return -1;   // the exact integers / tie sums of every gene come from the general path's kernels
     if (buf->workspace_bytes < gtab_bytes(b, plan->n_groups)) return -1;
     const int bs = (b + 63) & ~63;
     Gtab gt = gtab_carve(buf->workspace, b, plan->n_groups);
@@ -869,7 +853,7 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
         if (seg_hi < 1) seg_hi = 1;
         if (seg_hi > plan->n_segments) seg_hi = plan->n_segments;
     }
-    ILLICO_CUDA_OK(cudaMemsetAsync(gt.n_bad, 0, sizeof(int), stream));
+    ILLICO_CUDA_OK(cudaMemsetAsync(gt.n_bad, 0, 16 * sizeof(int), stream));
     {
         const int rc = launch_stage_dense_tma(X, ld, gene_lb, b, plan, buf->ir_vals, buf->ir_cnt, seg_lo, seg_hi, stream, 1);
         if (rc != 0) return rc;
@@ -880,29 +864,12 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
     }
     if (!OVO)   // the sample only seeds the slots; gt.mult restarts as the whole gene's histogram
         ILLICO_CUDA_OK(cudaMemsetAsync(gt.mult, 0, (size_t)bs * DCAP * sizeof(uint32_t), stream));
-    std::vector<unsigned char> bad((size_t)b);
-    ILLICO_CUDA_OK(cudaMemcpyAsync(bad.data(), gt.bad, (size_t)b, cudaMemcpyDeviceToHost, stream));
-    ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
-    // genes the table step already hands back (continuous data, high counts): is the fused pass still worth it?
-    {
-        int nb0 = 0;
-        for (int j = 0; j < b; ++j) nb0 += bad[j] ? 1 : 0;
-        const bool compactable = env_int("ILLICO_FUSED_COMPACT", 1) != 0 && !dbg && !flags->group_sums && 8ll * nb0 <= b;
-        if (!compactable && hand_back_coverage(bad, b) > max_hand_back()) return -1;
-    }
 
-    // 2. the pass over the matrix
+    // 2. the pass over the matrix (CTAs whose genes were all handed back by the table step leave at once)
     long long avg_g = plan->n_cells / plan->n_groups;
     if (avg_g < 1) avg_g = 1;
     int gpc = (int)(env_int("ILLICO_FUSED_ROWS", 1536) / avg_g);
     if (gpc < 1) gpc = 1;
-    const bool timed = env_int("ILLICO_PROFILE", 0) != 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (timed) {
-        ILLICO_CUDA_OK(cudaEventCreate(&e0));
-        ILLICO_CUDA_OK(cudaEventCreate(&e1));
-        ILLICO_CUDA_OK(cudaEventRecord(e0, stream));
-    }
     // ring / buffer shapes measured at the K562 shape (profiles/README.md): stages of 8 rows, a 16-entry group buffer,
     // 3 CTAs per SM; the 5-stage ring (74 KB of shared memory per CTA) is 6-7 % faster than the 4-stage one
     int rc;
@@ -911,68 +878,30 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
     else
         rc = launch_pass_t<8, 4, 16, 3, OVO>(X, ld, gene_lb, b, plan, gpc, gt, bs, results, gstride, stream);
     if (rc) return rc;
-    if (timed) ILLICO_CUDA_OK(cudaEventRecord(e1, stream));
+    g_last_fused_ms = 0.0f;
 
-    // 3. per-gene weights, then the epilogue
+    // 3. per-group constants, per-gene weights, then the epilogue
     ILLICO_LAUNCH("fused_group_kernel", stream, fused_group_kernel<OVO><<<(plan->n_groups + 255) / 256, 256, 0, stream>>>(*plan, gt));
-    ILLICO_LAUNCH("fused_gene_kernel", stream, fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, (dbg && !OVO) ? dbg->tie_sum : nullptr,
-                                                                (dbg && !OVO) ? (long long*)dbg->tie_exact : nullptr));
+    ILLICO_LAUNCH("fused_gene_kernel", stream, fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, nullptr, nullptr));
     ILLICO_CUDA_OK(cudaGetLastError());
-    {
-        ILLICO_LAUNCH("fused_epilogue_kernel", stream, fused_epilogue_kernel<OVO><<<dim3((unsigned)((b + 255) / 256), (unsigned)((plan->n_groups + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
-            b, *plan, *flags, gt, bs, results, gstride, dbg ? (long long*)dbg->u2 : nullptr,
-            (dbg && OVO) ? dbg->tie_sum : nullptr, (dbg && OVO) ? (long long*)dbg->tie_exact : nullptr));
-        ILLICO_CUDA_OK(cudaGetLastError());
-    }
+    ILLICO_LAUNCH("fused_epilogue_kernel", stream, fused_epilogue_kernel<OVO><<<dim3((unsigned)((b + 255) / 256), (unsigned)((plan->n_groups + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
+            b, *plan, *flags, gt, bs, results, gstride, nullptr, nullptr, nullptr));
+    ILLICO_CUDA_OK(cudaGetLastError());
 
-    // 4. genes handed back: general path, in merged runs
-    ILLICO_CUDA_OK(cudaMemcpyAsync(bad.data(), gt.bad, (size_t)b, cudaMemcpyDeviceToHost, stream));
-    ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
-    if (timed) {
-        ILLICO_CUDA_OK(cudaEventElapsedTime(&g_last_fused_ms, e0, e1));
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-    }
-    {
-        // few flagged genes, scattered: gather their columns and run the general path on the compact matrix
-        std::vector<int> list;
-        for (int j = 0; j < b; ++j) if (bad[j]) list.push_back(j);
-        const int nb = (int)list.size(), nbp = (nb + 3) & ~3;
-        const bool side_arrays = dbg != nullptr || flags->group_sums != nullptr;
-        const long long n = plan->n_cells;
-        // carve-up of the batch's staged-list buffer (sized for b genes): lists of nbp genes | Xc | tmp results | list
-        const size_t ir_floats = (size_t)b * (size_t)plan->slot_cap;
-        size_t off = ((size_t)nbp * (size_t)plan->slot_cap + 63) & ~(size_t)63;
-        const size_t xc_off = off; off += ((size_t)n * nbp + 63) & ~(size_t)63;
-        const size_t tmp_off = off; off += ((size_t)plan->n_groups * nbp * 6 + 63) & ~(size_t)63;   // doubles = 2 floats
-        const size_t list_off = off; off += (size_t)nbp + 64;
-        if (nb > 0 && !side_arrays && env_int("ILLICO_FUSED_COMPACT", 1) != 0 && 8ll * nb <= b && off <= ir_floats &&
-            hand_back_coverage(bad, b) > 2.0 * (double)nb / (double)b) {
-            float* Xc = buf->ir_vals + xc_off;
-            double* tmp = reinterpret_cast<double*>(buf->ir_vals + tmp_off);
-            int* dlist = reinterpret_cast<int*>(buf->ir_vals + list_off);
-            ILLICO_CUDA_OK(cudaMemcpyAsync(dlist, list.data(), (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, stream));
-            ILLICO_LAUNCH("gather_genes_kernel", stream, gather_genes_kernel<<<148 * 16, 256, 0, stream>>>(X, ld, gene_lb, dlist, nb, nbp, (int)n, Xc));
-            ILLICO_CUDA_OK(cudaGetLastError());
-            if (launch_stage_dense(Xc, nbp, 0, nbp, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
-            const int rr = OVO ? launch_ovo(buf->ir_vals, buf->ir_cnt, nbp, plan, flags, tmp, 3ll * nbp, buf->workspace,
-                                            buf->workspace_bytes, nullptr, stream)
-                               : launch_ovr(buf->ir_vals, buf->ir_cnt, nbp, plan, flags, tmp, 3ll * nbp, buf->workspace,
-                                            buf->workspace_bytes, nullptr, stream);
-            if (rr) return 1;
-            ILLICO_LAUNCH("scatter_results_kernel", stream, scatter_results_kernel<<<148 * 4, 256, 0, stream>>>(tmp, nb, nbp, dlist, plan->n_groups, results, gstride));
-            ILLICO_CUDA_OK(cudaGetLastError());
-            ILLICO_CUDA_OK(cudaStreamSynchronize(stream));   // `list` (pageable) must outlive its copy
-            return 0;
-        }
-    }
-    return hand_back(bad, b, dbg != nullptr || flags->group_sums != nullptr, [&](int lb, int ub) {
-        if (launch_stage_dense(X, ld, gene_lb + lb, ub - lb, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
-        return OVO ? launch_ovo(buf->ir_vals, buf->ir_cnt, ub - lb, plan, flags, results + (long long)lb * 3, gstride,
-                                buf->workspace, buf->workspace_bytes, nullptr, stream)
-                   : launch_ovr(buf->ir_vals, buf->ir_cnt, ub - lb, plan, flags, results + (long long)lb * 3, gstride,
-                                buf->workspace, buf->workspace_bytes, nullptr, stream);
-    });
+    // 4. genes handed back: listed on the device, staged from the matrix by a persistent kernel, ranked by the general
+    // path with the device-side count (an empty list costs three nearly empty launches)
+    ILLICO_LAUNCH("fused_list_kernel", stream, fused_list_kernel<<<1, 1024, 0, stream>>>(b, gt, list_share_1024(), 1024, 0));
+    ILLICO_CUDA_OK(cudaGetLastError());
+    if (launch_stage_dense_list(X, ld, gene_lb, gt.list, gt.n_bad + 1, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
+    // the rank kernels' scratch lies behind the tables (they are read until the list has been ranked)
+    const size_t tab = (gtab_bytes(b, plan->n_groups) + 255) & ~(size_t)255;
+    if (buf->workspace_bytes <= tab) return 1;
+    char* ws = reinterpret_cast<char*>(buf->workspace) + tab;
+    const size_t ws_bytes = buf->workspace_bytes - tab;
+    return OVO ? launch_ovo_mapped(buf->ir_vals, buf->ir_cnt, b, gt.n_bad + 1, gt.list, b, plan, flags, results, gstride, ws, ws_bytes,
+                                   nullptr, stream)
+               : launch_ovr_mapped(buf->ir_vals, buf->ir_cnt, b, gt.n_bad + 1, gt.list, b, plan, flags, results, gstride, ws, ws_bytes,
+                                   nullptr, stream);
 }
 
 }  // namespace
@@ -994,20 +923,20 @@ int launch_ovr_dense_fused(const float* X, long long ld, int gene_lb, int b, con
 }
 
 
-int launch_stage_csr(const float*, const int32_t*, const long long*, int, int, const illico_plan_t*, float*, uint32_t*,
-                     void*, size_t, cudaStream_t);
-
 namespace {
 
-// The fused path for one gene batch of a CSR matrix.  0 = done, 1 = error, -1 = not applicable.
+// The fused path for one gene batch of a CSR matrix, enqueued without a host read-back.  0 = enqueued, 1 = error,
+// -1 = not applicable.
 template <bool OVO>
 int run_fused_csr(const float* data, const int32_t* indices, const long long* indptr, int gene_lb, int b,
                   const illico_plan_t* plan, const illico_flags_t* flags, const illico_batch_buffers_t* buf, double* results,
                   long long gstride, const illico_debug_t* dbg, cudaStream_t stream) {
+    g_last_fused_ms = -1.0f;
     if (env_int(OVO ? "ILLICO_OVO_FUSED" : "ILLICO_OVR_FUSED", 1) == 0 || env_int("ILLICO_CSR_FUSED", 1) == 0 || b <= 0) return -1;
     if (plan->max_target_group_size >= 65536 || plan->n_groups < 2 || plan->n_groups > 65535 || plan->n_segments > 65535) return -1;
     if (OVO && (long long)plan->ref_group_size + plan->max_target_group_size > PAIR_MAX) return -1;
     if (!OVO && flags->group_sums) return -1;
+    if (dbg) return -1;
     if (buf->workspace_bytes < gtab_bytes(b, plan->n_groups)) return -1;
     const int bs = (b + 63) & ~63;
     Gtab gt = gtab_carve(buf->workspace, b, plan->n_groups);
@@ -1015,69 +944,55 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
     const int G = plan->n_groups;
 
     // tables: raw counts get slots 1 .. 12 up front (log1p data claims its slots while streaming)
+    ILLICO_CUDA_OK(cudaMemsetAsync(gt.n_bad, 0, 16 * sizeof(int), stream));
     ILLICO_LAUNCH("fused_seed_kernel", stream, fused_seed_kernel<<<(bs + 255) / 256, 256, 0, stream>>>(gt, bs, flags->is_log1p ? 0 : 1));
     ILLICO_LAUNCH("fused_zero_multi_kernel", stream, fused_zero_multi_kernel<<<dim3(8, (unsigned)G), 256, 0, stream>>>(b, *plan, rec, gstride));
     ILLICO_CUDA_OK(cudaGetLastError());
-
-    const bool timed = env_int("ILLICO_PROFILE", 0) != 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (timed) {
-        ILLICO_CUDA_OK(cudaEventCreate(&e0));
-        ILLICO_CUDA_OK(cudaEventCreate(&e1));
-        ILLICO_CUDA_OK(cudaEventRecord(e0, stream));
-    }
     {
-        // raw counts (identity tables): row-at-a-time kernel without atomics; log1p data: tables claimed on the fly
         // (An atomics-free variant -- the whole CTA applies one row at a time, plain LDS/STS -- measured 1.5-2.7 x
-        // slower: 150 CTA-wide barriers per segment cost more than the shared atomics they avoid.)
+        // slower: 150 CTA-wide barriers per segment cost more than the shared atomics they avoid.  Counting part of the
+        // updates in a per-SM global histogram with L2 reductions instead of shared atomics measured 1.4-1.9 x slower.)
         auto kern = fused_csr_pass_kernel<OVO>;
         const int tile = b < CSRF_TILE ? b : CSRF_TILE;
         const size_t smem = (size_t)tile * 24;
         ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const dim3 grid((unsigned)((b + CSRF_TILE - 1) / CSRF_TILE), (unsigned)plan->n_segments);
-        // (Counting part of the updates in a per-SM global histogram with L2 reductions instead of shared atomics
-        // measured 1.4-1.9 x slower.)
         ILLICO_LAUNCH("fused_csr_pass_kernel", stream, kern<<<grid, CSRF_THREADS, smem, stream>>>(data, indices, indptr, gene_lb, b, *plan, gt, bs, rec, gstride));
         ILLICO_CUDA_OK(cudaGetLastError());
     }
-    if (timed) ILLICO_CUDA_OK(cudaEventRecord(e1, stream));
-    int n_bad = 0;
-    ILLICO_CUDA_OK(cudaMemcpyAsync(&n_bad, gt.n_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
-    if (timed) {
-        ILLICO_CUDA_OK(cudaEventElapsedTime(&g_last_fused_ms, e0, e1));
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-    }
-    if (8 * n_bad > b) return -1;   // the pass stopped early (continuous data, high counts): the general path does the batch
-
+    g_last_fused_ms = 0.0f;
+    // (when the pass stopped early -- an eighth of the genes flagged: continuous data -- the kernels below work on
+    // incomplete records; the list kernel then hands the WHOLE batch to the general path, which overwrites everything)
     if (!OVO) {
         const int gpb = 64;
         ILLICO_LAUNCH("fused_hist_sum_kernel", stream, fused_hist_sum_kernel<<<dim3((unsigned)((b + 255) / 256), (unsigned)((G + gpb - 1) / gpb)), 256, 0, stream>>>(b, G, gpb, gt, bs, rec,
                                                                                                                  gstride));
     }
     ILLICO_LAUNCH("fused_group_kernel", stream, fused_group_kernel<OVO><<<(plan->n_groups + 255) / 256, 256, 0, stream>>>(*plan, gt));
-    ILLICO_LAUNCH("fused_gene_kernel", stream, fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, (dbg && !OVO) ? dbg->tie_sum : nullptr,
-                                                                (dbg && !OVO) ? (long long*)dbg->tie_exact : nullptr));
-    {
-        ILLICO_LAUNCH("fused_epilogue_kernel", stream, fused_epilogue_kernel<OVO><<<dim3((unsigned)((b + 255) / 256), (unsigned)((G + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
-            b, *plan, *flags, gt, bs, results, gstride, dbg ? (long long*)dbg->u2 : nullptr,
-            (dbg && OVO) ? dbg->tie_sum : nullptr, (dbg && OVO) ? (long long*)dbg->tie_exact : nullptr));
-        ILLICO_CUDA_OK(cudaGetLastError());
-    }
-    if (n_bad == 0) return 0;
-    std::vector<unsigned char> bad((size_t)b);
-    ILLICO_CUDA_OK(cudaMemcpyAsync(bad.data(), gt.bad, (size_t)b, cudaMemcpyDeviceToHost, stream));
-    ILLICO_CUDA_OK(cudaStreamSynchronize(stream));
-    if (hand_back_coverage(bad, b) > 2.0 * max_hand_back()) return -1;   // the merged runs are most of the batch anyway
-    return hand_back(bad, b, dbg != nullptr || flags->group_sums != nullptr, [&](int lb, int ub) {
-        if (launch_stage_csr(data, indices, indptr, gene_lb + lb, ub - lb, plan, buf->ir_vals, buf->ir_cnt, buf->workspace,
-                             buf->workspace_bytes, stream)) return 1;
-        return OVO ? launch_ovo(buf->ir_vals, buf->ir_cnt, ub - lb, plan, flags, results + (long long)lb * 3, gstride,
-                                buf->workspace, buf->workspace_bytes, nullptr, stream)
-                   : launch_ovr(buf->ir_vals, buf->ir_cnt, ub - lb, plan, flags, results + (long long)lb * 3, gstride,
-                                buf->workspace, buf->workspace_bytes, nullptr, stream);
-    });
+    ILLICO_LAUNCH("fused_gene_kernel", stream, fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, nullptr, nullptr));
+    ILLICO_LAUNCH("fused_epilogue_kernel", stream, fused_epilogue_kernel<OVO><<<dim3((unsigned)((b + 255) / 256), (unsigned)((G + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
+            b, *plan, *flags, gt, bs, results, gstride, nullptr, nullptr, nullptr));
+    ILLICO_CUDA_OK(cudaGetLastError());
+
+    // hand-back, decided on the device: a few scattered genes -> one filtered pass over the stored values (HB_LIST);
+    // many (or a pass that stopped early: 8 n_bad > b) -> the general CSR staging of the whole batch (HB_ALL)
+    int share = list_share_1024();
+    if (share > 128) share = 128;                       // the pass itself stops at an eighth
+    ILLICO_LAUNCH("fused_list_kernel", stream, fused_list_kernel<<<1, 1024, 0, stream>>>(b, gt, share, 1024, 0));
+    ILLICO_CUDA_OK(cudaGetLastError());
+    const size_t tab = (gtab_bytes(b, plan->n_groups) + 255) & ~(size_t)255;
+    if (buf->workspace_bytes <= tab) return 1;
+    char* ws = reinterpret_cast<char*>(buf->workspace) + tab;
+    const size_t ws_bytes = buf->workspace_bytes - tab;
+    const int max_list = (int)(((long long)b * share) / 1024) + 1;
+    if (launch_stage_csr_list(data, indices, indptr, gene_lb, b, gt.cmap, gt.n_bad + 2, HB_LIST, max_list < b ? max_list : b, plan,
+                              buf->ir_vals, buf->ir_cnt, stream)) return 1;
+    if (launch_stage_csr_if(data, indices, indptr, gene_lb, b, plan, buf->ir_vals, buf->ir_cnt, ws, ws_bytes, gt.n_bad + 2, HB_ALL, stream))
+        return 1;
+    return OVO ? launch_ovo_mapped(buf->ir_vals, buf->ir_cnt, b, gt.n_bad + 1, gt.list, b, plan, flags, results, gstride, ws, ws_bytes,
+                                   nullptr, stream)
+               : launch_ovr_mapped(buf->ir_vals, buf->ir_cnt, b, gt.n_bad + 1, gt.list, b, plan, flags, results, gstride, ws, ws_bytes,
+                                   nullptr, stream);
 }
 
 }  // namespace

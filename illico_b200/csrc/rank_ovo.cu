@@ -57,7 +57,8 @@ struct OvoParams {
     int scratch_words;       // shared scratch (control ping-pong partner, later the tier buffers)
     int* gene_counter;       // next gene to hand out (zeroed before the launch)
     const int* n_genes_dev;  // optional: number of genes decided on the device (a hand-back list), else n_genes
-    const int* gene_map;     // optional: results of gene j go to column gene_map[j] (compacted hand-back)
+    const int* gene_map;     // optional: staged gene j is column gene_map[j] of the results / debug / group-sum arrays
+    int n_cols;              // width of the debug / group-sum arrays (= n_genes unless gene_map is set)
     const double* gc;        // [GCN][Gs] per-group constants (ovo_group_consts_kernel)
     int Gs;
     long long* dbg_u2;
@@ -231,7 +232,8 @@ __device__ __forceinline__ void finalize_group(const OvoParams& P, const RefInfo
                                                const uint32_t* gkeys = nullptr, int gstride = 1) {
     const long long n_t = P.plan.group_size[g];
     const long long z_t = n_t - m;
-    if (P.flags.group_sums) sum = P.flags.group_sums[(long long)g * P.n_genes + j];
+    const int jo = P.gene_map ? P.gene_map[j] : j;
+    if (P.flags.group_sums) sum = P.flags.group_sums[(long long)g * P.n_cols + jo];
     const long long Z = (long long)R.zeros + z_t;
     u2 += (unsigned long long)(z_t * (2ll * R.npos + R.zeros));
     const unsigned long long tie_exact = R.tie + tie_nz + (unsigned long long)cube_minus(Z);
@@ -248,10 +250,9 @@ __device__ __forceinline__ void finalize_group(const OvoParams& P, const RefInfo
     const double tie_corr = __dsub_rn(1.0, __ddiv_rn(P.flags.tie_correct ? tie : 0.0, gc[3 * P.Gs]));
     const double p = pval_core(gc[1 * P.Gs], gc[0], gc[2 * P.Gs], tie_corr, U, cc, P.flags.alternative);
     const double fc = (R.mean == 0.0) ? INFINITY : (sum * gc[4 * P.Gs]) * R.inv_mean;
-    const int jo = P.gene_map ? P.gene_map[j] : j;
     double* o = P.results + (long long)g * P.gstride + (long long)jo * 3;
     o[0] = p; o[1] = U; o[2] = fc;
-    const long long di = (long long)g * P.n_genes + j;
+    const long long di = (long long)g * P.n_cols + jo;
     if (P.dbg_u2) P.dbg_u2[di] = (long long)u2;
     if (P.dbg_tie) P.dbg_tie[di] = tie;
     if (P.dbg_tie_exact) P.dbg_tie_exact[di] = (long long)tie_exact;
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
             }
         }
         rsum = block_sum<double>(rsum, redd);
-        R.sum = P.flags.group_sums ? P.flags.group_sums[(long long)ref * P.n_genes + j] : rsum;
+        R.sum = P.flags.group_sums ? P.flags.group_sums[(long long)ref * P.n_cols + (P.gene_map ? P.gene_map[j] : j)] : rsum;
         R.mean = R.sum / (double)R.n_ref;
         R.inv_mean = 1.0 / R.mean;
         unsigned long long tsum = 0;
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                     const int jo = P.gene_map ? P.gene_map[j] : j;
                     double* o = P.results + (long long)g * P.gstride + (long long)jo * 3;
                     o[0] = 1.0; o[1] = -1.0; o[2] = (R.mean == 0.0) ? INFINITY : R.mean / R.mean;
-                    const long long di = (long long)g * P.n_genes + j;
+                    const long long di = (long long)g * P.n_cols + jo;
                     if (P.dbg_u2) P.dbg_u2[di] = -2;
                     if (P.dbg_tie) P.dbg_tie[di] = 0.0;
                     if (P.dbg_tie_exact) P.dbg_tie_exact[di] = 0;
@@ -872,7 +873,7 @@ static int launch_ovo_t(OvoParams& P, const illico_plan_t* plan, void* workspace
 }
 
 // n_genes_dev / gene_map: see OvoParams (both may be NULL)
-int launch_ovo_mapped(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const int* n_genes_dev, const int* gene_map,
+int launch_ovo_mapped(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const int* n_genes_dev, const int* gene_map, int n_cols,
                       const illico_plan_t* plan, const illico_flags_t* flags, double* results, long long gstride,
                       void* workspace, size_t workspace_bytes, const illico_debug_t* dbg, cudaStream_t stream) {
     if (n_genes <= 0) return 0;
@@ -890,7 +891,7 @@ int launch_ovo_mapped(const float* ir_vals, const uint32_t* ir_cnt, int n_genes,
     OvoParams P;
     P.ir_vals = ir_vals; P.ir_cnt = ir_cnt; P.n_genes = n_genes; P.plan = *plan; P.flags = *flags;
     P.results = results; P.gstride = gstride;
-    P.n_genes_dev = n_genes_dev; P.gene_map = gene_map;
+    P.n_genes_dev = n_genes_dev; P.gene_map = gene_map; P.n_cols = n_cols;
     P.dbg_u2 = dbg ? (long long*)dbg->u2 : nullptr; P.dbg_tie = dbg ? dbg->tie_sum : nullptr;
     P.dbg_tie_exact = dbg ? (long long*)dbg->tie_exact : nullptr;
     static const int nt = env_int("ILLICO_OVO_THREADS", 256);
@@ -905,7 +906,7 @@ int launch_ovo_mapped(const float* ir_vals, const uint32_t* ir_cnt, int n_genes,
 int launch_ovo(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const illico_plan_t* plan,
                const illico_flags_t* flags, double* results, long long gstride, void* workspace,
                size_t workspace_bytes, const illico_debug_t* dbg, cudaStream_t stream) {
-    return launch_ovo_mapped(ir_vals, ir_cnt, n_genes, nullptr, nullptr, plan, flags, results, gstride, workspace, workspace_bytes,
+    return launch_ovo_mapped(ir_vals, ir_cnt, n_genes, nullptr, nullptr, n_genes, plan, flags, results, gstride, workspace, workspace_bytes,
                              dbg, stream);
 }
 

@@ -49,6 +49,9 @@ struct OvrParams {
     long long* dbg_u2;
     double* dbg_tie;
     long long* dbg_tie_exact;
+    const int* n_genes_dev;    // optional: number of genes decided on the device (a hand-back list), else n_genes
+    const int* gene_map;       // optional: staged gene j is column gene_map[j] of the results / debug / group-sum arrays
+    int n_cols;                // width of the debug / group-sum arrays (= n_genes unless gene_map is set)
     int* todo;        // genes the table kernel could not take (NULL: the general kernel ranks every gene)
     int* todo_count;
     uint4* table_rec;          // table kernel: per-CTA [n_segments][2] segment records (NULL: second pass re-reads the values)
@@ -111,9 +114,10 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
 
     const double cc = P.flags.use_continuity ? 0.5 : 0.0;
 
-    const int n_work = P.todo ? *P.todo_count : P.n_genes;
+    const int n_work = P.todo ? *P.todo_count : (P.n_genes_dev ? *P.n_genes_dev : P.n_genes);
     for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const int j = P.todo ? P.todo[wi] : wi;
+        const int jo = P.gene_map ? P.gene_map[j] : j;   // column of the results / side arrays
         const uint32_t* cnt = P.ir_cnt + (long long)j * S;
         const float* vals = P.ir_vals + (long long)j * pl.slot_cap;
 
@@ -316,22 +320,22 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
             double sum = 0.0;
             long long nnz_g = 0;
             for (int s = pl.group_seg[g]; s < pl.group_seg[g + 1]; ++s) { R2 += seg_r2[s]; sum += seg_sum[s]; nnz_g += cnt[s]; }
-            if (P.flags.group_sums) sum = P.flags.group_sums[(long long)g * P.n_genes + j];
+            if (P.flags.group_sums) sum = P.flags.group_sums[(long long)g * P.n_cols + jo];
             const long long n_t = pl.group_size[g], n_r = n - n_t;
             R2 += (unsigned long long)(n_t - nnz_g) * r2_zero;
             const long long u2 = 2 * n_r * n_t + n_t * (n_t + 1) - (long long)R2;
             const double U = (double)u2 / 2.0;
             const double mu = (double)(n_r * n_t) / 2.0;
             const double p = compute_pval(n_r, n_t, n, P.flags.tie_correct ? tie : 0.0, U, mu, cc, P.flags.alternative);
-            double* o = P.results + (long long)g * P.gstride + (long long)j * 3;
+            double* o = P.results + (long long)g * P.gstride + (long long)jo * 3;
             o[0] = p; o[1] = U; o[2] = sum;
             my_total += sum;
-            if (P.dbg_u2) P.dbg_u2[(long long)g * P.n_genes + j] = u2;
+            if (P.dbg_u2) P.dbg_u2[(long long)g * P.n_cols + jo] = u2;
         }
         const double total = block_sum<double>(my_total, redd);
         // ================= phase D: fold change (illico/utils/math.py:168-193, one-versus-rest branch) ============
         for (int g = tid; g < G; g += OVR_THREADS) {
-            double* o = P.results + (long long)g * P.gstride + (long long)j * 3;
+            double* o = P.results + (long long)g * P.gstride + (long long)jo * 3;
             const double sum = o[2];
             const long long n_t = pl.group_size[g];
             const double mu_t = sum * (1.0 / (double)n_t);   // (the fused epilogue's form: every path gives the same bits)
@@ -339,8 +343,8 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
             o[2] = (mu_r == 0.0) ? INFINITY : mu_t / mu_r;
         }
         if (tid == 0) {
-            if (P.dbg_tie) P.dbg_tie[j] = tie;
-            if (P.dbg_tie_exact) P.dbg_tie_exact[j] = (long long)(tie_nz_exact + (unsigned long long)cube_minus(n0));
+            if (P.dbg_tie) P.dbg_tie[jo] = tie;
+            if (P.dbg_tie_exact) P.dbg_tie_exact[jo] = (long long)(tie_nz_exact + (unsigned long long)cube_minus(n0));
         }
         __syncthreads();
     }
@@ -378,7 +382,9 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
     const double cc = P.flags.use_continuity ? 0.5 : 0.0;
     uint4* rec = P.table_rec ? P.table_rec + (long long)blockIdx.x * P.table_rec_stride : nullptr;
 
-    for (int j = blockIdx.x; j < P.n_genes; j += gridDim.x) {
+    const int n_genes = P.n_genes_dev ? *P.n_genes_dev : P.n_genes;
+    for (int j = blockIdx.x; j < n_genes; j += gridDim.x) {
+        const int jo = P.gene_map ? P.gene_map[j] : j;   // column of the results / side arrays
         const uint32_t* cnt = P.ir_cnt + (long long)j * S;
         const float* vals = P.ir_vals + (long long)j * pl.slot_cap;
         __syncthreads();
@@ -573,9 +579,9 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
             const double mu_t = sum * (1.0 / (double)n_t);   // (the fused epilogue's form: every path gives the same bits)
             // exactly zero when the group holds every non-zero of the gene (see fused_epilogue_kernel)
             const double mu_r = (nnz_g == nnz) ? 0.0 : (total - sum) / (double)(n - n_t);
-            double* o = P.results + (long long)g * P.gstride + (long long)j * 3;
+            double* o = P.results + (long long)g * P.gstride + (long long)jo * 3;
             o[0] = p; o[1] = U; o[2] = (mu_r == 0.0) ? INFINITY : mu_t / mu_r;
-            if (P.dbg_u2) P.dbg_u2[(long long)g * P.n_genes + j] = u2;
+            if (P.dbg_u2) P.dbg_u2[(long long)g * P.n_cols + jo] = u2;
         };
         for (int g = tid; g < G; g += T_THREADS) {
             const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
@@ -603,8 +609,8 @@ __global__ void __launch_bounds__(T_THREADS, 8) ovr_table_kernel(const OvrParams
             if (lane == 0) finish_group(g, R2, sum, nnz_g);
         }
         if (tid == 0) {
-            if (P.dbg_tie) P.dbg_tie[j] = tie;
-            if (P.dbg_tie_exact) P.dbg_tie_exact[j] = (long long)(redu[4] + (unsigned long long)cube_minus(n0));
+            if (P.dbg_tie) P.dbg_tie[jo] = tie;
+            if (P.dbg_tie_exact) P.dbg_tie_exact[jo] = (long long)(redu[4] + (unsigned long long)cube_minus(n0));
         }
     }
 }
@@ -616,9 +622,21 @@ size_t ovr_slab_qwords(const illico_plan_t* plan) {
     return 2 * (size_t)plan->n_segments + (size_t)((plan->n_cells + 1) & ~1) + 2;
 }
 
+int launch_ovr_mapped(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const int* n_genes_dev, const int* gene_map, int n_cols,
+                      const illico_plan_t* plan, const illico_flags_t* flags, double* results, long long gstride, void* workspace,
+                      size_t workspace_bytes, const illico_debug_t* dbg, cudaStream_t stream);
+
 int launch_ovr(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const illico_plan_t* plan,
                const illico_flags_t* flags, double* results, long long gstride, void* workspace,
                size_t workspace_bytes, const illico_debug_t* dbg, cudaStream_t stream) {
+    return launch_ovr_mapped(ir_vals, ir_cnt, n_genes, nullptr, nullptr, n_genes, plan, flags, results, gstride, workspace, workspace_bytes,
+                             dbg, stream);
+}
+
+// n_genes: how many genes the staged lists can hold at most (sizes the grids); n_genes_dev / gene_map / n_cols: see OvrParams
+int launch_ovr_mapped(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const int* n_genes_dev, const int* gene_map, int n_cols,
+                      const illico_plan_t* plan, const illico_flags_t* flags, double* results, long long gstride, void* workspace,
+                      size_t workspace_bytes, const illico_debug_t* dbg, cudaStream_t stream) {
     if (n_genes <= 0) return 0;
     int dev = 0, sms = 0, max_smem = 0;
     ILLICO_CUDA_OK(cudaGetDevice(&dev));
@@ -628,6 +646,7 @@ int launch_ovr(const float* ir_vals, const uint32_t* ir_cnt, int n_genes, const 
     OvrParams P;
     P.ir_vals = ir_vals; P.ir_cnt = ir_cnt; P.n_genes = n_genes; P.plan = *plan; P.flags = *flags;
     P.results = results; P.gstride = gstride;
+    P.n_genes_dev = n_genes_dev; P.gene_map = gene_map; P.n_cols = n_cols;
     P.dbg_u2 = dbg ? (long long*)dbg->u2 : nullptr; P.dbg_tie = dbg ? dbg->tie_sum : nullptr;
     P.dbg_tie_exact = dbg ? (long long*)dbg->tie_exact : nullptr;
 

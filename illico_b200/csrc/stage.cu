@@ -147,6 +147,58 @@ __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const flo
     }
 }
 
+// Hand-back of the fused paths: the genes to stage are named by a list that was built ON THE DEVICE (n = *n_list_dev of
+// them; gene k of the list is column gene_lb + list[k] of X and goes to slot space k of ir_vals / ir_cnt).  Nothing about
+// the list is known on the host when this kernel is enqueued, so the grid is persistent (a fixed number of CTAs walking
+// the (256-gene tile, segment chunk) work items) and an empty list costs a few microseconds.  Same compaction as
+// stage_dense_kernel<true, 1>; a scattered list reads one 32-byte sector per 4-byte element.
+__global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_list_kernel(const float* __restrict__ X, long long ld, int gene_lb,
+                                                                            const int* __restrict__ list,
+                                                                            const int* __restrict__ n_list_dev,
+                                                                            const illico_plan_t pl, float* __restrict__ ir_vals,
+                                                                            uint32_t* __restrict__ ir_cnt, int segs_per_cta) {
+    constexpr int NT = STAGE_WARPS * 32;
+    __shared__ __align__(16) float wbuf[NT][8];
+    const int lane = threadIdx.x & 31, t = threadIdx.x;
+    const int n = *n_list_dev;
+    if (n <= 0) return;
+    const int S = pl.n_segments;
+    const int tiles_x = (n + NT - 1) / NT, tiles_y = (S + segs_per_cta - 1) / segs_per_cta;
+    const uint32_t ldb = (uint32_t)(ld * 4);
+    const uint32_t wbuf_t = (uint32_t)__cvta_generic_to_shared(&wbuf[t][0]);
+    for (long long tile = blockIdx.x; tile < (long long)tiles_x * tiles_y; tile += gridDim.x) {
+        const int bx = (int)(tile % tiles_x), by = (int)(tile / tiles_x);
+        const int jb = bx * NT + t;                        // position in the list = gene index of the staged lists
+        const bool active = jb < n;
+        const float* col = X + gene_lb + (active ? list[jb] : list[0]);
+        const int s_begin = by * segs_per_cta, s_end = min(S, s_begin + segs_per_cta);
+        for (int s = s_begin; s < s_end; ++s) {
+            const int p0 = pl.seg_pos[s], p1 = pl.seg_pos[s + 1];
+            float* out0 = ir_vals + (long long)(active ? jb : 0) * pl.slot_cap + pl.seg_base[s];
+            uint32_t done = 0, off = 0;
+            for (int p = p0; p < p1; p += 32) {
+                const int nrows = min(32, p1 - p);
+                const int myrow = pl.perm[p + min(lane, nrows - 1)];
+                for (int k0 = 0; k0 < nrows; k0 += STAGE_INFLIGHT) {
+                    float v[STAGE_INFLIGHT];
+#pragma unroll
+                    for (int u = 0; u < STAGE_INFLIGHT; ++u)
+                        v[u] = __ldcs(row_ptr(col, __shfl_sync(FULL, myrow, (k0 + u) & 31), ldb));
+                    if (active) {
+#pragma unroll
+                        for (int u = 0; u < STAGE_INFLIGHT; ++u)
+                            if (k0 + u < nrows) append_nonzero(out0, done, off, v[u], wbuf_t);
+                    }
+                }
+            }
+            if (active) {
+                if (off) flush8(out0, done, wbuf_t);
+                ir_cnt[(long long)jb * S + s] = done + (off >> 2);   // (a thread's segments are consecutive: one short run)
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ long long lower_bound_i32(const int32_t* a, long long n, int key) {
     long long lo = 0, hi = n;
     while (lo < hi) {
@@ -169,7 +221,9 @@ constexpr int CSR_THREADS = 256;
 constexpr int CSR_MAX_SEGS = 16;
 
 __global__ void __launch_bounds__(256) csr_split_kernel(const int32_t* __restrict__ indices, const long long* __restrict__ indptr,
-                                                        int n_rows, int gene_lb, int b, int K, int32_t* __restrict__ split) {
+                                                        int n_rows, int gene_lb, int b, int K, int32_t* __restrict__ split,
+                                                        const int* __restrict__ mode_dev, int want_mode) {
+    if (mode_dev && *mode_dev != want_mode) return;   // (hand-back decided on the device: see launch_stage_csr_if)
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -188,7 +242,8 @@ __global__ void __launch_bounds__(CSR_THREADS) stage_csr_kernel(const float* __r
                                                                 const long long* __restrict__ indptr, int gene_lb, int b, int K,
                                                                 const int32_t* __restrict__ split, const illico_plan_t pl,
                                                                 float* __restrict__ ir_vals, uint32_t* __restrict__ ir_cnt,
-                                                                int segs_per_cta) {
+                                                                int segs_per_cta, const int* __restrict__ mode_dev, int want_mode) {
+    if (mode_dev && *mode_dev != want_mode) return;
     extern __shared__ __align__(16) unsigned char csr_smem[];
     long long* row_a = reinterpret_cast<long long*>(csr_smem);             // [CSR_MAX_ROWS] first stored element of each row in the range
     float* vals = reinterpret_cast<float*>(row_a + CSR_MAX_ROWS);          // [CSR_CAP]
@@ -345,6 +400,40 @@ __global__ void __launch_bounds__(CSR_THREADS) stage_csr_kernel(const float* __r
     }
 }
 
+// CSR hand-back of a few scattered genes (device-side list): one pass over the stored values of the batch's gene window;
+// a value whose gene is on the list (cmap[gene] = its position k, else -1) is appended to slot space k with one atomic
+// (the counts of the listed genes were zeroed).  Only runs when *mode_dev == want_mode.
+__global__ void __launch_bounds__(256) stage_csr_list_kernel(const float* __restrict__ data, const int32_t* __restrict__ indices,
+                                                             const long long* __restrict__ indptr, int n_rows, int gene_lb, int b,
+                                                             const int* __restrict__ cmap, const int* __restrict__ mode_dev,
+                                                             int want_mode, const illico_plan_t pl, float* __restrict__ ir_vals,
+                                                             uint32_t* __restrict__ ir_cnt) {
+    if (*mode_dev != want_mode) return;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int S = pl.n_segments, c_hi = gene_lb + b;
+    for (long long r = warp; r < n_rows; r += nwarps) {
+        long long e0 = indptr[r];
+        const long long e1 = indptr[r + 1];
+        if (gene_lb > 0) e0 += lower_bound_i32(indices + e0, e1 - e0, gene_lb);
+        const int seg = pl.cell_seg[r];
+        const int base = pl.seg_base[seg], cap = pl.seg_base[seg + 1] - base;
+        for (long long e = e0 + lane; ; e += 32) {
+            const int c = (e < e1) ? __ldcs(indices + e) : 0x7fffffff;
+            if (__all_sync(FULL, c >= c_hi)) break;
+            if (c < c_hi) {
+                const int k = cmap[c - gene_lb];
+                const float v = __ldcs(data + e);
+                if (k >= 0 && v != 0.0f) {
+                    const uint32_t slot = atomicAdd(&ir_cnt[(long long)k * S + seg], 1u);
+                    if (slot < (uint32_t)cap) ir_vals[(long long)k * pl.slot_cap + base + slot] = v;
+                }
+            }
+        }
+    }
+}
+
 // CSC: one CTA per gene column of the batch.
 __global__ void __launch_bounds__(256) stage_csc_kernel(const float* __restrict__ data, const int32_t* __restrict__ indices,
                                                         const long long* __restrict__ indptr, int gene_lb, int b,
@@ -432,9 +521,10 @@ size_t stage_csr_workspace_bytes(const illico_plan_t* plan, int b) {
     return (size_t)plan->n_cells * (size_t)(K + 1) * sizeof(int32_t) + 256;
 }
 
-int launch_stage_csr(const float* data, const int32_t* indices, const long long* indptr, int gene_lb, int b,
-                     const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, void* workspace, size_t workspace_bytes,
-                     cudaStream_t stream) {
+// mode_dev != NULL: the kernels only run when *mode_dev == want_mode (a decision taken on the device)
+int launch_stage_csr_if(const float* data, const int32_t* indices, const long long* indptr, int gene_lb, int b,
+                        const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, void* workspace, size_t workspace_bytes,
+                        const int* mode_dev, int want_mode, cudaStream_t stream) {
     if (b <= 0 || plan->n_cells <= 0) return 0;
     const int K = (b + CSR_GC - 1) / CSR_GC;
     if (!workspace || workspace_bytes < stage_csr_workspace_bytes(plan, b)) {
@@ -444,7 +534,7 @@ int launch_stage_csr(const float* data, const int32_t* indices, const long long*
     int32_t* split = reinterpret_cast<int32_t*>(workspace);
     long long blocks = ((long long)plan->n_cells + 7) / 8;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    ILLICO_LAUNCH("csr_split_kernel", stream, csr_split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indices, indptr, plan->n_cells, gene_lb, b, K, split));
+    ILLICO_LAUNCH("csr_split_kernel", stream, csr_split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indices, indptr, plan->n_cells, gene_lb, b, K, split, mode_dev, want_mode));
     ILLICO_CUDA_OK(cudaGetLastError());
     const int S = plan->n_segments;
     long long avg = plan->n_cells / S;
@@ -462,7 +552,46 @@ int launch_stage_csr(const float* data, const int32_t* indices, const long long*
                         CSR_MAX_SEGS * CSR_GC * 2 + 16;
     ILLICO_CUDA_OK(cudaFuncSetAttribute(stage_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ILLICO_LAUNCH("stage_csr_kernel", stream, stage_csr_kernel<<<dim3((unsigned)K, (unsigned)gy), CSR_THREADS, smem, stream>>>(data, indices, indptr, gene_lb, b, K, split,
-                                                                                     *plan, ir_vals, ir_cnt, segs_per_cta));
+                                                                                     *plan, ir_vals, ir_cnt, segs_per_cta, mode_dev, want_mode));
+    ILLICO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_stage_csr(const float* data, const int32_t* indices, const long long* indptr, int gene_lb, int b,
+                     const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
+    return launch_stage_csr_if(data, indices, indptr, gene_lb, b, plan, ir_vals, ir_cnt, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+// stages the genes of a device-side list (see stage_csr_list_kernel); the counts of up to `max_list` genes are zeroed first
+int launch_stage_csr_list(const float* data, const int32_t* indices, const long long* indptr, int gene_lb, int b, const int* cmap,
+                          const int* mode_dev, int want_mode, int max_list, const illico_plan_t* plan, float* ir_vals,
+                          uint32_t* ir_cnt, cudaStream_t stream) {
+    if (b <= 0 || plan->n_cells <= 0 || max_list <= 0) return 0;
+    ILLICO_CUDA_OK(cudaMemsetAsync(ir_cnt, 0, (size_t)max_list * (size_t)plan->n_segments * sizeof(uint32_t), stream));
+    long long blocks = ((long long)plan->n_cells + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ILLICO_LAUNCH("stage_csr_list_kernel", stream,
+                  stage_csr_list_kernel<<<(unsigned)blocks, 256, 0, stream>>>(data, indices, indptr, plan->n_cells, gene_lb, b, cmap, mode_dev,
+                                                                              want_mode, *plan, ir_vals, ir_cnt));
+    ILLICO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// stages the genes of a device-side list from a dense matrix (see stage_dense_list_kernel)
+int launch_stage_dense_list(const float* X, long long ld, int gene_lb, const int* list, const int* n_list_dev,
+                            const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, cudaStream_t stream) {
+    const int S = plan->n_segments;
+    if (S <= 0) return 0;
+    if (ld <= 0 || ld >= (1ll << 30)) { set_error("leading dimension %lld out of range", ld); return 1; }
+    long long avg = plan->n_cells / S;
+    if (avg < 1) avg = 1;
+    int segs_per_cta = (int)(512 / avg);
+    if (segs_per_cta < 1) segs_per_cta = 1;
+    if (segs_per_cta > STAGE_MAX_SEGS) segs_per_cta = STAGE_MAX_SEGS;
+    ILLICO_LAUNCH("stage_dense_list_kernel", stream,
+                  stage_dense_list_kernel<<<148 * 8, STAGE_WARPS * 32, 0, stream>>>(X, ld, gene_lb, list, n_list_dev, *plan, ir_vals, ir_cnt,
+                                                                                     segs_per_cta));
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }

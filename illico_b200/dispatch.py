@@ -104,15 +104,35 @@ def clear_caches() -> None:
         _matrices.clear()
 
 
+_tls = threading.local()
+
+
+def _thread_stream(device) -> torch.cuda.Stream:
+    """One CUDA stream per host thread and device: the reference's joblib threads then run their batches concurrently on
+    the GPU instead of queueing on the default stream (the C ABI never synchronises)."""
+    streams = getattr(_tls, "streams", None)
+    if streams is None:
+        streams = _tls.streams = {}
+    st = streams.get(str(device))
+    if st is None:
+        st = streams[str(device)] = torch.cuda.Stream(device=device)
+    return st
+
+
 def _dispatch(fmt: str, X, chunk_lb, chunk_ub, grpc, is_log1p, use_continuity, tie_correct, alternative, debug=None):
     eng = engine_for(grpc)
-    M = _resident(X, fmt, eng)
     lb, ub = int(chunk_lb), int(chunk_ub)
     b = ub - lb
     flags = make_flags(is_log1p, use_continuity, tie_correct, alternative, fmt)
-    res = torch.empty((eng.n_groups, max(b, 0), 3), dtype=torch.float64, device=eng.device)
-    eng.run_batch(M, lb, ub, flags, res, 0, debug)
-    host = res.cpu().numpy()
+    stream = _thread_stream(eng.device)
+    with torch.cuda.device(eng.device), torch.cuda.stream(stream):
+        M = _resident(X, fmt, eng)
+        res = torch.empty((eng.n_groups, max(b, 0), 3), dtype=torch.float64, device=eng.device)
+        eng.run_batch(M, lb, ub, flags, res, 0, debug)
+        host = torch.empty(res.shape, dtype=torch.float64, pin_memory=True)
+        host.copy_(res, non_blocking=True)
+        stream.synchronize()          # this thread's stream only: the caller gets host arrays back
+    host = host.numpy()
     return (np.ascontiguousarray(host[:, :, 0]), np.ascontiguousarray(host[:, :, 1]),
             np.ascontiguousarray(host[:, :, 2]))
 

@@ -41,6 +41,8 @@ class DeviceMatrix:
     #                                  `data` is then unused and every batch is recoded (Engine._run_batch_wide)
     pending: list = field(default_factory=list)   # hostio.Pending uploads still in flight
     unconverted: torch.Tensor | None = None       # uploaded values of another dtype, converted once the upload is in
+    _lock: object = field(default_factory=threading.Lock, repr=False, compare=False)
+    _ready_event: object = field(default=None, repr=False, compare=False)
 
     @property
     def ld(self) -> int:
@@ -48,14 +50,24 @@ class DeviceMatrix:
 
     def ready(self) -> "DeviceMatrix":
         """Joins the uploads (the current stream then waits for their copies) and converts non-float32 values.
-        Call from the thread, and under the stream, that is going to launch kernels on this matrix."""
-        if self.pending:
-            for p in self.pending:
-                p.finish()
-            self.pending = []
-        if self.unconverted is not None:
-            self.data, self.raw = _to_f32_or_wide(self.unconverted)
-            self.unconverted = None
+        Call from the thread, and under the stream, that is going to launch kernels on this matrix; any number of
+        threads / streams may do so (the first one finishes the upload, the others wait for its event)."""
+        with self._lock:
+            if self.pending or self.unconverted is not None:
+                for p in self.pending:
+                    p.finish()
+                self.pending = []
+                if self.unconverted is not None:
+                    self.data, self.raw = _to_f32_or_wide(self.unconverted)
+                    self.unconverted = None
+                dev = (self.data if self.data is not None else self.raw).device
+                self._ready_event = torch.cuda.Event()
+                self._ready_event.record(torch.cuda.current_stream(dev))
+                return self
+            ev = self._ready_event
+        if ev is not None:
+            dev = (self.data if self.data is not None else self.raw).device
+            torch.cuda.current_stream(dev).wait_event(ev)
         return self
 
 
@@ -83,12 +95,11 @@ class Engine:
             max_group_size=hp.max_group_size, ref_group_size=hp.ref_group_size, ref_seg_begin=hp.ref_seg_begin,
             ref_seg_end=hp.ref_seg_end, slot_cap=hp.slot_cap, max_target_group_size=hp.max_target_group_size,
             **{k: self._tables[k].data_ptr() for k in HostPlan.TABLES})
-        self._buf_genes = 0
-        self._ir_vals = self._ir_cnt = self._ws = None
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-        # The reference calls its dispatchers from joblib threads (ctypes drops the GIL): one batch at a time per engine,
-        # since the batch buffers, the per-gene tables and the dispatcher's host read-backs belong to one call.
-        self._lock = threading.RLock()
+        # The reference calls its dispatchers from joblib threads (ctypes drops the GIL).  The C ABI only enqueues work and
+        # owns nothing, so concurrency is a matter of buffers: every host thread gets its own batch buffers (staged lists,
+        # counts, workspace) and the engine needs no lock.
+        self._tls = threading.local()
 
     # ---- sizes ---------------------------------------------------------------------------------------
     @property
@@ -108,19 +119,35 @@ class Engine:
         b = int(min(n_genes, b, _env_int("ILLICO_B200_BATCH_GENES", 1 << 30)))
         return b if b < 8 or b == n_genes else (b // 4) * 4  # multiples of 4 keep the 128-bit staging path
 
-    def _ensure_buffers(self, b: int) -> None:
-        if b <= self._buf_genes:
-            return
+    def _ensure_buffers(self, b: int):
+        """This thread's batch buffers, large enough for ``b`` genes."""
+        t = self._tls
+        if getattr(t, "buf_genes", 0) >= b:
+            return t
         hp = self.host_plan
-        self._ir_vals = self._ir_cnt = self._ws = None
+        t.ir_vals = t.ir_cnt = t.ws = None
         with torch.cuda.device(self.device):
-            self._ir_vals = torch.empty(b * hp.slot_cap, dtype=torch.float32, device=self.device)
-            self._ir_cnt = torch.empty(b * hp.n_segments, dtype=torch.int32, device=self.device)
+            t.ir_vals = torch.empty(b * hp.slot_cap, dtype=torch.float32, device=self.device)
+            t.ir_cnt = torch.empty(b * hp.n_segments, dtype=torch.int32, device=self.device)
             ws = int(self.lib.illico_rank_workspace_bytes(C.byref(self.plan), b))
             if ws == 0:
                 raise _lib.IllicoCudaError("illico_rank_workspace_bytes failed: " + self.lib.illico_last_error().decode())
-            self._ws = torch.empty(ws, dtype=torch.uint8, device=self.device)
-        self._buf_genes = b
+            t.ws = torch.empty(ws, dtype=torch.uint8, device=self.device)
+        t.buf_genes = b
+        return t
+
+    # (bench.py's per-kernel timing and older scripts read the calling thread's buffers through these)
+    @property
+    def _ir_vals(self):
+        return getattr(self._tls, "ir_vals", None)
+
+    @property
+    def _ir_cnt(self):
+        return getattr(self._tls, "ir_cnt", None)
+
+    @property
+    def _ws(self):
+        return getattr(self._tls, "ws", None)
 
     # ---- uploads (plumbing) -----------------------------------------------------------------------------
     def upload_dense(self, X: np.ndarray, gene_lb: int = 0, gene_ub: int | None = None) -> DeviceMatrix:
@@ -144,10 +171,6 @@ class Engine:
 
         ``results`` is a device tensor ``[G, N_total, 3]`` float64 (contiguous).
         """
-        with self._lock:
-            return self._run_batch_locked(M, lb, ub, flags, results, result_gene0, debug)
-
-    def _run_batch_locked(self, M, lb, ub, flags, results, result_gene0, debug=None) -> None:
         b = ub - lb
         if b <= 0:
             return
@@ -159,11 +182,14 @@ class Engine:
             M.ready()
         if M.raw is not None:
             return self._run_batch_wide(M, lb, ub, flags, results, result_gene0, debug)
-        self._ensure_buffers(b)
+        t = self._ensure_buffers(b)
         G, Ntot = results.shape[0], results.shape[1]
         assert results.dtype == torch.float64 and results.is_contiguous() and G == self.n_groups
-        st = torch.cuda.current_stream(self.device).cuda_stream
-        buf = _lib.BatchBuffers(self._ir_vals.data_ptr(), self._ir_cnt.data_ptr(), self._ws.data_ptr(), self._ws.numel())
+        stream = torch.cuda.current_stream(self.device)
+        st = stream.cuda_stream
+        for x in (t.ir_vals, t.ir_cnt, t.ws):   # a thread may enqueue on different streams over time: keep the allocator informed
+            x.record_stream(stream)
+        buf = _lib.BatchBuffers(t.ir_vals.data_ptr(), t.ir_cnt.data_ptr(), t.ws.data_ptr(), t.ws.numel())
         dbg = None
         if debug is not None:
             shape_t = (G, b) if self.is_ovo else (b,)

@@ -48,9 +48,11 @@
  * (at most 12 distinct non-zero values per gene): ONE pass over the input writes each group's histogram over the
  * gene's value table into the 24 bytes its result will occupy, and an epilogue turns it into (p, U, fold change) in
  * place -- no staged lists, no rank kernel (illico_b200/csrc/fused.cu; same statistics bit for bit).  Genes that
- * do not qualify are finished by the stage + rank kernels above, through the same buffers; the caller sees no
- * difference except that `workspace` must be illico_rank_workspace_bytes() large (it also holds the per-gene
- * tables) and that the call may synchronise `stream` to read back which genes were handed over.
+ * do not qualify are listed ON THE DEVICE and finished by the stage + rank kernels above, through the same buffers.
+ *
+ * Every entry point only ENQUEUES work on `stream` and returns: no dispatcher synchronises the stream or reads anything
+ * back (illico_check_csr_sorted is the one call whose answer is a host value).  Calls on different streams with different
+ * illico_batch_buffers_t run concurrently; `workspace` must be illico_rank_workspace_bytes() large.
  */
 #ifndef ILLICO_B200_H
 #define ILLICO_B200_H
@@ -117,8 +119,8 @@ int illico_abi_version(void);
 const char* illico_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t illico_launch_count(void);
-/* with ILLICO_PROFILE=1 in the environment: duration (ms, CUDA events on the caller's stream) of the last
- * fused_pass_kernel launch of this thread, -1 if none (bench.py's roofline) */
+/* >= 0 when the last dispatcher call of this thread enqueued a fused pass (fused.cu), -1 when it took the general stage +
+ * rank path (per-kernel durations: illico_profile_report) */
 double illico_last_fused_ms(void);
 /* with ILLICO_PROFILE=1: every kernel this library launches is bracketed by CUDA events on the launching stream.  This
  * call waits for the recorded launches, writes one line "kernel_name\ttotal_ms\tlaunches\n" per kernel (in first-launch

@@ -24,8 +24,7 @@ for name in ("edge", "negatives", "k562_mini_cont"):
 # count data: the fused single-pass kernels (TMA ring + mbarriers, shared-memory histograms), with genes handed back
 from illico_b200 import synth  # noqa: E402
 
-os.environ["ILLICO_FUSED_MAX_HANDBACK"] = "1.0"
-os.environ["ILLICO_FUSED_GAP"] = "2"
+os.environ["ILLICO_FUSED_LIST_SHARE"] = "1.0"
 X, labels = synth.k562_like(seed=3, n_cells=3000, n_genes=24, n_perts=9)
 X[:, 5] = np.random.RandomState(0).poisson(30.0, X.shape[0])   # more than 12 distinct values: handed back
 for fmt in ("dense", "csr"):

@@ -175,19 +175,31 @@ def test_backed_streaming_matches_in_ram(tmp_path, test):
     ref = reference if test == "ovo" else None
     path = tmp_path / "x.f32"
     X.tofile(path)
-    want = asymptotic_wilcoxon(FakeAnnData(X, labels), is_log1p=False, group_keys="pert", reference=ref).to_numpy()
+    # the ORACLE is the yardstick, and the committed golden vectors of this case
+    g, po, Uo, fco = oracle.run(X, labels, ref, is_log1p=False)
+    ref_row = int(np.searchsorted(g, ref)) if ref is not None else None
+    G = len(g)
     bd = _BackedDense(path, X.shape)
     got = asymptotic_wilcoxon(FakeAnnData(bd, labels), is_log1p=False, group_keys="pert", reference=ref, batch_size=64,
-                              n_threads=3).to_numpy()
+                              n_threads=3)
     assert bd.reads == -(-X.shape[1] // 64)
-    np.testing.assert_array_equal(got, want)
+    assert_parity(planes(got, G, X.shape[1]), (po, Uo, fco), ref_row=ref_row, what="backed dense vs oracle")
     got = asymptotic_wilcoxon(FakeAnnData(_BackedCSC(sparse.csc_matrix(X)), labels), is_log1p=False, group_keys="pert",
                               reference=ref, batch_size=50, n_threads=2)
-    g = len(set(labels))
-    p, U, _ = planes(got, g, X.shape[1])
-    wp, wU, _ = planes(want, g, X.shape[1])
-    np.testing.assert_array_equal(U, wU)
-    np.testing.assert_allclose(p, wp, rtol=1e-12, atol=2.3e-308)
+    assert_parity(planes(got, G, X.shape[1]), (po, Uo, fco), ref_row=ref_row, what="backed CSC vs oracle")
+    # the package's own on-disk containers (np.memmap behind obj[:, lb:ub]; BASELINE config 4 on boxes without h5py)
+    from illico_b200.backed import MemmapCSC, MemmapDense, save_csc, save_dense
+
+    Xc = sparse.csc_matrix(X)
+    save_csc(str(tmp_path / "csc"), Xc.data, Xc.indices, Xc.indptr, Xc.shape)
+    save_dense(str(tmp_path / "dense.bin"), X)
+    for cont in (MemmapCSC(str(tmp_path / "csc")), MemmapDense(str(tmp_path / "dense.bin"))):
+        got = asymptotic_wilcoxon(FakeAnnData(cont, labels), is_log1p=False, group_keys="pert", reference=ref, batch_size=96,
+                                  n_threads=4)
+        assert_parity(planes(got, G, X.shape[1]), (po, Uo, fco), ref_row=ref_row, what=f"{type(cont).__name__} vs oracle")
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "batched.npz"))
+    want = gold[C.combo_key("csc", test, True, True, "two-sided", False)]
+    assert_parity(planes(got, G, X.shape[1]), (want[0], want[1], want[2]), ref_row=ref_row, what="backed vs golden")
 
 
 def test_k562_shape_properties_and_oracle_sample():
@@ -390,8 +402,7 @@ def test_fused_ovo_routes_match_general_path_and_oracle(monkeypatch, kind):
 
     monkeypatch.setenv("ILLICO_OVO_FUSED", "1")
     monkeypatch.setenv("ILLICO_PROFILE", "1")
-    monkeypatch.setenv("ILLICO_FUSED_MAX_HANDBACK", "1.0")   # keep the fused pass although many genes are handed back
-    monkeypatch.setenv("ILLICO_FUSED_GAP", "2")              # ... in several separate runs
+    monkeypatch.setenv("ILLICO_FUSED_LIST_SHARE", "1.0")     # hand the flagged genes back one by one however many there are
     groups, fused = _run(X, labels, ref, batch_size="auto", **kw)
     assert _lib.load().illico_last_fused_ms() >= 0, "the fused kernel did not run"
     monkeypatch.setenv("ILLICO_OVO_FUSED", "0")
@@ -456,8 +467,7 @@ def test_fused_ovr_routes_match_general_path_and_oracle(monkeypatch, kind):
 
     monkeypatch.setenv("ILLICO_OVR_FUSED", "1")
     monkeypatch.setenv("ILLICO_PROFILE", "1")
-    monkeypatch.setenv("ILLICO_FUSED_MAX_HANDBACK", "1.0")
-    monkeypatch.setenv("ILLICO_FUSED_GAP", "2")
+    monkeypatch.setenv("ILLICO_FUSED_LIST_SHARE", "1.0")
     groups, fused = _run(X, labels, None, batch_size="auto", **kw)
     assert _lib.load().illico_last_fused_ms() >= 0, "the fused kernel did not run"
     monkeypatch.setenv("ILLICO_OVR_FUSED", "0")
@@ -505,8 +515,7 @@ def test_fused_csr_routes_match_general_path_and_oracle(monkeypatch, test, kind)
 
     monkeypatch.setenv("ILLICO_CSR_FUSED", "1")
     monkeypatch.setenv("ILLICO_PROFILE", "1")
-    monkeypatch.setenv("ILLICO_FUSED_MAX_HANDBACK", "1.0")
-    monkeypatch.setenv("ILLICO_FUSED_GAP", "2")
+    monkeypatch.setenv("ILLICO_FUSED_LIST_SHARE", "1.0")
     groups, fused = _run(Xs, labels, reference, batch_size="auto", **kw)
     assert _lib.load().illico_last_fused_ms() >= 0, "the fused CSR pass did not run"
     monkeypatch.setenv("ILLICO_CSR_FUSED", "0")
@@ -524,8 +533,8 @@ def test_fused_csr_routes_match_general_path_and_oracle(monkeypatch, test, kind)
 
 @pytest.mark.parametrize("fmt", ["dense", "csr"])
 def test_fused_gate_falls_back_when_many_genes_are_handed_back(monkeypatch, fmt):
-    """Default policy: a batch whose handed-back genes (merged runs) cover more than 30 % of it is done by the general
-    path as a whole; the answer is the same either way."""
+    """Default policy, decided on the device: when more than an eighth of a batch is flagged the whole batch goes through
+    the general path (hand-back mode ALL); the answer is the same either way."""
     X, labels, ref = _fused_case("middle")
     X = np.abs(X)
     X[X > 1e20] = 3.0
@@ -584,30 +593,47 @@ def test_dispatchers_called_from_concurrent_threads(fmt):
 
 @pytest.mark.parametrize("test", ["ovo", "ovr"])
 def test_fused_dense_compacted_hand_back(monkeypatch, test):
-    """Scattered handed-back genes (here 7 of 72): their columns are gathered into a compact matrix, ranked by the
-    general path and scattered back; same answer as merged runs and as the general path alone."""
+    """Scattered handed-back genes (here 7 of 72), listed on the device: staged one by one from the matrix and ranked by
+    the general path with the device-side count (mode LIST); same answer when the whole batch is redone (mode ALL) and
+    from the general path alone."""
     X, labels, ref = _fused_case("middle")
     X = np.abs(X)
     X[X > 1e20] = 3.0
     reference = ref if test == "ovo" else None
-    monkeypatch.setenv("ILLICO_FUSED_COMPACT", "1")
+    monkeypatch.setenv("ILLICO_FUSED_LIST_SHARE", "1.0")
     groups, compact = _run(X, labels, reference, is_log1p=False)
-    monkeypatch.setenv("ILLICO_FUSED_COMPACT", "0")
-    monkeypatch.setenv("ILLICO_FUSED_MAX_HANDBACK", "1.0")
+    monkeypatch.setenv("ILLICO_FUSED_LIST_SHARE", "0.0")
     _, merged = _run(X, labels, reference, is_log1p=False)
     monkeypatch.setenv("ILLICO_OVO_FUSED", "0")
     monkeypatch.setenv("ILLICO_OVR_FUSED", "0")
     _, general = _run(X, labels, reference, is_log1p=False)
-    for a, b in zip(compact, merged):
+    for a, b in zip(merged, general):
         np.testing.assert_array_equal(a, b)
-    np.testing.assert_array_equal(compact[1], general[1])
-    rows = np.ones(len(groups), bool)
-    if reference is not None:
-        rows[int(np.searchsorted(groups, reference))] = False
-    np.testing.assert_allclose(compact[0][rows], general[0][rows], rtol=1e-13, atol=2.3e-308)
+    for a, b in zip(compact, general):
+        np.testing.assert_array_equal(a, b)
     g, p, U, fc = oracle.run(X, labels, reference, is_log1p=False)
     ref_row = int(np.searchsorted(groups, reference)) if reference is not None else None
     assert_parity(compact, (p, U, fc), ref_row=ref_row, what=f"compacted hand-back {test}")
+
+
+@pytest.mark.parametrize("fmt", ["dense", "csr"])
+@pytest.mark.parametrize("test", ["ovo", "ovr"])
+def test_hand_back_modes_on_the_device(monkeypatch, fmt, test):
+    """The three device-side hand-back modes of the fused dispatchers (none / listed genes / whole batch) on one matrix:
+    count genes with 0, 3 and 40 % high-count genes scattered among them; dense and CSR; against the oracle."""
+    from illico_b200 import synth
+
+    for frac in (0.0, 0.03, 0.4):
+        X, labels = synth.k562_like(seed=95, n_cells=5000, n_genes=200, n_perts=14)
+        rng = np.random.RandomState(3)
+        for j in rng.choice(200, size=int(200 * frac), replace=False):
+            X[:, j] = rng.poisson(25.0, X.shape[0]) * (rng.rand(X.shape[0]) < 0.6)
+        reference = synth.CONTROL if test == "ovo" else None
+        Xf = C.to_format(X, fmt)
+        groups, got = _run(Xf, labels, reference, is_log1p=False)
+        g, p, U, fc = oracle.run(Xf, labels, reference, is_log1p=False, n_threads=4)
+        ref_row = int(np.searchsorted(groups, reference)) if reference is not None else None
+        assert_parity(got, (p, U, fc), ref_row=ref_row, what=f"hand-back {fmt} {test} frac={frac}")
 
 
 @pytest.mark.parametrize("fmt", ["dense", "csr"])
