@@ -36,8 +36,11 @@
 namespace illico {
 
 // general path (stage.cu, rank_ovo.cu, rank_ovr.cu) for the genes the fused path hands back
-int launch_stage_dense_list(const float* X, long long ld, int gene_lb, const int* list, const int* n_list_dev,
-                            const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, cudaStream_t stream);
+int launch_stage_dense_list(const float* X, long long ld, int gene_lb, const int* list, const int* n_list_dev, const int* mode_dev,
+                            int want_mode, const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, cudaStream_t stream);
+int launch_stage_dense_tma_if(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
+                              uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream, int segs_per_cta_req,
+                              const int* mode_dev, int want_mode);
 int launch_stage_csr_if(const float*, const int32_t*, const long long*, int, int, const illico_plan_t*, float*, uint32_t*, void*, size_t,
                         const int*, int, cudaStream_t);
 int launch_stage_csr_list(const float*, const int32_t*, const long long*, int, int, const int*, const int*, int, int,
@@ -180,7 +183,7 @@ template <int ROWS, int STAGES, int BUF, int MINB, bool OVO>
 __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const float* __restrict__ X, long long ld, int gene_lb,
                                                                          int b, const illico_plan_t pl, int groups_per_cta,
                                                                          Gtab gt, int bs, unsigned long long* __restrict__ rec,
-                                                                         long long gstride) {
+                                                                         long long gstride, int share_1024) {
     using L = FusedLayout<ROWS, STAGES, BUF>;
     static_assert(32 % ROWS == 0 && BUF > ROWS, "layout");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -199,6 +202,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const f
     if (nv <= 0) return;
     // every gene of this CTA was already handed back by the table step (continuous data: all of them): nothing to stream.
     // The decision is the CTA's own, taken on the device: the host enqueues the pass without knowing.
+    // Likewise when the table step flagged more genes than are handed back one by one: the whole batch will be redone by
+    // the general path (fused_list_kernel takes the same decision from the same count), so the pass has nothing to add.
+    if ((long long)gt.n_bad[0] * 1024 > (long long)b * share_1024) return;
     if (__syncthreads_and(t >= FUSED_LANES || g0 + t >= b || gt.bad[g0 + t] != 0)) return;
 
     if (t == 0) {
@@ -820,7 +826,7 @@ int launch_pass_t(const float* X, long long ld, int gene_lb, int b, const illico
     ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
     const dim3 grid((unsigned)((b + FUSED_LANES - 1) / FUSED_LANES), (unsigned)((plan->n_groups + gpc - 1) / gpc));
     ILLICO_LAUNCH("fused_pass_kernel", stream, kern<<<grid, FUSED_THREADS, L::BYTES, stream>>>(X, ld, gene_lb, b, *plan, gpc, gt, bs,
-                                                    reinterpret_cast<unsigned long long*>(results), gstride));
+                                                    reinterpret_cast<unsigned long long*>(results), gstride, list_share_1024()));
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -892,7 +898,11 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
     // path with the device-side count (an empty list costs three nearly empty launches)
     ILLICO_LAUNCH("fused_list_kernel", stream, fused_list_kernel<<<1, 1024, 0, stream>>>(b, gt, list_share_1024(), 1024, 0));
     ILLICO_CUDA_OK(cudaGetLastError());
-    if (launch_stage_dense_list(X, ld, gene_lb, gt.list, gt.n_bad + 1, plan, buf->ir_vals, buf->ir_cnt, stream)) return 1;
+    if (launch_stage_dense_list(X, ld, gene_lb, gt.list, gt.n_bad + 1, gt.n_bad + 2, HB_LIST, plan, buf->ir_vals, buf->ir_cnt, stream))
+        return 1;
+    if (launch_stage_dense_tma_if(X, ld, gene_lb, b, plan, buf->ir_vals, buf->ir_cnt, 0, plan->n_segments, stream, 0, gt.n_bad + 2,
+                                  HB_ALL))
+        return 1;
     // the rank kernels' scratch lies behind the tables (they are read until the list has been ranked)
     const size_t tab = (gtab_bytes(b, plan->n_groups) + 255) & ~(size_t)255;
     if (buf->workspace_bytes <= tab) return 1;

@@ -155,11 +155,13 @@ __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_kernel(const flo
 __global__ void __launch_bounds__(STAGE_WARPS * 32) stage_dense_list_kernel(const float* __restrict__ X, long long ld, int gene_lb,
                                                                             const int* __restrict__ list,
                                                                             const int* __restrict__ n_list_dev,
+                                                                            const int* __restrict__ mode_dev, int want_mode,
                                                                             const illico_plan_t pl, float* __restrict__ ir_vals,
                                                                             uint32_t* __restrict__ ir_cnt, int segs_per_cta) {
     constexpr int NT = STAGE_WARPS * 32;
     __shared__ __align__(16) float wbuf[NT][8];
     const int lane = threadIdx.x & 31, t = threadIdx.x;
+    if (mode_dev && *mode_dev != want_mode) return;
     const int n = *n_list_dev;
     if (n <= 0) return;
     const int S = pl.n_segments;
@@ -580,7 +582,8 @@ int launch_stage_csr_list(const float* data, const int32_t* indices, const long 
 
 // stages the genes of a device-side list from a dense matrix (see stage_dense_list_kernel)
 int launch_stage_dense_list(const float* X, long long ld, int gene_lb, const int* list, const int* n_list_dev,
-                            const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt, cudaStream_t stream) {
+                            const int* mode_dev, int want_mode, const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt,
+                            cudaStream_t stream) {
     const int S = plan->n_segments;
     if (S <= 0) return 0;
     if (ld <= 0 || ld >= (1ll << 30)) { set_error("leading dimension %lld out of range", ld); return 1; }
@@ -590,8 +593,8 @@ int launch_stage_dense_list(const float* X, long long ld, int gene_lb, const int
     if (segs_per_cta < 1) segs_per_cta = 1;
     if (segs_per_cta > STAGE_MAX_SEGS) segs_per_cta = STAGE_MAX_SEGS;
     ILLICO_LAUNCH("stage_dense_list_kernel", stream,
-                  stage_dense_list_kernel<<<148 * 8, STAGE_WARPS * 32, 0, stream>>>(X, ld, gene_lb, list, n_list_dev, *plan, ir_vals, ir_cnt,
-                                                                                     segs_per_cta));
+                  stage_dense_list_kernel<<<148 * 8, STAGE_WARPS * 32, 0, stream>>>(X, ld, gene_lb, list, n_list_dev, mode_dev, want_mode,
+                                                                                     *plan, ir_vals, ir_cnt, segs_per_cta));
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }

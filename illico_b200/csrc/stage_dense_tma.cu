@@ -69,7 +69,11 @@ __global__ void __launch_bounds__(TMA_THREADS) stage_dense_tma_kernel(const floa
                                                                       int b, const illico_plan_t pl,
                                                                       float* __restrict__ ir_vals,
                                                                       uint32_t* __restrict__ ir_cnt, int segs_per_cta, int seg_lo,
-                                                                      int seg_hi, int no_store) {
+                                                                      int seg_hi, int no_store, int tiles_x, int tiles_y,
+                                                                      const int* __restrict__ mode_dev, int want_mode) {
+    // A decision taken on the device (hand-back of the fused paths): the host enqueued this launch without knowing
+    // whether it is needed.  Such launches are persistent (a fixed 1-D grid walking the tiles), so a no costs microseconds.
+    if (mode_dev && *mode_dev != want_mode) return;
     using L = TmaLayout<VEC, ROWS, STAGES>;
     static_assert(32 % ROWS == 0, "a 32-row group of the permutation holds whole stages");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -78,11 +82,12 @@ __global__ void __launch_bounds__(TMA_THREADS) stage_dense_tma_kernel(const floa
     uint16_t* cnt_tile = reinterpret_cast<uint16_t*>(smem + L::CNT_OFF);
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int S = pl.n_segments;
-    const int s_begin = seg_lo + blockIdx.y * segs_per_cta, s_end = min(seg_hi, s_begin + segs_per_cta);
-    const int p_begin = pl.seg_pos[s_begin], p_end = pl.seg_pos[s_end];
-    const int g0 = blockIdx.x * L::GENES;                      // first gene of the CTA inside the batch
-    // bytes of the row piece this CTA reads: whole 16-byte units (the host checked that the round-up stays in the row)
-    const uint32_t row_bytes = (uint32_t)min(L::GENES, (b - g0 + 3) & ~3) * 4u;
+    // tiles: (256 * VEC genes) x (segs_per_cta segments).  A 2-D grid gives every CTA its own tile; a 1-D (persistent)
+    // grid walks them.  The ring's stage counters run on across tiles, so the producer fills the ring with the next
+    // tile's rows while the consumers finish the current one.
+    const long long n_tiles = (long long)tiles_x * tiles_y;
+    const long long tile0 = (gridDim.y > 1 || gridDim.x == (unsigned)n_tiles) ? (long long)blockIdx.y * gridDim.x + blockIdx.x : blockIdx.x;
+    const long long tile_step = (gridDim.y > 1 || gridDim.x == (unsigned)n_tiles) ? n_tiles : gridDim.x;
 
     if (t == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -97,10 +102,17 @@ __global__ void __launch_bounds__(TMA_THREADS) stage_dense_tma_kernel(const floa
         // ---------------- producer warp: one bulk copy per (row, CTA gene range)
         uint64_t policy;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-        const char* base = reinterpret_cast<const char*>(X + gene_lb + g0);
         const unsigned long long ldb = (unsigned long long)ld * 4ull;
+        int k = 0;                                                       // stage counter (runs on across tiles)
+        for (long long tile = tile0; tile < n_tiles; tile += tile_step) {
+        const int bx = (int)(tile % tiles_x), by = (int)(tile / tiles_x);
+        const int s_begin = seg_lo + by * segs_per_cta, s_end = min(seg_hi, s_begin + segs_per_cta);
+        const int p_begin = pl.seg_pos[s_begin], p_end = pl.seg_pos[s_end];
+        const int g0 = bx * L::GENES;                              // first gene of the tile inside the batch
+        // bytes of the row piece this tile reads: whole 16-byte units (the host checked that the round-up stays in the row)
+        const uint32_t row_bytes = (uint32_t)min(L::GENES, (b - g0 + 3) & ~3) * 4u;
+        const char* base = reinterpret_cast<const char*>(X + gene_lb + g0);
         int myrow = (p_begin + lane < p_end) ? pl.perm[p_begin + lane] : 0;
-        int k = 0;                                                       // stage counter
         for (int p = p_begin; p < p_end; p += 32) {
             const int nxt = (p + 32 + lane < p_end) ? pl.perm[p + 32 + lane] : 0;   // next group's rows, ahead of use
             const int nrows = min(32, p_end - p);
@@ -120,10 +132,17 @@ __global__ void __launch_bounds__(TMA_THREADS) stage_dense_tma_kernel(const floa
             }
             myrow = nxt;
         }
+        }
         return;
     }
 
     // ---------------- consumer warps: lane = VEC adjacent genes
+    int k = 0;                                                           // stage counter (runs on across tiles)
+    for (long long tile = tile0; tile < n_tiles; tile += tile_step) {
+    const int bx = (int)(tile % tiles_x), by = (int)(tile / tiles_x);
+    const int s_begin = seg_lo + by * segs_per_cta, s_end = min(seg_hi, s_begin + segs_per_cta);
+    const int p_begin = pl.seg_pos[s_begin], p_end = pl.seg_pos[s_end];
+    const int g0 = bx * L::GENES;
     const int jb = g0 + t * VEC;
     bool act[VEC];
     float* gene_base[VEC];
@@ -153,7 +172,6 @@ __global__ void __launch_bounds__(TMA_THREADS) stage_dense_tma_kernel(const floa
         }
     };
     const unsigned char* my_ring = smem + L::RING_OFF + t * VEC * 4;
-    int k = 0;
     for (int p = p_begin; p < p_end; p += ROWS, ++k) {
         const int slot = k % STAGES;
         mbar_wait(bars + 8 * slot, (k / STAGES) & 1);
@@ -230,6 +248,8 @@ __global__ void __launch_bounds__(TMA_THREADS) stage_dense_tma_kernel(const floa
             for (int ls = 0; ls < nseg; ++ls) dst[ls] = cnt_tile[ls * L::GENES + g];
         }
     }
+    asm volatile("bar.sync 1, %0;" ::"r"(TMA_CONSUMERS) : "memory");   // the count tile is free for the next tile
+    }
 }
 
 int env_int(const char* name, int dflt) {
@@ -239,16 +259,26 @@ int env_int(const char* name, int dflt) {
 
 template <int VEC, int ROWS, int STAGES>
 int launch_t(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt,
-             int segs_per_cta, int seg_lo, int seg_hi, cudaStream_t stream) {
+             int segs_per_cta, int seg_lo, int seg_hi, cudaStream_t stream, const int* mode_dev, int want_mode) {
     using L = TmaLayout<VEC, ROWS, STAGES>;
     const unsigned gx = (unsigned)((b + L::GENES - 1) / L::GENES);
     const unsigned gy = (unsigned)((seg_hi - seg_lo + segs_per_cta - 1) / segs_per_cta);
     const size_t smem = L::bytes(segs_per_cta);
     auto kern = stage_dense_tma_kernel<VEC, ROWS, STAGES>;
     ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(gx, gy);
+    if (mode_dev) {                                    // decided on the device: persistent 1-D grid
+        int occ = 0;
+        ILLICO_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TMA_THREADS, smem));
+        long long ctas = 148ll * (occ > 0 ? occ : 1);
+        if (ctas > (long long)gx * gy) ctas = (long long)gx * gy;
+        if (ctas == (long long)gx * gy && gy > 1) ctas -= 1;   // (a 1-D grid of exactly n_tiles CTAs would read as 2-D)
+        grid = dim3((unsigned)ctas, 1);
+    }
     ILLICO_LAUNCH("stage_dense_tma_kernel", stream,
-                  kern<<<dim3(gx, gy), TMA_THREADS, smem, stream>>>(X, ld, gene_lb, b, *plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi,
-                                                                    env_int("ILLICO_STAGE_TMA_NOSTORE", 0)));  // (measurement aid: read path alone)
+                  kern<<<grid, TMA_THREADS, smem, stream>>>(X, ld, gene_lb, b, *plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi,
+                                                            env_int("ILLICO_STAGE_TMA_NOSTORE", 0),   // (measurement aid: read path alone)
+                                                            (int)gx, (int)gy, mode_dev, want_mode));
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -266,8 +296,9 @@ bool stage_dense_tma_ok(const float* X, long long ld, int gene_lb, int b, const 
 
 // Stages segments [seg_lo, seg_hi) of the plan (the whole plan: 0, n_segments; the control group alone for the fused
 // one-versus-reference path).
-int launch_stage_dense_tma(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
-                           uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream, int segs_per_cta_req) {
+int launch_stage_dense_tma_if(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
+                              uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream, int segs_per_cta_req,
+                              const int* mode_dev, int want_mode) {
     const int S = plan->n_segments;
     if (seg_lo < 0 || seg_hi > S || seg_lo >= seg_hi) { set_error("segment range [%d, %d) out of bounds", seg_lo, seg_hi); return 1; }
     long long avg = plan->n_cells / S;
@@ -275,15 +306,20 @@ int launch_stage_dense_tma(const float* X, long long ld, int gene_lb, int b, con
     int segs_per_cta = segs_per_cta_req > 0 ? segs_per_cta_req : (int)(env_int("ILLICO_STAGE_ROWS", 512) / avg);
     if (segs_per_cta < 1) segs_per_cta = 1;
     if (segs_per_cta > TMA_MAX_SEGS) segs_per_cta = TMA_MAX_SEGS;
-    if ((S + segs_per_cta - 1) / segs_per_cta > 65535) return -1;      // caller falls back to the plain kernel
+    if (!mode_dev && (S + segs_per_cta - 1) / segs_per_cta > 65535) return -1;      // caller falls back to the plain kernel
     // Ring configurations measured at the K562 shape (profiles/README.md): all within 3 % of each other; one gene
     // per lane (1 KB row pieces, 32 KB ring, 2-3 CTAs per SM) is the fastest and has the smallest footprint.
     switch (env_int("ILLICO_STAGE_TMA_CFG", 0)) {
-        case 1: return launch_t<2, 4, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream);
-        case 2: return launch_t<2, 8, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream);
-        case 3: return launch_t<4, 4, 3>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream);
-        default: return launch_t<1, 8, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream);
+        case 1: return launch_t<2, 4, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
+        case 2: return launch_t<2, 8, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
+        case 3: return launch_t<4, 4, 3>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
+        default: return launch_t<1, 8, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
     }
+}
+
+int launch_stage_dense_tma(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
+                           uint32_t* ir_cnt, int seg_lo, int seg_hi, cudaStream_t stream, int segs_per_cta_req) {
+    return launch_stage_dense_tma_if(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, seg_lo, seg_hi, stream, segs_per_cta_req, nullptr, 0);
 }
 
 }  // namespace illico
