@@ -74,15 +74,21 @@ struct Gtab {
     int* list;                 // [bs]        the genes handed back to the general path (built on the device after the pass)
     int* cmap;                 // [bs]        CSR hand-back: position of a gene in `list`, -1 when it is not on it
     unsigned char* bad;        // [bs]        1 = the gene takes the general path
+    unsigned char* cls;        // [bs]        what the table step found: CLS_NARROW | CLS_IDENT | CLS_WANTS_WIDE
+    unsigned char* mode;       // [bs]        0 = 12-slot histogram records (fused_pass_kernel), 1 = wide table (fused_wide_pass_kernel)
+    uint32_t* wm;              // [DW/2][bs]  wide table: multiplicity of the integer values q + 1 | q + 33 (16 bits each) in the control
     double* gc;                // [GC_N][Gs]  per-group constants of the p-value (fused_group_kernel)
     int Gs;                    //             groups, padded to a multiple of 64
 };
+constexpr int DW = 64;                                // wide table: integer counts 1 .. DW, indexed by value
+constexpr int CLS_NARROW = 1, CLS_IDENT = 2, CLS_WANTS_WIDE = 4;
+constexpr int WIDE_FROM = 11;                         // control tables this full go wide when they can (the other groups add values)
 constexpr int HB_NONE = 0, HB_LIST = 1, HB_ALL = 2;   // hand-back modes (control block [2])
 constexpr int GC_MU = 0, GC_NRNT = 1, GC_PROD12 = 2, GC_DENOM = 3, GC_INV_NT = 4, GC_N = 5;
 
 size_t gtab_bytes(int b, int G) {
     const size_t bs = (size_t)((b + 63) & ~63), Gs = (size_t)((G + 63) & ~63);
-    return bs * ((size_t)DCAP * 20 + 4 + 8 + 8 + 1 + 8) + Gs * 8 * GC_N + 1024;
+    return bs * ((size_t)DCAP * 20 + 4 + 8 + 8 + 1 + 8 + 2 + (size_t)DW * 2) + Gs * 8 * GC_N + 1024;
 }
 Gtab gtab_carve(void* ws, int b, int G) {
     const size_t bs = (size_t)((b + 63) & ~63), Gs = (size_t)((G + 63) & ~63);
@@ -100,31 +106,50 @@ Gtab gtab_carve(void* ws, int b, int G) {
     c.n_bad = reinterpret_cast<int*>(p); p += 64;
     c.list = reinterpret_cast<int*>(p); p += bs * 4;
     c.cmap = reinterpret_cast<int*>(p); p += bs * 4;
-    c.bad = reinterpret_cast<unsigned char*>(p);
+    c.wm = reinterpret_cast<uint32_t*>(p); p += bs * 2 * DW;
+    c.bad = reinterpret_cast<unsigned char*>(p); p += bs;
+    c.cls = reinterpret_cast<unsigned char*>(p); p += bs;
+    c.mode = reinterpret_cast<unsigned char*>(p);
     return c;
 }
 
 // ---- 1. per-gene tables from the staged segments [seg_lo, seg_hi) -------------------------------------------------
 // One warp per gene; lane t holds table slot t in registers.  Equal values of a 32-value load are merged with
 // match.any, their leaders are inserted one after the other.
+// Two tables are tried at once.  NARROW: at most DCAP distinct values of any kind (keys + multiplicities, slots in
+// ascending value order).  WIDE (wide_on, one-versus-reference only): every value is an integer count in 1 .. DW, the
+// table is indexed by the value itself (wm[v - 1] = multiplicity) and holds no keys.  What the gene qualifies for goes to
+// gt.cls; fused_mode_kernel turns that into the gene's mode.
+constexpr float ROUND_MAGIC = 12582912.0f;            // 1.5 * 2^23: v + MAGIC has the integer nearest to v in its low mantissa bits
+constexpr uint32_t ROUND_MAGIC_BITS = 0x4B400000u;
+// bin (value - 1) of an integer count in 1 .. DW; anything else (zero, negative, fractional, huge, NaN) gives ok = false
+__device__ __forceinline__ uint32_t count_bin(float v, bool& ok) {
+    const float tt = __fadd_rn(v, ROUND_MAGIC);
+    const uint32_t q1 = __float_as_uint(tt) - (ROUND_MAGIC_BITS + 1u);
+    ok = (__fsub_rn(tt, ROUND_MAGIC) == v) && (q1 < (uint32_t)DW);
+    return q1;
+}
+
 __global__ void __launch_bounds__(256) fused_ctab_kernel(const float* __restrict__ ir_vals, const uint32_t* __restrict__ ir_cnt,
                                                          int b, const illico_plan_t pl, int seg_lo, int seg_hi, int is_log1p,
-                                                         Gtab gt, int bs) {
-    const int lane = threadIdx.x & 31;
+                                                         Gtab gt, int bs, int wide_on) {
+    __shared__ uint32_t wh[8][DW];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int S = pl.n_segments;
     for (int j = warp; j < b; j += nwarps) {
         float mykey = 0.0f;
         uint32_t mycnt = 0;
         int D = 0;
-        bool bad = false;
-        for (int s = seg_lo; s < seg_hi && !bad; ++s) {
+        bool nbad = false;                 // the narrow table does not hold the gene
+        bool general = false;              // a negative value or a NaN: neither table
+        for (int s = seg_lo; s < seg_hi && !nbad; ++s) {
             const int c = (int)ir_cnt[(long long)j * S + s];
             const float* src = ir_vals + (long long)j * pl.slot_cap + pl.seg_base[s];
-            for (int i0 = 0; i0 < c && !bad; i0 += 32) {
+            for (int i0 = 0; i0 < c && !nbad; i0 += 32) {
                 const bool valid = i0 + lane < c;
                 const float v = valid ? src[i0 + lane] : 0.0f;
-                if (__any_sync(FULL, valid && !(v > 0.0f))) { bad = true; break; }   // negative or NaN: general path
+                if (__any_sync(FULL, valid && !(v > 0.0f))) { nbad = general = true; break; }   // negative or NaN: general path
                 const unsigned same = __match_any_sync(FULL, __float_as_uint(v));
                 const bool leader = valid && (__ffs(same) - 1 == lane);
                 const uint32_t n = (uint32_t)__popc(same);
@@ -141,16 +166,56 @@ __global__ void __launch_bounds__(256) fused_ctab_kernel(const float* __restrict
                         if (lane == D) { mykey = vv; mycnt = nn; }
                         ++D;
                     } else {
-                        bad = true;
+                        nbad = true;
                         break;
                     }
                 }
             }
         }
-        if (bad) {
-            if (lane == 0) { gt.bad[j] = 1; atomicAdd(gt.n_bad, 1); }
-            continue;
+        // ---- wide table: the multiplicities by value.  A gene the narrow table holds gets it from that table; one it
+        // does not hold has its control values read once more (they are in L2).
+        bool ident = wide_on != 0 && !general;
+        if (ident) {
+            wh[wl][lane] = 0u;
+            wh[wl][lane + 32] = 0u;
+            __syncwarp();
+            if (!nbad) {
+                bool okv = true;
+                const uint32_t q1 = count_bin(mykey, okv);
+                if (__any_sync(FULL, lane < D && !okv)) ident = false;
+                else if (lane < D) wh[wl][q1] = mycnt;
+            } else {
+                for (int s = seg_lo; s < seg_hi && ident; ++s) {
+                    const int c = (int)ir_cnt[(long long)j * S + s];
+                    const float* src = ir_vals + (long long)j * pl.slot_cap + pl.seg_base[s];
+                    for (int i0 = 0; i0 < c; i0 += 32) {
+                        const bool valid = i0 + lane < c;
+                        const float v = valid ? src[i0 + lane] : 0.0f;
+                        bool okv;
+                        const uint32_t q1 = count_bin(v, okv);
+                        if (__any_sync(FULL, valid && !okv)) { ident = false; break; }
+                        const unsigned same = __match_any_sync(FULL, __float_as_uint(v));
+                        if (valid && (__ffs(same) - 1 == lane)) wh[wl][q1] += (uint32_t)__popc(same);   // leaders: distinct bins
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncwarp();
         }
+        int cls = nbad ? 0 : CLS_NARROW;
+        if (ident) {
+            const uint32_t c0 = wh[wl][lane], c1 = wh[wl][lane + 32];
+            if (__any_sync(FULL, (c0 | c1) > 0xffffu)) {
+                ident = false;                                        // (16-bit multiplicities in the pass's shared table)
+            } else {
+                gt.wm[(long long)lane * bs + j] = c0 | (c1 << 16);    // packed as the pass keeps it: values q + 1 | q + 33
+                cls |= CLS_IDENT;
+                if (nbad || D >= WIDE_FROM) cls |= CLS_WANTS_WIDE;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) gt.cls[j] = (unsigned char)cls;
+        if (nbad) continue;
         // slots in ascending value order (position = number of smaller values); the rest are free
         int pos = 0;
         for (int t = 0; t < D; ++t) pos += (__shfl_sync(FULL, mykey, t) < mykey) ? 1 : 0;
@@ -160,8 +225,23 @@ __global__ void __launch_bounds__(256) fused_ctab_kernel(const float* __restrict
         const uint32_t nnz = warp_sum<uint32_t>(mine ? mycnt : 0u);
         const unsigned long long tie = warp_sum_u64(mine ? (unsigned long long)cube_minus((long long)mycnt) : 0ull);
         const double sum = warp_sum_f64(mine ? (double)mycnt * fc_value(mykey, is_log1p) : 0.0);
-        if (lane == 0) { gt.nnz[j] = nnz; gt.tie[j] = tie; gt.sum[j] = sum; gt.bad[j] = 0; }
+        if (lane == 0) { gt.nnz[j] = nnz; gt.tie[j] = tie; gt.sum[j] = sum; }
     }
+}
+
+// Mode of every gene, per tile of FUSED_LANES genes (= one CTA column of the passes): a tile goes wide when one of its
+// genes needs the wide table (too many distinct values for the narrow one, or nearly so); every gene of such a tile that
+// qualifies then rides along, the others keep the narrow pass (both passes then stream the tile; raw-count matrices
+// never mix the two).  Genes that fit neither table are flagged for the general path and counted.
+__global__ void __launch_bounds__(256) fused_mode_kernel(int b, Gtab gt) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (j < b) ? gt.cls[j] : 0;
+    const bool tile_wide = __syncthreads_or((c & CLS_WANTS_WIDE) != 0) != 0;
+    const int mode = (tile_wide && (c & CLS_IDENT)) ? 1 : 0;
+    const bool bad = j < b && mode == 0 && !(c & CLS_NARROW);
+    if (j < b) { gt.mode[j] = (unsigned char)mode; gt.bad[j] = bad ? 1 : 0; }
+    const int nb = __syncthreads_count(bad);
+    if (threadIdx.x == 0 && nb) atomicAdd(gt.n_bad, nb);
 }
 
 // ---- 2. the pass over the matrix ------------------------------------------------------------------------------------
@@ -205,7 +285,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const f
     // Likewise when the table step flagged more genes than are handed back one by one: the whole batch will be redone by
     // the general path (fused_list_kernel takes the same decision from the same count), so the pass has nothing to add.
     if ((long long)gt.n_bad[0] * 1024 > (long long)b * share_1024) return;
-    if (__syncthreads_and(t >= FUSED_LANES || g0 + t >= b || gt.bad[g0 + t] != 0)) return;
+    if (__syncthreads_and(t >= FUSED_LANES || g0 + t >= b || gt.bad[g0 + t] != 0 || gt.mode[g0 + t] != 0)) return;
 
     if (t == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -263,7 +343,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const f
     auto sts_f = [](uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
     auto lds_h = [](uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return (uint32_t)v; };
     auto sts_h = [](uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); };
-    bool bad = !in_batch || gt.bad[j] != 0;
+    const bool mine = in_batch && gt.bad[j] == 0 && gt.mode[j] == 0;   // (wide-table genes belong to fused_wide_pass_kernel)
+    bool bad = !mine;
     float* gkey = gt.key + (in_batch ? j : 0);
     // The gene's table is global: slots are filled in order, the sample's values first; every slot already taken is
     // cached in the lane's shared column, later ones are found (or claimed) on a miss.
@@ -374,7 +455,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const f
         if (__any_sync(FULL, wr > wr_limit)) drain();                     // keep room for one more stage
     }
     close_group(g);
-    if (in_batch) {
+    if (mine) {
         if (bad) {
             gt.bad[j] = 1;
         } else if (!OVO) {
@@ -383,6 +464,216 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const f
                 if (Hacc[q]) atomicAdd(gt.mult + (long long)q * bs + j, Hacc[q]);
         }
     }
+}
+
+// ---- 2b. the pass over the matrix with the wide table (integer counts 1 .. DW; one-versus-reference) --------------------
+// Same TMA ring and lane = gene layout as fused_pass_kernel.  The table is indexed by the value itself, so an element costs
+// no look-up: the lane's own 16-bit counter of that value is bumped in shared memory (plain LDS / STS, conflict-free: bins
+// q and q + 32 share the 32-bit word [q & 31][lane]).  A 24-byte record cannot hold DW counters, so the histogram is folded
+// at the end of each group against the control's multiplicities, which the CTA keeps in shared memory in the same packed
+// layout: with a_t the control's multiplicity of value t + 1 and b_t the group's,
+//      2U_nz = sum_t b_t (2 #{control > t + 1} + a_t),   T_nz = sum_t [(a_t + b_t)^3 - (a_t + b_t) - (a_t^3 - a_t)],
+// and the record is (2U_nz | non-zeros << 40, T_nz, sum of the values) -- all exact integers.  Values the control does not
+// have need no special case (a_t = 0).  A value that is not an integer count in 1 .. DW flags the gene for the general path.
+// The grid is persistent (CTA = one tile of 256 genes, walking every GY-th chunk of groups): the launch is enqueued
+// without knowing whether any gene is wide, a no costs 296 CTA starts, and the control's table is loaded once per CTA.
+template <int ROWS, int STAGES>
+struct WideLayout {
+    static constexpr int ROW_BYTES = FUSED_LANES * 4;
+    static constexpr int STAGE_BYTES = ROWS * ROW_BYTES;
+    static constexpr int RING_OFF = 0;
+    static constexpr int HIST_OFF = STAGES * STAGE_BYTES;          // u32 [DW / 2][256]  group's counts of values q + 1 | q + 33
+    static constexpr int ATAB_OFF = HIST_OFF + (DW / 2) * ROW_BYTES;   // u32 [DW / 2][256]  the control's, same layout
+    static constexpr int BAR_OFF = ATAB_OFF + (DW / 2) * ROW_BYTES;
+    static constexpr int BYTES = BAR_OFF + 2 * STAGES * 8;
+};
+constexpr int WIDE_M_SHIFT = 40;                                   // 2U_nz < 2^37 (pairs of at most PAIR_MAX cells)
+static_assert(DW == 64, "packed layout: two 16-bit bins per word, bins q and q + 32");
+
+template <int ROWS, int STAGES, int MINB>
+__global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_wide_pass_kernel(const float* __restrict__ X, long long ld, int gene_lb,
+                                                                              int b, const illico_plan_t pl, int groups_per_cta,
+                                                                              Gtab gt, int bs, unsigned long long* __restrict__ rec,
+                                                                              long long gstride, int share_1024) {
+    using L = WideLayout<ROWS, STAGES>;
+    static_assert(32 % ROWS == 0, "layout");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t smem_a = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t bars = smem_a + L::BAR_OFF;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int G = pl.n_groups, ref = pl.ref_group;
+    const int g0 = blockIdx.x * FUSED_LANES;
+    const uint32_t row_bytes = (uint32_t)min(FUSED_LANES, (b - g0 + 3) & ~3) * 4u;
+    if ((long long)gt.n_bad[0] * 1024 > (long long)b * share_1024) return;   // the general path redoes the batch
+    if (__syncthreads_and(t >= FUSED_LANES || g0 + t >= b || gt.bad[g0 + t] != 0 || gt.mode[g0 + t] != 1)) return;
+
+    if (t == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(bars + 8 * i, 1);
+            mbar_init(bars + 8 * (STAGES + i), FUSED_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int n_chunks = (G + groups_per_cta - 1) / groups_per_cta;
+    // rows of chunk c: the positions of its groups, the control's skipped
+    struct Chunk { int gy0, p_begin, ref_p0, ref_len, nv; bool ref_in; };
+    auto chunk_of = [&](int c) {
+        Chunk k;
+        k.gy0 = c * groups_per_cta;
+        const int gy1 = min(G, k.gy0 + groups_per_cta);
+        k.p_begin = pl.seg_pos[pl.group_seg[k.gy0]];
+        const int p_end = pl.seg_pos[pl.group_seg[gy1]];
+        k.ref_in = ref >= k.gy0 && ref < gy1;
+        k.ref_p0 = k.ref_in ? pl.seg_pos[pl.group_seg[ref]] : 0;
+        k.ref_len = k.ref_in ? pl.seg_pos[pl.group_seg[ref + 1]] - k.ref_p0 : 0;
+        k.nv = p_end - k.p_begin - k.ref_len;
+        return k;
+    };
+
+    if (w == FUSED_WARPS) {
+        // ---------------- producer warp (as in fused_pass_kernel); the ring's stage counter runs on across chunks
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        const char* base = reinterpret_cast<const char*>(X + gene_lb + g0);
+        const unsigned long long ldb = (unsigned long long)ld * 4ull;
+        int k = 0;
+        for (int c = blockIdx.y; c < n_chunks; c += gridDim.y) {
+            const Chunk ch = chunk_of(c);
+            auto row_of = [&](int i) {
+                int p = ch.p_begin + i;
+                if (ch.ref_in && p >= ch.ref_p0) p += ch.ref_len;
+                return pl.perm[p];
+            };
+            int myrow = (lane < ch.nv) ? row_of(lane) : 0;
+            for (int i0 = 0; i0 < ch.nv; i0 += 32) {
+                const int nxt = (i0 + 32 + lane < ch.nv) ? row_of(i0 + 32 + lane) : 0;
+                const int nrows = min(32, ch.nv - i0);
+#pragma unroll
+                for (int q = 0; q < 32 / ROWS; ++q, ++k) {
+                    if (q * ROWS >= nrows) break;
+                    const int slot = k % STAGES;
+                    const uint32_t full = bars + 8 * slot, empty = bars + 8 * (STAGES + slot);
+                    mbar_wait(empty, ((k / STAGES) & 1) ^ 1);
+                    const int rows_here = min(ROWS, nrows - q * ROWS);
+                    if (lane == 0) mbar_expect_tx(full, (uint32_t)rows_here * row_bytes);
+                    __syncwarp();
+                    const int u = lane - q * ROWS;
+                    if (u >= 0 && u < rows_here)
+                        bulk_g2s(smem_a + L::RING_OFF + slot * L::STAGE_BYTES + u * L::ROW_BYTES,
+                                 base + (unsigned long long)(uint32_t)myrow * ldb, row_bytes, full, policy);
+                }
+                myrow = nxt;
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps: lane = gene
+    const int j = g0 + t;
+    const bool in_batch = j < b;
+    const bool mine = in_batch && gt.bad[j] == 0 && gt.mode[j] == 1;
+    const uint32_t hist_a = smem_a + L::HIST_OFF + t * 4;
+    const uint32_t atab_a = smem_a + L::ATAB_OFF + t * 4;
+    auto lds_f = [](uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; };
+    auto lds_u = [](uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; };
+    auto sts_u = [](uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); };
+    auto lds_h = [](uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return (uint32_t)v; };
+    auto sts_h = [](uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); };
+    // (lanes that are not `mine` count along -- their columns are private and their records are not written)
+    {
+        const uint32_t* wm_j = gt.wm + (in_batch ? j : 0);
+#pragma unroll 8
+        for (int q = 0; q < DW / 2; ++q) {
+            sts_u(hist_a + q * L::ROW_BYTES, 0u);
+            sts_u(atab_a + q * L::ROW_BYTES, mine ? __ldg(wm_j + (long long)q * bs) : 0u);
+        }
+    }
+    bool bad = false;
+
+    // one element: bump the 16-bit counter of its value (bin q1 = value - 1 lives in word q1 & 31, half q1 >> 5)
+    auto take = [&](float v) {
+        bool ok;
+        const uint32_t q1 = count_bin(v, ok);
+        if (ok) {
+            const uint32_t a = hist_a + q1 * L::ROW_BYTES - (q1 >> 5) * (32u * L::ROW_BYTES - 2u);
+            sts_h(a, lds_h(a) + 1u);
+        } else if (v != 0.0f) {
+            bad = true;                                           // not an integer count in 1 .. DW: general path
+        }
+    };
+    // end of group g: fold the histogram against the control's multiplicities, write the record, clear the counters
+    auto close_group = [&](int g) {
+        uint32_t m = 0, s1 = 0, above = 0;
+        unsigned long long u2 = 0, tie = 0;
+        auto bin = [&](uint32_t bq, uint32_t a, int q) {
+            if (bq) {
+                u2 += (unsigned long long)bq * (2u * above + a);
+                // (a+b)^3 - (a+b) - (a^3 - a) = b (3 a (a + b) + b^2) - b
+                tie += (unsigned long long)bq * (3ull * a * (unsigned long long)(a + bq) + (unsigned long long)bq * bq);
+                s1 += bq * (uint32_t)(q + 1);
+                m += bq;
+            }
+            above += a;
+        };
+#pragma unroll 4
+        for (int q = DW / 2 - 1; q >= 0; --q)                       // values 64 .. 33, descending
+            bin(lds_u(hist_a + q * L::ROW_BYTES) >> 16, lds_u(atab_a + q * L::ROW_BYTES) >> 16, q + 32);
+#pragma unroll 4
+        for (int q = DW / 2 - 1; q >= 0; --q) {                     // values 32 .. 1
+            const uint32_t ha = hist_a + q * L::ROW_BYTES;
+            const uint32_t hb = lds_u(ha);
+            if (hb) sts_u(ha, 0u);
+            bin(hb & 0xffffu, lds_u(atab_a + q * L::ROW_BYTES) & 0xffffu, q);
+        }
+        if (mine && !bad) {
+            unsigned long long* o = rec + (long long)g * gstride + (long long)j * 3;
+            o[0] = u2 | ((unsigned long long)m << WIDE_M_SHIFT);
+            o[1] = tie - m;
+            o[2] = (unsigned long long)s1;
+        }
+    };
+
+    const uint32_t ring_a = smem_a + L::RING_OFF + t * 4;
+    int slot = 0;
+    uint32_t parity = 0;
+    for (int c = blockIdx.y; c < n_chunks; c += gridDim.y) {
+        const Chunk ch = chunk_of(c);
+        if (ch.nv <= 0) continue;
+        auto group_end_v = [&](int gg) {
+            return pl.seg_pos[pl.group_seg[gg + 1]] - ch.p_begin - ((ch.ref_in && gg > ref) ? ch.ref_len : 0);
+        };
+        int g = (ch.gy0 == ref) ? ch.gy0 + 1 : ch.gy0;
+        int gend = group_end_v(g);
+        for (int i = 0; i < ch.nv; i += ROWS) {
+            mbar_wait(bars + 8 * slot, parity);
+            const uint32_t src = ring_a + slot * L::STAGE_BYTES;
+            if (i + ROWS <= gend) {
+                float v[ROWS];
+#pragma unroll
+                for (int u = 0; u < ROWS; ++u) v[u] = lds_f(src + u * L::ROW_BYTES);
+#pragma unroll
+                for (int u = 0; u < ROWS; ++u) take(v[u]);
+            } else {
+                const int nr = min(ROWS, ch.nv - i);
+#pragma unroll 1
+                for (int u = 0; u < nr; ++u) {
+                    if (i + u == gend) {                                     // CTA-uniform: the next group starts here
+                        close_group(g);
+                        ++g;
+                        if (g == ref) ++g;
+                        gend = group_end_v(g);
+                    }
+                    take(lds_f(src + u * L::ROW_BYTES));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 8 * (STAGES + slot));
+            if (++slot == STAGES) { slot = 0; parity ^= 1u; }
+        }
+        close_group(g);
+    }
+    if (mine && bad) gt.bad[j] = 1;
 }
 
 // ---- 3a. per-gene weights ---------------------------------------------------------------------------------------------
@@ -397,6 +688,20 @@ __global__ void __launch_bounds__(128) fused_gene_kernel(int b, const illico_pla
                                                          double* dbg_tie, long long* dbg_tie_exact) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= b || gt.bad[j]) return;
+    if (OVO && gt.mode[j] == 1) {
+        // wide table: the control's own sums from its multiplicities by value (value of bin q = q + 1)
+        unsigned long long nnz = 0, tie = 0, sum = 0;
+        for (int q = 0; q < DW; ++q) {
+            const unsigned long long c = (gt.wm[(long long)(q & 31) * bs + j] >> (16 * (q >> 5))) & 0xffffu;
+            nnz += c;
+            tie += (unsigned long long)cube_minus((long long)c);
+            sum += c * (unsigned long long)(q + 1);
+        }
+        gt.nnz[j] = (uint32_t)nnz;
+        gt.tie[j] = tie;
+        gt.sum[j] = (double)sum;
+        return;
+    }
     float key[DCAP];
     int order[DCAP];
     int D = 0;
@@ -493,10 +798,11 @@ __global__ void __launch_bounds__(256) fused_group_kernel(const illico_plan_t pl
 // its divisions by the group sizes are multiplications by precomputed reciprocals; everything that feeds the p-value
 // keeps the reference's IEEE operations.
 constexpr int EPI_GROUPS = 16;   // groups per thread
-template <bool OVO>
+template <bool OVO, bool WIDE>
 __global__ void __launch_bounds__(256, 3) fused_epilogue_kernel(int b, const illico_plan_t pl, const illico_flags_t fl, Gtab gt,
                                                              int bs, double* __restrict__ results, long long gstride,
-                                                             long long* dbg_u2, double* dbg_tie, long long* dbg_tie_exact) {
+                                                             long long* dbg_u2, double* dbg_tie, long long* dbg_tie_exact,
+                                                             int share_1024) {
     __shared__ double gcs[GC_N][EPI_GROUPS];
     __shared__ int nts[EPI_GROUPS];
     const int G = pl.n_groups, ref = pl.ref_group;
@@ -511,13 +817,19 @@ __global__ void __launch_bounds__(256, 3) fused_epilogue_kernel(int b, const ill
     __syncthreads();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= b || gt.bad[j]) return;
-    uint32_t wgt[DCAP], mult[OVO ? DCAP : 1];
-    double fval[DCAP];
+    // the batch is being handed back as a whole (the table step flagged too many genes): nothing here will be kept
+    if ((long long)gt.n_bad[0] * 1024 > (long long)b * share_1024) return;
+    // WIDE: the genes of the wide table, whose record is (2U_nz | non-zeros << 40, T_nz, sum) and not a histogram
+    if ((gt.mode[j] == 1) != WIDE) return;
+    uint32_t wgt[WIDE ? 1 : DCAP], mult[(OVO && !WIDE) ? DCAP : 1];
+    double fval[WIDE ? 1 : DCAP];
+    if (!WIDE) {
 #pragma unroll
-    for (int q = 0; q < DCAP; ++q) {
-        wgt[q] = gt.wgt[(long long)q * bs + j];
-        fval[q] = gt.fval[(long long)q * bs + j];
-        if (OVO) mult[OVO ? q : 0] = gt.mult[(long long)q * bs + j];
+        for (int q = 0; q < DCAP; ++q) {
+            wgt[WIDE ? 0 : q] = gt.wgt[(long long)q * bs + j];
+            fval[WIDE ? 0 : q] = gt.fval[(long long)q * bs + j];
+            if (OVO) mult[(OVO && !WIDE) ? q : 0] = gt.mult[(long long)q * bs + j];
+        }
     }
     const long long n = pl.n_cells;
     const double cc = fl.use_continuity ? 0.5 : 0.0;
@@ -549,16 +861,23 @@ __global__ void __launch_bounds__(256, 3) fused_epilogue_kernel(int b, const ill
         unsigned long long acc = 0, tie_nz = 0;              // acc: OVO 2U without the zero block, OVR 2R without it
         uint32_t m = 0;
         double sum = 0.0;
+        if (WIDE) {
+            acc = wds[0] & ((1ull << WIDE_M_SHIFT) - 1ull);
+            m = (uint32_t)(wds[0] >> WIDE_M_SHIFT);
+            tie_nz = wds[1];
+            sum = (double)wds[2];
+        } else {
 #pragma unroll
-        for (int q = 0; q < DCAP; ++q) {
-            const uint32_t bq = (uint32_t)(wds[q >> 2] >> (16 * (q & 3))) & 0xffffu;
-            if (bq) {
-                acc += (unsigned long long)bq * wgt[q];
-                sum += (double)bq * fval[q];
-                m += bq;
-                if (OVO) {
-                    const unsigned long long a = mult[OVO ? q : 0];
-                    tie_nz += bq * (3ull * a * a - 1ull + bq * (3ull * a + bq));   // (a+b)^3 - (a+b) - (a^3 - a)
+            for (int q = 0; q < DCAP; ++q) {
+                const uint32_t bq = (uint32_t)(wds[q >> 2] >> (16 * (q & 3))) & 0xffffu;
+                if (bq) {
+                    acc += (unsigned long long)bq * wgt[WIDE ? 0 : q];
+                    sum += (double)bq * fval[WIDE ? 0 : q];
+                    m += bq;
+                    if (OVO) {
+                        const unsigned long long a = mult[(OVO && !WIDE) ? q : 0];
+                        tie_nz += bq * (3ull * a * a - 1ull + bq * (3ull * a + bq));   // (a+b)^3 - (a+b) - (a^3 - a)
+                    }
                 }
             }
         }
@@ -629,6 +948,7 @@ __global__ void fused_seed_kernel(Gtab gt, int bs, int identity) {
         gt.mult[(long long)q * bs + i] = 0u;
     }
     gt.bad[i] = 0;
+    gt.mode[i] = 0;
     if (i == 0) *gt.n_bad = 0;
 }
 
@@ -849,6 +1169,9 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
     const int bs = (b + 63) & ~63;
     Gtab gt = gtab_carve(buf->workspace, b, plan->n_groups);
 
+    // wide table (integer counts up to DW, folded against the control at the end of each group): one-versus-reference on
+    // raw counts only -- the ranks of one-versus-rest are not known before the whole gene has been seen
+    const bool wide_on = OVO && !flags->is_log1p && env_int("ILLICO_FUSED_WIDE", 1) != 0;
     // 1. table segments: the control group (OVO) or a sample of about 16k cells (OVR: the first segments)
     int seg_lo = plan->ref_seg_begin, seg_hi = plan->ref_seg_end;
     if (!OVO) {
@@ -865,7 +1188,8 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
         if (rc != 0) return rc;
         int blocks = (b + 7) / 8;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        ILLICO_LAUNCH("fused_ctab_kernel", stream, fused_ctab_kernel<<<blocks, 256, 0, stream>>>(buf->ir_vals, buf->ir_cnt, b, *plan, seg_lo, seg_hi, flags->is_log1p, gt, bs));
+        ILLICO_LAUNCH("fused_ctab_kernel", stream, fused_ctab_kernel<<<blocks, 256, 0, stream>>>(buf->ir_vals, buf->ir_cnt, b, *plan, seg_lo, seg_hi, flags->is_log1p, gt, bs, wide_on ? 1 : 0));
+        ILLICO_LAUNCH("fused_mode_kernel", stream, fused_mode_kernel<<<(b + FUSED_LANES - 1) / FUSED_LANES, FUSED_LANES, 0, stream>>>(b, gt));
         ILLICO_CUDA_OK(cudaGetLastError());
     }
     if (!OVO)   // the sample only seeds the slots; gt.mult restarts as the whole gene's histogram
@@ -884,14 +1208,31 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
     else
         rc = launch_pass_t<8, 4, 16, 3, OVO>(X, ld, gene_lb, b, plan, gpc, gt, bs, results, gstride, stream);
     if (rc) return rc;
+    if (wide_on) {
+        using L = WideLayout<8, 5>;
+        auto kern = fused_wide_pass_kernel<8, 5, 2>;
+        ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+        // persistent: two CTAs per SM, each a tile of 256 genes walking every gy-th chunk of groups
+        const int tiles = (b + FUSED_LANES - 1) / FUSED_LANES, chunks = (plan->n_groups + gpc - 1) / gpc;
+        int gy = (2 * 148) / tiles;
+        if (gy < 1) gy = 1;
+        if (gy > chunks) gy = chunks;
+        const dim3 grid((unsigned)tiles, (unsigned)gy);
+        ILLICO_LAUNCH("fused_wide_pass_kernel", stream, kern<<<grid, FUSED_THREADS, L::BYTES, stream>>>(
+                X, ld, gene_lb, b, *plan, gpc, gt, bs, reinterpret_cast<unsigned long long*>(results), gstride, list_share_1024()));
+        ILLICO_CUDA_OK(cudaGetLastError());
+    }
     g_last_fused_ms = 0.0f;
 
     // 3. per-group constants, per-gene weights, then the epilogue
     ILLICO_LAUNCH("fused_group_kernel", stream, fused_group_kernel<OVO><<<(plan->n_groups + 255) / 256, 256, 0, stream>>>(*plan, gt));
     ILLICO_LAUNCH("fused_gene_kernel", stream, fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, nullptr, nullptr));
     ILLICO_CUDA_OK(cudaGetLastError());
-    ILLICO_LAUNCH("fused_epilogue_kernel", stream, fused_epilogue_kernel<OVO><<<dim3((unsigned)((b + 255) / 256), (unsigned)((plan->n_groups + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
-            b, *plan, *flags, gt, bs, results, gstride, nullptr, nullptr, nullptr));
+    ILLICO_LAUNCH("fused_epilogue_kernel", stream, fused_epilogue_kernel<OVO, false><<<dim3((unsigned)((b + 255) / 256), (unsigned)((plan->n_groups + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
+            b, *plan, *flags, gt, bs, results, gstride, nullptr, nullptr, nullptr, list_share_1024()));
+    if (wide_on)
+        ILLICO_LAUNCH("fused_wide_epilogue_kernel", stream, fused_epilogue_kernel<OVO, true><<<dim3((unsigned)((b + 255) / 256), (unsigned)((plan->n_groups + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
+                b, *plan, *flags, gt, bs, results, gstride, nullptr, nullptr, nullptr, list_share_1024()));
     ILLICO_CUDA_OK(cudaGetLastError());
 
     // 4. genes handed back: listed on the device, staged from the matrix by a persistent kernel, ranked by the general
@@ -980,8 +1321,8 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
     }
     ILLICO_LAUNCH("fused_group_kernel", stream, fused_group_kernel<OVO><<<(plan->n_groups + 255) / 256, 256, 0, stream>>>(*plan, gt));
     ILLICO_LAUNCH("fused_gene_kernel", stream, fused_gene_kernel<OVO><<<(b + 127) / 128, 128, 0, stream>>>(b, *plan, *flags, gt, bs, nullptr, nullptr));
-    ILLICO_LAUNCH("fused_epilogue_kernel", stream, fused_epilogue_kernel<OVO><<<dim3((unsigned)((b + 255) / 256), (unsigned)((G + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
-            b, *plan, *flags, gt, bs, results, gstride, nullptr, nullptr, nullptr));
+    ILLICO_LAUNCH("fused_epilogue_kernel", stream, fused_epilogue_kernel<OVO, false><<<dim3((unsigned)((b + 255) / 256), (unsigned)((G + EPI_GROUPS - 1) / EPI_GROUPS)), 256, 0, stream>>>(
+            b, *plan, *flags, gt, bs, results, gstride, nullptr, nullptr, nullptr, 128));   // (the CSR pass stops at an eighth)
     ILLICO_CUDA_OK(cudaGetLastError());
 
     // hand-back, decided on the device: a few scattered genes -> one filtered pass over the stored values (HB_LIST);

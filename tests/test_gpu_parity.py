@@ -416,6 +416,49 @@ def test_fused_ovo_routes_match_general_path_and_oracle(monkeypatch, kind):
     assert_parity(fused, (p, U, fc), ref_row=ref_row, fc_rtol=fc_rtol, what=f"fused ovo {kind}")
 
 
+@pytest.mark.parametrize("kind", ["first", "middle", "last:less", "middle:batched"])
+def test_fused_ovo_wide_table_matches_general_path_and_oracle(monkeypatch, kind):
+    """fused.cu, wide table (integer counts up to 64 indexed by value, histogram folded against the control at the end
+    of each group): dense high-count genes next to sparse ones, values the control lacks, the largest value the table
+    holds and one beyond it, fractional / negative genes in the same tile -- identical U to the general path and to the
+    oracle, with and without the wide pass."""
+    from illico_b200 import _lib
+
+    X, labels, ref = _fused_case(kind)
+    rng = np.random.RandomState(5)
+    n = X.shape[0]
+    ctrl = np.array(labels) == ref
+    X[:, 10] = rng.poisson(12.0, n)                                   # dense, ~30 distinct values
+    X[:, 11] = rng.poisson(12.0, n) * (rng.rand(n) < 0.5)             # the reference's fixture: masked Poisson
+    X[:, 12] = rng.poisson(45.0, n)                                   # reaches past 64 somewhere: handed back during the pass
+    X[:, 13] = np.minimum(rng.poisson(50.0, n), 64)                   # the largest value the table holds, heavily tied
+    X[:, 14] = rng.poisson(20.0, n); X[ctrl, 14] = np.minimum(X[ctrl, 14], 18)   # values above every control value
+    X[:, 15] = rng.poisson(20.0, n); X[np.flatnonzero(~ctrl)[7], 15] = 2.5   # one fractional value outside the control
+    X[:, 17] = rng.poisson(20.0, n); X[np.flatnonzero(~ctrl)[9], 17] = -3.0  # one negative value outside the control
+    X[:, 16] = rng.poisson(9.0, n)                                    # 11+ distinct control values: goes wide by choice
+    kw = dict(is_log1p=False, alternative="less" if kind.endswith("less") else "two-sided",
+              batch_size=40 if kind.endswith("batched") else "auto")
+    monkeypatch.setenv("ILLICO_OVO_FUSED", "1")
+    monkeypatch.setenv("ILLICO_PROFILE", "1")
+    monkeypatch.setenv("ILLICO_FUSED_LIST_SHARE", "1.0")
+    _lib.profile_report()
+    groups, wide = _run(X, labels, ref, **kw)
+    assert "fused_wide_pass_kernel" in _lib.profile_report(), "the wide pass did not run"
+    monkeypatch.setenv("ILLICO_FUSED_WIDE", "0")
+    _, narrow = _run(X, labels, ref, **kw)
+    assert "fused_wide_pass_kernel" not in _lib.profile_report()
+    monkeypatch.setenv("ILLICO_OVO_FUSED", "0")
+    _, general = _run(X, labels, ref, **kw)
+    ref_row = int(np.searchsorted(groups, ref))
+    rows = np.arange(len(groups)) != ref_row
+    for got, what in ((wide, "wide"), (narrow, "narrow")):
+        np.testing.assert_array_equal(got[1], general[1], err_msg=what)
+        np.testing.assert_allclose(got[0][rows], general[0][rows], rtol=1e-13, atol=2.3e-308, err_msg=what)
+        np.testing.assert_allclose(got[2][rows], general[2][rows], rtol=1e-13, atol=0, err_msg=what)
+    g, p, U, fc = oracle.run(X, labels, ref, is_log1p=False, alternative=kw["alternative"])
+    assert_parity(wide, (p, U, fc), ref_row=ref_row, what=f"fused ovo wide {kind}")
+
+
 def test_fused_ovo_debug_integers_and_continuous_batches(monkeypatch):
     """Exact 2U / tie sums through the fused path's debug outputs; a mostly continuous batch skips the fused path."""
     import ctypes as Ct
