@@ -76,7 +76,7 @@ struct Gtab {
     unsigned char* bad;        // [bs]        1 = the gene takes the general path
     unsigned char* cls;        // [bs]        what the table step found: CLS_NARROW | CLS_IDENT | CLS_WANTS_WIDE
     unsigned char* mode;       // [bs]        0 = 12-slot histogram records (fused_pass_kernel), 1 = wide table (fused_wide_pass_kernel)
-    uint32_t* wm;              // [DW/2][bs]  wide table: multiplicity of the integer values q + 1 | q + 33 (16 bits each) in the control
+    uint32_t* wm;              // [DW/2][bs]  wide table: multiplicity of the integer values 2 q + 1 | 2 q + 2 (16 bits each) in the control
     double* gc;                // [GC_N][Gs]  per-group constants of the p-value (fused_group_kernel)
     int Gs;                    //             groups, padded to a multiple of 64
 };
@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(256) fused_ctab_kernel(const float* __restrict
             if (__any_sync(FULL, (c0 | c1) > 0xffffu)) {
                 ident = false;                                        // (16-bit multiplicities in the pass's shared table)
             } else {
-                gt.wm[(long long)lane * bs + j] = c0 | (c1 << 16);    // packed as the pass keeps it: values q + 1 | q + 33
+                // packed as the pass keeps it: word q = multiplicities of the values 2 q + 1 | 2 q + 2
+                const uint32_t e0 = wh[wl][2 * lane], e1 = wh[wl][2 * lane + 1];
+                gt.wm[(long long)lane * bs + j] = e0 | (e1 << 16);
                 cls |= CLS_IDENT;
                 if (nbad || D >= WIDE_FROM) cls |= CLS_WANTS_WIDE;
             }
@@ -263,7 +265,7 @@ template <int ROWS, int STAGES, int BUF, int MINB, bool OVO>
 __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const float* __restrict__ X, long long ld, int gene_lb,
                                                                          int b, const illico_plan_t pl, int groups_per_cta,
                                                                          Gtab gt, int bs, unsigned long long* __restrict__ rec,
-                                                                         long long gstride, int share_1024) {
+                                                                         long long gstride, int share_1024, int backoff) {
     using L = FusedLayout<ROWS, STAGES, BUF>;
     static_assert(32 % ROWS == 0 && BUF > ROWS, "layout");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const f
                 if (q * ROWS >= nrows) break;
                 const int slot = k % STAGES;
                 const uint32_t full = bars + 8 * slot, empty = bars + 8 * (STAGES + slot);
-                mbar_wait(empty, ((k / STAGES) & 1) ^ 1);
+                if (backoff) mbar_wait_backoff(empty, ((k / STAGES) & 1) ^ 1); else mbar_wait(empty, ((k / STAGES) & 1) ^ 1);
                 const int rows_here = min(ROWS, nrows - q * ROWS);
                 if (lane == 0) mbar_expect_tx(full, (uint32_t)rows_here * row_bytes);
                 __syncwarp();
@@ -468,8 +470,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const f
 
 // ---- 2b. the pass over the matrix with the wide table (integer counts 1 .. DW; one-versus-reference) --------------------
 // Same TMA ring and lane = gene layout as fused_pass_kernel.  The table is indexed by the value itself, so an element costs
-// no look-up: the lane's own 16-bit counter of that value is bumped in shared memory (plain LDS / STS, conflict-free: bins
-// q and q + 32 share the 32-bit word [q & 31][lane]).  A 24-byte record cannot hold DW counters, so the histogram is folded
+// no look-up: the lane's own 16-bit counter of that value is bumped in shared memory (plain LDS / STS, laid out so that a
+// warp never meets a bank conflict).  A 24-byte record cannot hold DW counters, so the histogram is folded
 // at the end of each group against the control's multiplicities, which the CTA keeps in shared memory in the same packed
 // layout: with a_t the control's multiplicity of value t + 1 and b_t the group's,
 //      2U_nz = sum_t b_t (2 #{control > t + 1} + a_t),   T_nz = sum_t [(a_t + b_t)^3 - (a_t + b_t) - (a_t^3 - a_t)],
@@ -482,13 +484,13 @@ struct WideLayout {
     static constexpr int ROW_BYTES = FUSED_LANES * 4;
     static constexpr int STAGE_BYTES = ROWS * ROW_BYTES;
     static constexpr int RING_OFF = 0;
-    static constexpr int HIST_OFF = STAGES * STAGE_BYTES;          // u32 [DW / 2][256]  group's counts of values q + 1 | q + 33
-    static constexpr int ATAB_OFF = HIST_OFF + (DW / 2) * ROW_BYTES;   // u32 [DW / 2][256]  the control's, same layout
+    static constexpr int HIST_OFF = STAGES * STAGE_BYTES;          // u16 [DW][256]      the group's count of each value
+    static constexpr int ATAB_OFF = HIST_OFF + (DW / 2) * ROW_BYTES;   // u32 [DW / 2][256]  the control's counts of values 2 q + 1 | 2 q + 2
     static constexpr int BAR_OFF = ATAB_OFF + (DW / 2) * ROW_BYTES;
     static constexpr int BYTES = BAR_OFF + 2 * STAGES * 8;
 };
 constexpr int WIDE_M_SHIFT = 40;                                   // 2U_nz < 2^37 (pairs of at most PAIR_MAX cells)
-static_assert(DW == 64, "packed layout: two 16-bit bins per word, bins q and q + 32");
+static_assert(DW % 2 == 0 && DW <= 64, "packed layout: two 16-bit bins per word; the table step keeps two bins per lane");
 
 template <int ROWS, int STAGES, int MINB>
 __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_wide_pass_kernel(const float* __restrict__ X, long long ld, int gene_lb,
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_wide_pass_kernel(co
                     if (q * ROWS >= nrows) break;
                     const int slot = k % STAGES;
                     const uint32_t full = bars + 8 * slot, empty = bars + 8 * (STAGES + slot);
-                    mbar_wait(empty, ((k / STAGES) & 1) ^ 1);
+                    mbar_wait_backoff(empty, ((k / STAGES) & 1) ^ 1);
                     const int rows_here = min(ROWS, nrows - q * ROWS);
                     if (lane == 0) mbar_expect_tx(full, (uint32_t)rows_here * row_bytes);
                     __syncwarp();
@@ -573,41 +575,52 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_wide_pass_kernel(co
     const int j = g0 + t;
     const bool in_batch = j < b;
     const bool mine = in_batch && gt.bad[j] == 0 && gt.mode[j] == 1;
-    const uint32_t hist_a = smem_a + L::HIST_OFF + t * 4;
-    const uint32_t atab_a = smem_a + L::ATAB_OFF + t * 4;
+    // counters: u16 [DW][256], bin stride 512 bytes.  Inside a bin row the 32 lanes of a warp sit in 32 different words
+    // (warps 2 i and 2 i + 1 share the words of quarter i, one half each), so a warp's read-modify-write never meets a
+    // bank conflict whatever the values are, and the address of bin q is one multiply-add away
+    const uint32_t hist_a = smem_a + L::HIST_OFF + (uint32_t)(w >> 1) * 128u + (uint32_t)lane * 4u + (uint32_t)(w & 1) * 2u;
+    const uint32_t atab_a = smem_a + L::ATAB_OFF + t * 4;     // u32 [DW / 2][256]: the control's multiplicities, two per word
+    constexpr uint32_t BIN_BYTES = FUSED_LANES * 2;
     auto lds_f = [](uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; };
     auto lds_u = [](uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; };
     auto sts_u = [](uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); };
-    auto lds_h = [](uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return (uint32_t)v; };
-    auto sts_h = [](uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); };
+    auto lds_h = [](uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; };
+    auto sts_h = [](uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); };
     // (lanes that are not `mine` count along -- their columns are private and their records are not written)
     {
         const uint32_t* wm_j = gt.wm + (in_batch ? j : 0);
 #pragma unroll 8
         for (int q = 0; q < DW / 2; ++q) {
-            sts_u(hist_a + q * L::ROW_BYTES, 0u);
+            sts_h(hist_a + (2 * q) * BIN_BYTES, 0u);
+            sts_h(hist_a + (2 * q + 1) * BIN_BYTES, 0u);
             sts_u(atab_a + q * L::ROW_BYTES, mine ? __ldg(wm_j + (long long)q * bs) : 0u);
         }
     }
     bool bad = false;
 
-    // one element: bump the 16-bit counter of its value (bin q1 = value - 1 lives in word q1 & 31, half q1 >> 5)
+    // one element: bump the 16-bit counter of its value (bin q1 = value - 1); one predicated read-modify-write, no branch
     auto take = [&](float v) {
         bool ok;
         const uint32_t q1 = count_bin(v, ok);
-        if (ok) {
-            const uint32_t a = hist_a + q1 * L::ROW_BYTES - (q1 >> 5) * (32u * L::ROW_BYTES - 2u);
-            sts_h(a, lds_h(a) + 1u);
-        } else if (v != 0.0f) {
-            bad = true;                                           // not an integer count in 1 .. DW: general path
-        }
+        const uint32_t a = hist_a + q1 * BIN_BYTES;
+        asm volatile(
+            "{ .reg .pred p; .reg .u32 h;\n"
+            "setp.ne.u32 p, %1, 0;\n"
+            "@p ld.shared.u16 h, [%0];\n"
+            "@p add.u32 h, h, 1;\n"
+            "@p st.shared.u16 [%0], h; }"
+            ::"r"(a), "r"((uint32_t)ok) : "memory");
+        bad |= !ok && v != 0.0f;                                  // not an integer count in 1 .. DW: general path
     };
-    // end of group g: fold the histogram against the control's multiplicities, write the record, clear the counters
+    // end of group g: fold the histogram against the control's multiplicities (values descending, so that the number of
+    // control values above the current one is a running sum), write the record, clear the counters
     auto close_group = [&](int g) {
         uint32_t m = 0, s1 = 0, above = 0;
         unsigned long long u2 = 0, tie = 0;
-        auto bin = [&](uint32_t bq, uint32_t a, int q) {
+        auto bin = [&](uint32_t ha, uint32_t a, int q) {
+            const uint32_t bq = lds_h(ha);
             if (bq) {
+                sts_h(ha, 0u);
                 u2 += (unsigned long long)bq * (2u * above + a);
                 // (a+b)^3 - (a+b) - (a^3 - a) = b (3 a (a + b) + b^2) - b
                 tie += (unsigned long long)bq * (3ull * a * (unsigned long long)(a + bq) + (unsigned long long)bq * bq);
@@ -617,14 +630,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_wide_pass_kernel(co
             above += a;
         };
 #pragma unroll 4
-        for (int q = DW / 2 - 1; q >= 0; --q)                       // values 64 .. 33, descending
-            bin(lds_u(hist_a + q * L::ROW_BYTES) >> 16, lds_u(atab_a + q * L::ROW_BYTES) >> 16, q + 32);
-#pragma unroll 4
-        for (int q = DW / 2 - 1; q >= 0; --q) {                     // values 32 .. 1
-            const uint32_t ha = hist_a + q * L::ROW_BYTES;
-            const uint32_t hb = lds_u(ha);
-            if (hb) sts_u(ha, 0u);
-            bin(hb & 0xffffu, lds_u(atab_a + q * L::ROW_BYTES) & 0xffffu, q);
+        for (int q = DW / 2 - 1; q >= 0; --q) {                     // word q of the control's table: values 2 q + 2 | 2 q + 1
+            const uint32_t ab = lds_u(atab_a + q * L::ROW_BYTES);
+            bin(hist_a + (2 * q + 1) * BIN_BYTES, ab >> 16, 2 * q + 1);
+            bin(hist_a + (2 * q) * BIN_BYTES, ab & 0xffffu, 2 * q);
         }
         if (mine && !bad) {
             unsigned long long* o = rec + (long long)g * gstride + (long long)j * 3;
@@ -692,7 +701,7 @@ __global__ void __launch_bounds__(128) fused_gene_kernel(int b, const illico_pla
         // wide table: the control's own sums from its multiplicities by value (value of bin q = q + 1)
         unsigned long long nnz = 0, tie = 0, sum = 0;
         for (int q = 0; q < DW; ++q) {
-            const unsigned long long c = (gt.wm[(long long)(q & 31) * bs + j] >> (16 * (q >> 5))) & 0xffffu;
+            const unsigned long long c = (gt.wm[(long long)(q >> 1) * bs + j] >> (16 * (q & 1))) & 0xffffu;
             nnz += c;
             tie += (unsigned long long)cube_minus((long long)c);
             sum += c * (unsigned long long)(q + 1);
@@ -1146,7 +1155,8 @@ int launch_pass_t(const float* X, long long ld, int gene_lb, int b, const illico
     ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
     const dim3 grid((unsigned)((b + FUSED_LANES - 1) / FUSED_LANES), (unsigned)((plan->n_groups + gpc - 1) / gpc));
     ILLICO_LAUNCH("fused_pass_kernel", stream, kern<<<grid, FUSED_THREADS, L::BYTES, stream>>>(X, ld, gene_lb, b, *plan, gpc, gt, bs,
-                                                    reinterpret_cast<unsigned long long*>(results), gstride, list_share_1024()));
+                                                    reinterpret_cast<unsigned long long*>(results), gstride, list_share_1024(),
+                                                    env_int("ILLICO_FUSED_BACKOFF", 0)));
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -25,6 +25,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
 }
+// the producer's wait for a free ring slot: it is usually a whole ring ahead, so a failed probe sleeps instead of
+// spinning in the issue slots of the consumer warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITB_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAITB_DONE;\n"
+        "nanosleep.u32 128;\n"
+        "bra WAITB_LOOP;\n"
+        "WAITB_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
 // global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); the input is read once,
 // so it is marked evict-first in L2
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
