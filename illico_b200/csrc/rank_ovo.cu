@@ -59,6 +59,7 @@ struct OvoParams {
     const int* n_genes_dev;  // optional: number of genes decided on the device (a hand-back list), else n_genes
     const int* gene_map;     // optional: staged gene j is column gene_map[j] of the results / debug / group-sum arrays
     int n_cols;              // width of the debug / group-sum arrays (= n_genes unless gene_map is set)
+    int bucket_index;        // 1 = searches go through the bucket index of the search table
     const double* gc;        // [GCN][Gs] per-group constants (ovo_group_consts_kernel)
     int Gs;
     long long* dbg_u2;
@@ -73,7 +74,9 @@ struct SortedS {
 };
 __device__ __forceinline__ SortedS sorted_s(uint32_t base, int n) {
     SortedS a;
-    a.base = base; a.n = n; a.p = (n > 0) ? (1 << (31 - __clz(n))) : 0;
+    // (n = 0: p = 1, so that the first probe's address -- which the compiler may load ahead of the n > 0 test, lds_ro
+    // being a plain asm -- stays inside the array; `base` must be a valid shared address even then)
+    a.base = base; a.n = n; a.p = (n > 0) ? (1 << (31 - __clz(n))) : 1;
     return a;
 }
 
@@ -94,6 +97,11 @@ struct RefInfo {
     uint32_t st_key_s, st_lo_s;   // shared-memory addresses
     int st_n;
     SortedS st, ks;        // search descriptors of the table / of the keys when they are in shared memory
+    // bucket index over the search table (bk_T >= 0): the key range [kmin, kmax] is cut into <= 1023 equal buckets,
+    // bk[b] = first table entry of bucket b or later; a search reads its bucket's bounds and halves at most bk_T times
+    // (bk_T from the fullest bucket: uniform trip count, 2-4 for spread-out values instead of 10-11 over the table)
+    uint32_t bk_s, kmin;
+    int bk_shift, bk_last, bk_T;
 };
 
 template <bool LOG1P>
@@ -153,11 +161,43 @@ __device__ __forceinline__ int lb_shared(uint32_t base_s, int n, uint32_t key) {
 }
 
 // position of NK keys in the sorted control: [lo, hi) = the key's run (empty when the control does not have the value)
+// NK lower bounds in the search table through the bucket index
+template <int NK>
+__device__ __forceinline__ void bound_bucket(const RefInfo& R, const uint32_t (&key)[NK], int (&out)[NK]) {
+    uint32_t lo[NK], len[NK];
+#pragma unroll
+    for (int e = 0; e < NK; ++e) {
+        const uint32_t kk = max(key[e], R.kmin);
+        const uint32_t bq = min((kk - R.kmin) >> R.bk_shift, (uint32_t)R.bk_last);
+        const uint32_t a = R.bk_s + bq * 2u;
+        uint32_t i0, i1;
+        asm("ld.shared.u16 %0, [%1];" : "=r"(i0) : "r"(a));
+        asm("ld.shared.u16 %0, [%1+2];" : "=r"(i1) : "r"(a));
+        lo[e] = i0;
+        len[e] = i1 - i0;
+    }
+    for (int s = 0; s < R.bk_T; ++s) {
+        uint32_t k[NK];
+#pragma unroll
+        for (int e = 0; e < NK; ++e) k[e] = lds_ro(R.st_key_s + (lo[e] + (len[e] >> 1)) * 4u);
+#pragma unroll
+        for (int e = 0; e < NK; ++e) {
+            const uint32_t half = len[e] >> 1;
+            const bool right = len[e] != 0u && k[e] < key[e];
+            lo[e] = right ? lo[e] + half + 1u : lo[e];
+            len[e] = right ? len[e] - half - 1u : half;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < NK; ++e) out[e] = (int)lo[e];
+}
+
 template <int NK>
 __device__ __forceinline__ void rank_pos_n(const RefInfo& R, const uint32_t (&key)[NK], int (&lo)[NK], int (&hi)[NK]) {
     if (R.st_n >= 0) {
         int t[NK];
-        bound_shared<NK, false>(R.st, key, t);
+        if (R.bk_T >= 0) bound_bucket<NK>(R, key, t);
+        else bound_shared<NK, false>(R.st, key, t);
 #pragma unroll
         for (int e = 0; e < NK; ++e) {
             lo[e] = (int)lds_ro(R.st_lo_s + (uint32_t)t[e] * 4u);
@@ -285,9 +325,9 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
     uint32_t* scratch = refA + REF_CAP;                     // [scratch_words] (>= REF_CAP, >= 2 * HCAP)
     uint32_t* hist = scratch + P.scratch_words;             // [OVO_NW * 256]
     uint32_t* aux = hist + OVO_NW * 256;                    // [RADIX_AUX_WORDS]
-    uint16_t* mlist = (uint16_t*)(aux + RADIX_AUX_WORDS);   // [GROUP_CHUNK] groups left to the warp tier (index inside the chunk)
-    uint16_t* blist = mlist + GROUP_CHUNK;                  // [GROUP_CHUNK] ... to the block tier
-    uint16_t* order = blist + GROUP_CHUNK;                  // [GROUP_CHUNK] the chunk's groups by non-zero count
+    uint16_t* mlist = (uint16_t*)(aux + RADIX_AUX_WORDS);   // [GROUP_CHUNK] groups left to the warp tier (index inside the chunk; bit 15: passed on to the block tier)
+    uint16_t* bkidx = mlist + GROUP_CHUNK;                  // [GROUP_CHUNK] bucket index of the search table (RefInfo::bk_s)
+    uint16_t* order = bkidx + GROUP_CHUNK;                  // [GROUP_CHUNK] the chunk's groups by non-zero count
     uint16_t* marr = order + GROUP_CHUNK;                   // [GROUP_CHUNK] non-zero count of each group (capped)
     int* counters = (int*)(marr + GROUP_CHUNK);             // [8] rotating {medium, big} list counters, [6] scratch, [7] next gene
     int* mh = counters + 8;                                 // [MBINS] histogram / cursors of the non-zero counts
@@ -345,7 +385,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
         R.st_n = -1;
         R.st = sorted_s(R.st_key_s, 0);
         R.keys = nullptr; R.keys_s = 0u;
-        R.ks = sorted_s(0u, 0);
+        R.ks = sorted_s(R.st_key_s, 0);
         double rsum = 0.0;
         int D = 0;
         bool hashed = false;
@@ -444,7 +484,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
             }
             R.keys = rA;
             R.keys_s = ref_smem ? (uint32_t)__cvta_generic_to_shared(rA) : 0u;
-            R.ks = sorted_s(R.keys_s, ref_smem ? nref_nz : 0);
+            R.ks = sorted_s(ref_smem ? R.keys_s : R.st_key_s, ref_smem ? nref_nz : 0);
             // distinct control values: how many, then (when they fit) the ordered search table
             int heads = 0;
             for (int i = tid; i < nref_nz; i += OVO_THREADS) heads += (i == 0 || rA[i - 1] != rA[i]) ? 1 : 0;
@@ -473,6 +513,31 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 R.st = sorted_s(R.st_key_s, D);
                 __syncthreads();
             }
+        }
+        // ---- bucket index of the search table
+        R.bk_s = (uint32_t)__cvta_generic_to_shared(bkidx);
+        R.bk_T = -1; R.kmin = 0u; R.bk_shift = 0; R.bk_last = 0;
+        if (R.st_n > 1 && P.bucket_index) {
+            const uint32_t kmin = st_key[0], span = st_key[D - 1] - kmin;
+            int shift = max(0, 22 - __clz(span));                         // span >> shift < 1024
+            if ((span >> shift) > (uint32_t)(GROUP_CHUNK - 2)) ++shift;   // ... and at most GROUP_CHUNK - 1 buckets
+            const int NB = (int)(span >> shift) + 1;
+            if (tid == 0) counters[6] = 0;
+            __syncthreads();
+            for (int i = tid; i < D; i += OVO_THREADS) {
+                const int bi = (int)((st_key[i] - kmin) >> shift);
+                const int bp = i ? (int)((st_key[i - 1] - kmin) >> shift) : -1;
+                for (int bb = bp + 1; bb <= bi; ++bb) bkidx[bb] = (uint16_t)i;
+                if (i == D - 1) for (int bb = bi + 1; bb <= NB; ++bb) bkidx[bb] = (uint16_t)D;
+            }
+            __syncthreads();
+            int occ = 0;
+            for (int bb = tid; bb < NB; bb += OVO_THREADS) occ = max(occ, (int)bkidx[bb + 1] - (int)bkidx[bb]);
+            if (occ) atomicMax(&counters[6], occ);
+            __syncthreads();
+            R.kmin = kmin; R.bk_shift = shift; R.bk_last = NB - 1;
+            R.bk_T = 32 - __clz(counters[6]);                             // halvings that empty a range of that many entries
+            __syncthreads();
         }
         rsum = block_sum<double>(rsum, redd);
         R.sum = P.flags.group_sums ? P.flags.group_sums[(long long)ref * P.n_cols + (P.gene_map ? P.gene_map[j] : j)] : rsum;
@@ -747,7 +812,7 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
                 int m = 0;
                 for (int s = s0; s < s1; ++s) m += (int)cnt[s];
                 if (m > WARP_CAP || (R.keys == nullptr && R.n_ref + (long long)pl.group_size[g] > 208063)) {
-                    if (lane == 0) blist[atomicAdd(&cnt_m[1], 1)] = (uint16_t)(g - g0);
+                    if (lane == 0) { mlist[e] = (uint16_t)((g - g0) | 0x8000); atomicAdd(&cnt_m[1], 1); }
                     continue;
                 }
                 uint32_t* buf = scratch + w * wcap;
@@ -781,8 +846,10 @@ __global__ void __launch_bounds__(OVO_THREADS, MIN_CTAS) ovo_kernel(const OvoPar
             __syncthreads();
             // ---- block tier: one group at a time, sorted in the CTA's global slab
             const int nb = cnt_m[1];
-            for (int e = 0; e < nb; ++e) {
-                const int g = g0 + blist[e];
+            for (int e = 0; e < nm && nb > 0; ++e) {
+                const int me = mlist[e];
+                if (!(me & 0x8000)) continue;                             // (CTA-uniform)
+                const int g = g0 + (me & 0x7fff);
                 const int s0 = pl.group_seg[g], s1 = pl.group_seg[g + 1];
                 int m = 0;
                 for (int s = s0; s < s1; ++s) {
@@ -894,6 +961,7 @@ int launch_ovo_mapped(const float* ir_vals, const uint32_t* ir_cnt, int n_genes,
     P.n_genes_dev = n_genes_dev; P.gene_map = gene_map; P.n_cols = n_cols;
     P.dbg_u2 = dbg ? (long long*)dbg->u2 : nullptr; P.dbg_tie = dbg ? dbg->tie_sum : nullptr;
     P.dbg_tie_exact = dbg ? (long long*)dbg->tie_exact : nullptr;
+    P.bucket_index = env_int("ILLICO_OVO_BUCKETS", 1);
     static const int nt = env_int("ILLICO_OVO_THREADS", 256);
     if (nt == 512) {
         if (flags->is_log1p) return launch_ovo_t<512, 2, true>(P, plan, workspace, workspace_bytes, sms, max_smem, stream);

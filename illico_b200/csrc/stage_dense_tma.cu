@@ -64,8 +64,8 @@ struct TmaLayout {
     static size_t bytes(int segs_per_cta) { return (size_t)CNT_OFF + (size_t)segs_per_cta * GENES * 2; }
 };
 
-template <int VEC, int ROWS, int STAGES>
-__global__ void __launch_bounds__(TMA_THREADS) stage_dense_tma_kernel(const float* __restrict__ X, long long ld, int gene_lb,
+template <int VEC, int ROWS, int STAGES, int MINB>
+__global__ void __launch_bounds__(TMA_THREADS, MINB) stage_dense_tma_kernel(const float* __restrict__ X, long long ld, int gene_lb,
                                                                       int b, const illico_plan_t pl,
                                                                       float* __restrict__ ir_vals,
                                                                       uint32_t* __restrict__ ir_cnt, int segs_per_cta, int seg_lo,
@@ -85,9 +85,10 @@ __global__ void __launch_bounds__(TMA_THREADS) stage_dense_tma_kernel(const floa
     // tiles: (256 * VEC genes) x (segs_per_cta segments).  A 2-D grid gives every CTA its own tile; a 1-D (persistent)
     // grid walks them.  The ring's stage counters run on across tiles, so the producer fills the ring with the next
     // tile's rows while the consumers finish the current one.
-    const long long n_tiles = (long long)tiles_x * tiles_y;
-    const long long tile0 = (gridDim.y > 1 || gridDim.x == (unsigned)n_tiles) ? (long long)blockIdx.y * gridDim.x + blockIdx.x : blockIdx.x;
-    const long long tile_step = (gridDim.y > 1 || gridDim.x == (unsigned)n_tiles) ? n_tiles : gridDim.x;
+    const int n_tiles = tiles_x * tiles_y;
+    const bool own_tile = gridDim.y > 1 || gridDim.x == (unsigned)n_tiles;
+    const int tile0 = own_tile ? (int)(blockIdx.y * gridDim.x + blockIdx.x) : (int)blockIdx.x;
+    const int tile_step = own_tile ? n_tiles : (int)gridDim.x;
 
     if (t == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -104,8 +105,8 @@ __global__ void __launch_bounds__(TMA_THREADS) stage_dense_tma_kernel(const floa
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         const unsigned long long ldb = (unsigned long long)ld * 4ull;
         int k = 0;                                                       // stage counter (runs on across tiles)
-        for (long long tile = tile0; tile < n_tiles; tile += tile_step) {
-        const int bx = (int)(tile % tiles_x), by = (int)(tile / tiles_x);
+        for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+        const int bx = tile % tiles_x, by = tile / tiles_x;
         const int s_begin = seg_lo + by * segs_per_cta, s_end = min(seg_hi, s_begin + segs_per_cta);
         const int p_begin = pl.seg_pos[s_begin], p_end = pl.seg_pos[s_end];
         const int g0 = bx * L::GENES;                              // first gene of the tile inside the batch
@@ -138,8 +139,8 @@ __global__ void __launch_bounds__(TMA_THREADS) stage_dense_tma_kernel(const floa
 
     // ---------------- consumer warps: lane = VEC adjacent genes
     int k = 0;                                                           // stage counter (runs on across tiles)
-    for (long long tile = tile0; tile < n_tiles; tile += tile_step) {
-    const int bx = (int)(tile % tiles_x), by = (int)(tile / tiles_x);
+    for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+    const int bx = tile % tiles_x, by = tile / tiles_x;
     const int s_begin = seg_lo + by * segs_per_cta, s_end = min(seg_hi, s_begin + segs_per_cta);
     const int p_begin = pl.seg_pos[s_begin], p_end = pl.seg_pos[s_end];
     const int g0 = bx * L::GENES;
@@ -257,17 +258,17 @@ int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-template <int VEC, int ROWS, int STAGES>
+template <int VEC, int ROWS, int STAGES, int MINB>
 int launch_t(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals, uint32_t* ir_cnt,
              int segs_per_cta, int seg_lo, int seg_hi, cudaStream_t stream, const int* mode_dev, int want_mode) {
     using L = TmaLayout<VEC, ROWS, STAGES>;
     const unsigned gx = (unsigned)((b + L::GENES - 1) / L::GENES);
     const unsigned gy = (unsigned)((seg_hi - seg_lo + segs_per_cta - 1) / segs_per_cta);
     const size_t smem = L::bytes(segs_per_cta);
-    auto kern = stage_dense_tma_kernel<VEC, ROWS, STAGES>;
+    auto kern = stage_dense_tma_kernel<VEC, ROWS, STAGES, MINB>;
     ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(gx, gy);
-    if (mode_dev) {                                    // decided on the device: persistent 1-D grid
+    if (mode_dev || env_int("ILLICO_STAGE_PERSIST", 0)) {   // decided on the device: persistent 1-D grid
         int occ = 0;
         ILLICO_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TMA_THREADS, smem));
         long long ctas = 148ll * (occ > 0 ? occ : 1);
@@ -307,14 +308,23 @@ int launch_stage_dense_tma_if(const float* X, long long ld, int gene_lb, int b, 
     if (segs_per_cta < 1) segs_per_cta = 1;
     if (segs_per_cta > TMA_MAX_SEGS) segs_per_cta = TMA_MAX_SEGS;
     if (!mode_dev && (S + segs_per_cta - 1) / segs_per_cta > 65535) return -1;      // caller falls back to the plain kernel
-    // Ring configurations measured at the K562 shape (profiles/README.md): all within 3 % of each other; one gene
-    // per lane (1 KB row pieces, 32 KB ring, 2-3 CTAs per SM) is the fastest and has the smallest footprint.
+    // Ring configurations measured at the K562 shape (profiles/README.md): one gene per lane (1 KB row pieces) is the
+    // fastest and has the smallest footprint.
     switch (env_int("ILLICO_STAGE_TMA_CFG", 0)) {
-        case 1: return launch_t<2, 4, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
-        case 2: return launch_t<2, 8, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
-        case 3: return launch_t<4, 4, 3>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
-        default: return launch_t<1, 8, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
+        case 1: return launch_t<2, 4, 4, 2>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
+        case 2: return launch_t<2, 8, 4, 2>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
+        case 3: return launch_t<4, 4, 3, 2>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
+        case 4: return launch_t<1, 8, 4, 3>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
+        case 5: return launch_t<1, 8, 6, 2>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
+        case 6: return launch_t<1, 8, 4, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
+        default: break;
     }
+    // measured (scripts/exp/stage_persist.sh, continuous K562 shape): 72 registers / 3 CTAs per SM 2.01 ms as a 2-D grid and
+    // 2.14 ms persistent; 96 registers / 2 CTAs per SM with a 6-stage ring 2.05 / 2.09 ms; 56 registers / 4 CTAs per SM
+    // spills in the per-element loop and takes 3.4 ms
+    if (mode_dev || env_int("ILLICO_STAGE_PERSIST", 0))
+        return launch_t<1, 8, 6, 2>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
+    return launch_t<1, 8, 4, 3>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
 }
 
 int launch_stage_dense_tma(const float* X, long long ld, int gene_lb, int b, const illico_plan_t* plan, float* ir_vals,
