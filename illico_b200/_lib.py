@@ -33,7 +33,7 @@ class Flags(C.Structure):
     """``illico_flags_t``"""
 
     _fields_ = [("is_log1p", _i32), ("use_continuity", _i32), ("tie_correct", _i32), ("alternative", _i32),
-                ("tie_order", _i32), ("reserved", _i32), ("group_sums", _vp)]
+                ("tie_order", _i32), ("n_cols_hint", _i32), ("group_sums", _vp)]
 
 
 class Debug(C.Structure):

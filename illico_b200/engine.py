@@ -207,6 +207,9 @@ class Engine:
                 rc = fn(M.data.data_ptr(), M.ld, lb, b, C.byref(self.plan), C.byref(flags), C.byref(buf), out_ptr,
                         gstride, dbg_ref, st)
             else:
+                if M.fmt == "csr" and flags.n_cols_hint != M.shape[1]:
+                    flags = _lib.Flags(flags.is_log1p, flags.use_continuity, flags.tie_correct, flags.alternative, flags.tie_order,
+                                       int(M.shape[1]), flags.group_sums)
                 fn = getattr(self.lib, f"illico_{test}_{M.fmt}_f32")
                 rc = fn(M.data.data_ptr(), M.indices.data_ptr(), M.indptr.data_ptr(), lb, b, C.byref(self.plan),
                         C.byref(flags), C.byref(buf), out_ptr, gstride, dbg_ref, st)
