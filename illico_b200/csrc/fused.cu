@@ -617,13 +617,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_wide_pass_kernel(co
     auto close_group = [&](int g) {
         uint32_t m = 0, s1 = 0, above = 0;
         unsigned long long u2 = 0, tie = 0;
+        // a, b < 2^16 (checked by the table step / the group-size limit): every product below is formed from 32-bit
+        // factors, so each term is one widening multiply-add
         auto bin = [&](uint32_t ha, uint32_t a, int q) {
             const uint32_t bq = lds_h(ha);
             if (bq) {
                 sts_h(ha, 0u);
                 u2 += (unsigned long long)bq * (2u * above + a);
-                // (a+b)^3 - (a+b) - (a^3 - a) = b (3 a (a + b) + b^2) - b
-                tie += (unsigned long long)bq * (3ull * a * (unsigned long long)(a + bq) + (unsigned long long)bq * bq);
+                // (a+b)^3 - (a+b) - (a^3 - a) = 3 a b (a + b) + b^3 - b
+                tie += (unsigned long long)(a * bq) * (3u * (a + bq));
+                tie += (unsigned long long)(bq * bq) * bq;
                 s1 += bq * (uint32_t)(q + 1);
                 m += bq;
             }
@@ -1375,16 +1378,19 @@ int run_fused(const float* X, long long ld, int gene_lb, int b, const illico_pla
         rc = launch_pass_t<8, 4, 16, 3, OVO>(X, ld, gene_lb, b, plan, gpc, gt, bs, results, gstride, stream);
     if (rc) return rc;
     if (wide_on) {
-        using L = WideLayout<8, 5>;
-        auto kern = fused_wide_pass_kernel<8, 5, 2>;
-        ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+        // (a 6-stage ring -- 112 KB per CTA, the most two CTAs per SM leave room for -- makes the pass 3 % faster and the
+        // whole step 9 % slower: measured, scripts/exp/wide3.sh)
+        const bool six = env_int("ILLICO_WIDE_STAGES", 5) == 6;
+        auto kern = six ? fused_wide_pass_kernel<8, 6, 2> : fused_wide_pass_kernel<8, 5, 2>;
+        const int wide_smem = six ? WideLayout<8, 6>::BYTES : WideLayout<8, 5>::BYTES;
+        ILLICO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem));
         // persistent: two CTAs per SM, each a tile of 256 genes walking every gy-th chunk of groups
         const int tiles = (b + FUSED_LANES - 1) / FUSED_LANES, chunks = (plan->n_groups + gpc - 1) / gpc;
         int gy = (2 * 148) / tiles;
         if (gy < 1) gy = 1;
         if (gy > chunks) gy = chunks;
         const dim3 grid((unsigned)tiles, (unsigned)gy);
-        ILLICO_LAUNCH("fused_wide_pass_kernel", stream, kern<<<grid, FUSED_THREADS, L::BYTES, stream>>>(
+        ILLICO_LAUNCH("fused_wide_pass_kernel", stream, kern<<<grid, FUSED_THREADS, wide_smem, stream>>>(
                 X, ld, gene_lb, b, *plan, gpc, gt, bs, reinterpret_cast<unsigned long long*>(results), gstride, list_share_1024()));
         ILLICO_CUDA_OK(cudaGetLastError());
     }
