@@ -234,6 +234,7 @@ def kernel_bytes(name, fmt, test, cells, genes, G, nnz, n_ref, S):
     rank = nnz * 4 + S * genes * 4 + 24 * G * genes
     table = {
         "fused_pass_kernel": (cells - n_ref) * genes * 4 + 24 * Gt * genes,
+        "fused_wide_pass_kernel": (cells - n_ref) * genes * 4 + 24 * Gt * genes,
         "fused_csr_pass_kernel": sparse_in + 24 * Gt * genes,
         "fused_epilogue_kernel": 48 * G * genes,
         "stage_dense_tma_kernel": dense_in, "stage_dense_kernel": dense_in,
