@@ -74,6 +74,9 @@ SIGNATURES = {
     "illico_ovo_csr_f32": _DISPATCH_SPARSE,
     "illico_ovr_csc_f32": _DISPATCH_SPARSE,
     "illico_ovo_csc_f32": _DISPATCH_SPARSE,
+    "illico_enable_peer_access": (C.c_int, [_i32, _i32]),
+    "illico_csr_shard_count": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
+    "illico_csr_shard_scatter": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "illico_bh_workspace_bytes": (_sz, [_i32, _i32]),
     "illico_bh_adjust": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "illico_compute_pval_batch": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),

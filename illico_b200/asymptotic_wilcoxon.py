@@ -13,6 +13,7 @@ What changed relative to the reference's driver (same contract, different machin
 """
 from __future__ import annotations
 
+import os
 import threading
 from queue import Empty, Queue
 from typing import Literal
@@ -151,6 +152,24 @@ def asymptotic_wilcoxon(
     shards = [sh for sh in shards if sh.ub > sh.lb] or [_Shard(devs[0], 0, n_genes)]
     plan_ready = threading.Event()
     shared: dict = {}
+    # A CSR matrix on several GPUs: row blocks go up (each byte once), the GPUs cut them and exchange the pieces over
+    # NVLink (repartition.py), instead of every GPU receiving the whole matrix
+    prep = None
+    if fmt == CSR and len(shards) > 1 and data_handler.in_ram and isinstance(X, sparse.csr_matrix) \
+            and X.data.dtype == np.float32 and os.environ.get("ILLICO_CSR_REPARTITION", "1") != "0":
+        from . import repartition
+
+        if repartition.peer_access_ok([sh.device for sh in shards]):
+            def _prep():
+                try:
+                    Ms = repartition.repartition_csr(X, [sh.device for sh in shards], [sh.lb for sh in shards] + [shards[-1].ub])
+                    for sh, M in zip(shards, Ms):
+                        sh.started = (M, (0, sh.ub - sh.lb))
+                except BaseException as e:
+                    shared["prep_error"] = e
+
+            prep = threading.Thread(target=_prep, daemon=True)
+            prep.start()
 
     def run_shard(sh: _Shard):
         """Everything one GPU does, on its own host thread: upload its gene shard (started before the groups are
@@ -158,6 +177,10 @@ def asymptotic_wilcoxon(
         try:
             if len(shards) > 1:
                 hostio.bind_thread_to_device_node(sh.device.index if sh.device.index is not None else 0)
+            if prep is not None:
+                prep.join()
+                if "prep_error" in shared:
+                    raise shared["prep_error"]
             with torch.cuda.device(sh.device):
                 M = bounds = None
                 if data_handler.in_ram:

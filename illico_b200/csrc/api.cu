@@ -79,6 +79,10 @@ int launch_ovr_csr_fused(const float*, const int32_t*, const long long*, int, in
 size_t ovo_fused_workspace_bytes(int, int);
 float ovo_fused_last_ms();
 size_t ovr_table_rec_bytes(const illico_plan_t*);
+// repart.cu
+int launch_csr_shard_count(const int32_t*, const long long*, long long, const int32_t*, int, int32_t*, unsigned long long*, cudaStream_t);
+int launch_csr_shard_scatter(const float*, const int32_t*, const long long*, long long, long long, const int32_t*, int, const int32_t*,
+                             const long long*, float* const*, int32_t* const*, int32_t* const*, cudaStream_t);
 
 static int check_plan(const illico_plan_t* p) {
     if (!p) { set_error("plan is NULL"); return 1; }
@@ -154,6 +158,39 @@ int illico_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spit
     ILLICO_CUDA_OK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height,
                                      kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return 0;
+}
+
+int illico_enable_peer_access(int32_t device, int32_t peer_device) {
+    if (device == peer_device) return 0;
+    int can = 0;
+    ILLICO_CUDA_OK(cudaDeviceCanAccessPeer(&can, device, peer_device));
+    if (!can) { set_error("GPU %d cannot access GPU %d's memory", device, peer_device); return 1; }
+    int cur = 0;
+    ILLICO_CUDA_OK(cudaGetDevice(&cur));
+    ILLICO_CUDA_OK(cudaSetDevice(device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    cudaSetDevice(cur);
+    if (e != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", device, peer_device, cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
+int illico_csr_shard_count(const int32_t* indices, const int64_t* indptr, int64_t n_rows, const int32_t* bounds, int32_t n_shards,
+                           int32_t* cnt, uint64_t* totals, void* stream) {
+    if (!indptr || !bounds || !cnt || !totals) { set_error("illico_csr_shard_count: NULL argument"); return 1; }
+    return launch_csr_shard_count(indices, (const long long*)indptr, n_rows, bounds, n_shards, cnt, (unsigned long long*)totals,
+                                  (cudaStream_t)stream);
+}
+
+int illico_csr_shard_scatter(const float* data, const int32_t* indices, const int64_t* indptr, int64_t n_rows, int64_t row0,
+                             const int32_t* bounds, int32_t n_shards, const int32_t* cnt, const int64_t* out_pos,
+                             float* const* out_data, int32_t* const* out_indices, int32_t* const* out_row_cnt, void* stream) {
+    if (!indptr || !bounds || !cnt || !out_pos || !out_data || !out_indices || !out_row_cnt) {
+        set_error("illico_csr_shard_scatter: NULL argument");
+        return 1;
+    }
+    return launch_csr_shard_scatter(data, indices, (const long long*)indptr, n_rows, row0, bounds, n_shards, cnt, (const long long*)out_pos,
+                                    out_data, out_indices, out_row_cnt, (cudaStream_t)stream);
 }
 
 int illico_stage_dense_f32(const float* X, int64_t ld, int32_t gene_lb, int32_t n_genes_batch, const illico_plan_t* plan,

@@ -209,6 +209,26 @@ int illico_ovo_csc_f32(const float* data, const int32_t* indices, const int64_t*
                        const illico_batch_buffers_t* buf, double* results, int64_t result_group_stride,
                        const illico_debug_t* dbg, void* stream);
 
+/* ---- rows -> genes repartition of a CSR matrix across GPUs -------------------------------------
+ * Replaces, across GPUs, csr_get_contig_cols_into_csr (illico/utils/sparse/csr.py:144-196): every GPU holds a block of
+ * ROWS [row0, row0 + n_rows) of the CSR matrix (indptr rebased to the block: indptr[0] = 0) and cuts it into n_shards
+ * (<= 32) column ranges bounds[j] <= column < bounds[j + 1] (device array of n_shards + 1 ascending column indices).
+ *   illico_csr_shard_count    cnt[j * n_rows + r] = entries of row r in shard j; totals[j] += their sum (zero it first).
+ *   illico_csr_shard_scatter  writes row r's piece for shard j at out_data[j][out_pos[j * n_rows + r] ...] /
+ *                             out_indices[j][...] (column index rebased to the shard) and its count at
+ *                             out_row_cnt[j][row0 + r].  The out_* arrays (host arrays of n_shards device pointers) may live
+ *                             on OTHER GPUs with peer access enabled (illico_enable_peer_access): the kernel's stores are
+ *                             the exchange.  out_pos = the shard's running offset: entries of earlier row blocks + the
+ *                             exclusive scan of cnt over this block's rows.
+ * The owner of shard j then has its genes as a CSR matrix over all rows: data / indices as written, indptr = the scan of its
+ * row counts. */
+int illico_enable_peer_access(int32_t device, int32_t peer_device);
+int illico_csr_shard_count(const int32_t* indices, const int64_t* indptr, int64_t n_rows, const int32_t* bounds,
+                           int32_t n_shards, int32_t* cnt, uint64_t* totals, void* stream);
+int illico_csr_shard_scatter(const float* data, const int32_t* indices, const int64_t* indptr, int64_t n_rows, int64_t row0,
+                             const int32_t* bounds, int32_t n_shards, const int32_t* cnt, const int64_t* out_pos,
+                             float* const* out_data, int32_t* const* out_indices, int32_t* const* out_row_cnt, void* stream);
+
 /* ---- next to the path and a test hook ------------------------------------------- */
 
 /* Benjamini-Hochberg adjusted p-values over the genes of each group (statsmodels multipletests(method="fdr_bh") /

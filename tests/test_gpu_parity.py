@@ -869,3 +869,42 @@ def test_ovo_stream_tier_with_repeated_values(fmt, log1p):
     np.testing.assert_array_equal(dbg["u2"].cpu().numpy()[rows], (2 * U[rows]).astype(np.int64))
     dispatch.clear_caches()
     assert torch.cuda.is_available()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_shards", [1, 3, 8])
+def test_csr_repartition_matches_host_slicing(n_shards):
+    """repartition.py / csrc/repart.cu (rows -> genes repartition of a CSR matrix; csr_get_contig_cols_into_csr,
+    illico/utils/sparse/csr.py:144-196, across GPUs): row blocks cut on the device and scattered into the shards' arrays
+    give exactly the column slices scipy gives -- empty rows, empty shards' pieces, explicit zeros included.  (All shards
+    live on cuda:0 here; the stores are the same instructions when the arrays are another GPU's.)"""
+    import torch
+    from scipy import sparse
+
+    from illico_b200 import repartition
+
+    rng = np.random.RandomState(3)
+    n, N = 5000, 700
+    X = sparse.random(n, N, density=0.07, format="csr", dtype=np.float32, random_state=rng)
+    X.data[:] = rng.poisson(2.0, X.nnz).astype(np.float32)          # some stored zeros
+    X = sparse.csr_matrix(X)
+    X[17] = 0                                                        # (keeps explicit zeros: an all-zero row of stored values)
+    X.sort_indices()
+    edges = np.linspace(0, N, n_shards + 1).astype(int)
+    edges[1:-1] += rng.randint(-20, 20, size=n_shards - 1) if n_shards > 1 else 0
+    dev = torch.device("cuda", 0)
+    shards = repartition.repartition_csr(X, [dev] * n_shards, list(edges))
+    torch.cuda.synchronize()
+    for j, M in enumerate(shards):
+        want = X[:, edges[j]:edges[j + 1]]
+        assert M.shape == want.shape and M.gene_offset == edges[j]
+        np.testing.assert_array_equal(M.indptr.cpu().numpy(), want.indptr)
+        np.testing.assert_array_equal(M.indices.cpu().numpy(), want.indices)
+        np.testing.assert_array_equal(M.data.cpu().numpy(), want.data)
+    # unsorted rows are refused with the reference's error (asymptotic_wilcoxon.py:185-193)
+    Y = X.copy()
+    r = int(np.argmax(np.diff(Y.indptr) > 3))
+    a = Y.indptr[r]
+    Y.indices[a], Y.indices[a + 1] = Y.indices[a + 1], Y.indices[a]
+    with pytest.raises(ValueError, match="indices are not sorted"):
+        repartition.repartition_csr(Y, [dev] * n_shards, list(edges))
