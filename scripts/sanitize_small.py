@@ -34,4 +34,28 @@ for fmt in ("dense", "csr"):
             out = asymptotic_wilcoxon(FakeAnnData(C.to_format(Xi, fmt), labels), is_log1p=log1p, group_keys="pert",
                                       reference=ref, return_array=True)
             assert np.isfinite(out[2][:, :, 1]).all()
+# round 2: the wide-table pass (integer counts up to 64: dense high-count genes, a value past 64, a fractional one), the
+# whole-batch hand-back decided on the device, and the CSR rows -> genes repartition kernels
+os.environ["ILLICO_FUSED_LIST_SHARE"] = "0.125"
+rng = np.random.RandomState(1)
+X, labels = synth.k562_like(seed=4, n_cells=3000, n_genes=40, n_perts=9)
+X[:, 3] = rng.poisson(12.0, X.shape[0])
+X[:, 4] = rng.poisson(30.0, X.shape[0])
+X[:, 9] = rng.poisson(50.0, X.shape[0])
+X[7, 11] = 2.5
+out = asymptotic_wilcoxon(FakeAnnData(X, labels), is_log1p=False, group_keys="pert", reference=synth.CONTROL, return_array=True)
+assert np.isfinite(out[2][:, :, 1]).all()
+Xc = np.log1p(X / (X.sum(1, keepdims=True) + 1.0) * 1e4).astype(np.float32)      # continuous: every gene handed back (HB_ALL)
+for fmt in ("dense", "csr"):
+    out = asymptotic_wilcoxon(FakeAnnData(C.to_format(Xc, fmt), labels), is_log1p=False, group_keys="pert",
+                              reference=synth.CONTROL, return_array=True)
+    assert np.isfinite(out[2][:, :, 1]).all()
+import torch  # noqa: E402
+
+from illico_b200 import repartition  # noqa: E402
+
+csr = C.to_format(X, "csr")
+shards = repartition.repartition_csr(csr, [torch.device("cuda", 0)] * 3, [0, 13, 27, 40])
+torch.cuda.synchronize()
+assert sum(int(m.data.numel()) for m in shards) == csr.nnz
 print("sanitize run ok")
