@@ -1475,16 +1475,15 @@ int run_fused_csr(const float* data, const int32_t* indices, const long long* in
         // (An atomics-free variant -- the whole CTA applies one row at a time, plain LDS/STS -- measured 1.5-2.7 x
         // slower: 150 CTA-wide barriers per segment cost more than the shared atomics they avoid.  Counting part of the
         // updates in a per-SM global histogram with L2 reductions instead of shared atomics measured 1.4-1.9 x slower.)
-        // 1 = warp per row, shared-memory atomics (default); 2 / 4 / 3 = warp per gene range without atomics, 4 or 8 rows in
-        // flight / 512-gene ranges.  Measured at the K562 shape (scripts/exp/csr2.sh): 1.15 ms against 1.57 / 1.62 / 2.54 ms --
-        // finding the range's start in every row costs about 105 instructions per 24-entry row piece, more than the atomics.
+        // 1 = warp per row, shared-memory atomics (default); 2 = warp per gene range without atomics.  Measured at the K562
+        // shape (scripts/exp/csr2.sh): 1.15 ms against 1.57 ms (8 rows in flight: 1.62 ms; 512-gene ranges, one CTA per SM:
+        // 2.54 ms) -- finding the range's start in every row costs about 105 instructions per 24-entry row piece, more than
+        // the atomics it saves.
         const int pass_kind = env_int("ILLICO_CSR_PASS", 1);
         if (pass_kind >= 2) {
             const bool ident = !flags->is_log1p;                 // fused_seed_kernel seeded the slots with 1 .. 12
-            const int range = pass_kind == 3 ? 512 : 256;
-            auto kern2 = range == 512 ? (ident ? fused_csr_pass2_kernel<OVO, true, 512, 4> : fused_csr_pass2_kernel<OVO, false, 512, 4>)
-                         : pass_kind == 4 ? (ident ? fused_csr_pass2_kernel<OVO, true, 256, 8> : fused_csr_pass2_kernel<OVO, false, 256, 8>)
-                                          : (ident ? fused_csr_pass2_kernel<OVO, true, 256, 4> : fused_csr_pass2_kernel<OVO, false, 256, 4>);
+            const int range = 256;
+            auto kern2 = ident ? fused_csr_pass2_kernel<OVO, true, 256, 4> : fused_csr_pass2_kernel<OVO, false, 256, 4>;
             const int tile = CSR2_WARPS * range;
             const size_t smem2 = (size_t)(b < tile ? b : tile) * 24;
             ILLICO_CUDA_OK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));

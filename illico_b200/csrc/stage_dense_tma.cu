@@ -316,7 +316,6 @@ int launch_stage_dense_tma_if(const float* X, long long ld, int gene_lb, int b, 
         case 3: return launch_t<4, 4, 3, 2>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
         case 4: return launch_t<1, 8, 4, 3>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
         case 5: return launch_t<1, 8, 6, 2>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
-        case 6: return launch_t<1, 8, 4, 4>(X, ld, gene_lb, b, plan, ir_vals, ir_cnt, segs_per_cta, seg_lo, seg_hi, stream, mode_dev, want_mode);
         default: break;
     }
     // measured (scripts/exp/stage_persist.sh, continuous K562 shape): 72 registers / 3 CTAs per SM 2.01 ms as a 2-D grid and
