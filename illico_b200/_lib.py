@@ -74,6 +74,11 @@ SIGNATURES = {
     "illico_ovo_csr_f32": _DISPATCH_SPARSE,
     "illico_ovr_csc_f32": _DISPATCH_SPARSE,
     "illico_ovo_csc_f32": _DISPATCH_SPARSE,
+    "illico_convert_values": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "illico_recode_workspace_bytes": (_sz, [_i64, _i32]),
+    "illico_recode_dense": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "illico_recode_csc": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "illico_recode_csr": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "illico_enable_peer_access": (C.c_int, [_i32, _i32]),
     "illico_csr_shard_count": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
     "illico_csr_shard_scatter": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -81,6 +86,8 @@ SIGNATURES = {
     "illico_bh_adjust": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "illico_compute_pval_batch": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
 }
+
+DTYPE_F32, DTYPE_F64, DTYPE_F16, DTYPE_I8, DTYPE_U8, DTYPE_I16, DTYPE_I32, DTYPE_I64 = range(8)
 
 _lib = None
 

@@ -79,6 +79,14 @@ int launch_ovr_csr_fused(const float*, const int32_t*, const long long*, int, in
 size_t ovo_fused_workspace_bytes(int, int);
 float ovo_fused_last_ms();
 size_t ovr_table_rec_bytes(const illico_plan_t*);
+// recode.cu
+size_t recode_workspace_bytes(long long, int);
+int launch_convert_values(const void*, int, long long, float*, double*, int*, cudaStream_t);
+int launch_recode_dense(const double*, long long, int, int, long long, const int32_t*, int, int, float*, double*, void*, size_t, cudaStream_t);
+int launch_recode_csc(const double*, const int32_t*, const long long*, int, int, const int32_t*, int, long long, int, float*, double*, void*,
+                      size_t, cudaStream_t);
+int launch_recode_csr(const double*, const int32_t*, const long long*, long long, int, int, const int32_t*, int, int, float*, double*, void*,
+                      size_t, cudaStream_t);
 // repart.cu
 int launch_csr_shard_count(const int32_t*, const long long*, long long, const int32_t*, int, int32_t*, unsigned long long*, cudaStream_t);
 int launch_csr_shard_scatter(const float*, const int32_t*, const long long*, long long, long long, const int32_t*, int, const int32_t*,
@@ -158,6 +166,42 @@ int illico_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spit
     ILLICO_CUDA_OK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height,
                                      kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return 0;
+}
+
+static int check_recode(const void* values, int32_t dtype, const void* cell_group, const void* codes, const void* sums, const void* ws) {
+    if (dtype != ILLICO_DTYPE_F64) { set_error("illico_recode_*: dtype %d (float32-exact dtypes are converted on upload; pass float64)", dtype); return 1; }
+    if (!values || !cell_group || !codes || !sums || !ws) { set_error("illico_recode_*: NULL argument"); return 1; }
+    return 0;
+}
+int illico_convert_values(const void* src, int32_t dtype, int64_t count, float* dst_f32, double* dst_f64, int32_t* inexact, void* stream) {
+    if (count > 0 && (!src || (!dst_f32 && !dst_f64) || (dst_f32 && !inexact))) { set_error("illico_convert_values: NULL argument"); return 1; }
+    return launch_convert_values(src, dtype, count, dst_f32, dst_f64, inexact, (cudaStream_t)stream);
+}
+size_t illico_recode_workspace_bytes(int64_t total_keys, int32_t n_genes_batch) {
+    return recode_workspace_bytes(total_keys > 0 ? total_keys : 0, n_genes_batch > 0 ? n_genes_batch : 1);
+}
+int illico_recode_dense(const void* X, int32_t dtype, int64_t ld, int32_t gene_lb, int32_t nb, int64_t n_cells, const int32_t* cell_group,
+                        int32_t n_groups, int32_t is_log1p, float* codes, double* group_sums, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    if (check_recode(X, dtype, cell_group, codes, group_sums, workspace)) return 1;
+    return launch_recode_dense((const double*)X, ld, gene_lb, nb, n_cells, cell_group, n_groups, is_log1p, codes, group_sums, workspace,
+                               workspace_bytes, (cudaStream_t)stream);
+}
+int illico_recode_csc(const void* data, int32_t dtype, const int32_t* indices, const int64_t* indptr, int32_t gene_lb, int32_t nb,
+                      int64_t batch_nnz, const int32_t* cell_group, int32_t n_groups, int32_t is_log1p, float* codes, double* group_sums,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    if (batch_nnz > 0 && check_recode(data, dtype, cell_group, codes, group_sums, workspace)) return 1;
+    if (!indptr || !group_sums || !workspace) { set_error("illico_recode_csc: NULL argument"); return 1; }
+    return launch_recode_csc((const double*)data, indices, (const long long*)indptr, gene_lb, nb, cell_group, n_groups, batch_nnz, is_log1p,
+                             codes, group_sums, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int illico_recode_csr(const void* data, int32_t dtype, const int32_t* indices, const int64_t* indptr, int64_t n_cells, int32_t gene_lb,
+                      int32_t nb, const int32_t* cell_group, int32_t n_groups, int32_t is_log1p, float* codes, double* group_sums,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    if (!indptr || !group_sums || !workspace || !cell_group) { set_error("illico_recode_csr: NULL argument"); return 1; }
+    if (dtype != ILLICO_DTYPE_F64) { set_error("illico_recode_csr: dtype %d (pass float64)", dtype); return 1; }
+    return launch_recode_csr((const double*)data, indices, (const long long*)indptr, n_cells, gene_lb, nb, cell_group, n_groups, is_log1p,
+                             codes, group_sums, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int illico_enable_peer_access(int32_t device, int32_t peer_device) {

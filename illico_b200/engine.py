@@ -95,7 +95,7 @@ class Engine:
             max_group_size=hp.max_group_size, ref_group_size=hp.ref_group_size, ref_seg_begin=hp.ref_seg_begin,
             ref_seg_end=hp.ref_seg_end, slot_cap=hp.slot_cap, max_target_group_size=hp.max_target_group_size,
             **{k: self._tables[k].data_ptr() for k in HostPlan.TABLES})
-        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._flag = torch.empty(1, dtype=torch.int32, device=self.device)   # (written by illico_check_csr_sorted itself)
         # The reference calls its dispatchers from joblib threads (ctypes drops the GIL).  The C ABI only enqueues work and
         # owns nothing, so concurrency is a matter of buffers: every host thread gets its own batch buffers (staged lists,
         # counts, workspace) and the engine needs no lock.
@@ -216,29 +216,63 @@ class Engine:
         _lib.check(rc, f"illico_{test}_{M.fmt}_f32")
 
     def _run_batch_wide(self, M: DeviceMatrix, lb: int, ub: int, flags: _lib.Flags, results, result_gene0, debug):
-        """float64 / big-integer input: every sub-batch is recoded to order-preserving float32 codes (exact ranks,
-        U, ties, p) and the fold change uses float64 group sums computed from the original values."""
+        """float64 input (values float32 cannot hold): every sub-batch is recoded on the device to order-preserving
+        float32 codes in the input's own layout (exact ranks, U, ties, p) and the fold change uses float64 group sums
+        computed from the original values -- ``illico_recode_{dense,csr,csc}`` (csrc/recode.cu), then the ordinary
+        dispatcher.  The reference specialises its numba kernels per dtype instead (``ovr/dense_ovr.py:46-53``)."""
         n = self.host_plan.n_cells
-        step = max(1, min(ub - lb, (1 << 28) // max(n, 1)))  # ~2 GB of float64 per sub-batch
+        if n >= (1 << 24):
+            raise NotImplementedError("more than 2^24 cells with values float32 cannot hold")
+        dev = self.device
         enc = getattr(self, "_enc_dev", None)
         if enc is None:
-            enc = self._enc_dev = torch.from_numpy(np.ascontiguousarray(self.grpc.encoded_groups)).to(self.device)
+            enc = self._enc_dev = torch.from_numpy(np.ascontiguousarray(self.grpc.encoded_groups, dtype=np.int32)).to(dev)
+        G = self.n_groups
+        st = torch.cuda.current_stream(dev).cuda_stream
+        raw = M.raw
+        if M.fmt != DENSE and getattr(M, "_codes", None) is None:
+            M._codes = torch.empty(raw.shape, dtype=torch.float32, device=dev)     # parallel to the stored values
+        # dense / CSR key lists have one slot per cell and gene: a sub-batch holds at most 2^26 of them (1 GB of keys)
+        step = (ub - lb) if M.fmt == CSC else max(1, min(ub - lb, (1 << 26) // max(n, 1)))
         for a in range(lb, ub, step):
             z = min(ub, a + step)
-            with torch.cuda.device(self.device):
-                Xb = _dense_block_f64(M, a, z)
-                fx = torch.expm1(Xb) if flags.is_log1p else Xb
-                sums = torch.zeros((self.n_groups, z - a), dtype=torch.float64, device=self.device).index_add_(0, enc, fx)
-                codes = recode_order_preserving(Xb)
-            sub = DeviceMatrix(DENSE, (n, z - a), codes)
+            b = z - a
+            with torch.cuda.device(dev):
+                sums = torch.empty((G, b), dtype=torch.float64, device=dev)
+                if M.fmt == DENSE:
+                    keys = n * b
+                    codes = torch.empty((n, b), dtype=torch.float32, device=dev)
+                elif M.fmt == CSC:
+                    keys = int(M.indptr[z]) - int(M.indptr[a])
+                    codes = M._codes
+                else:
+                    keys = n * b
+                    codes = M._codes
+                ws = torch.empty(int(self.lib.illico_recode_workspace_bytes(keys, b)), dtype=torch.uint8, device=dev)
+                if M.fmt == DENSE:
+                    rc = self.lib.illico_recode_dense(raw.data_ptr(), _lib.DTYPE_F64, int(raw.stride(0)), a, b, n, enc.data_ptr(), G,
+                                                      int(flags.is_log1p), codes.data_ptr(), sums.data_ptr(), ws.data_ptr(),
+                                                      ws.numel(), st)
+                    sub, sub_lb = DeviceMatrix(DENSE, (n, b), codes), 0
+                elif M.fmt == CSC:
+                    rc = self.lib.illico_recode_csc(raw.data_ptr(), _lib.DTYPE_F64, M.indices.data_ptr(), M.indptr.data_ptr(), a, b,
+                                                    keys, enc.data_ptr(), G, int(flags.is_log1p), codes.data_ptr(), sums.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), st)
+                    sub, sub_lb = DeviceMatrix(CSC, M.shape, codes, M.indices, M.indptr), a
+                else:
+                    rc = self.lib.illico_recode_csr(raw.data_ptr(), _lib.DTYPE_F64, M.indices.data_ptr(), M.indptr.data_ptr(), n, a, b,
+                                                    enc.data_ptr(), G, int(flags.is_log1p), codes.data_ptr(), sums.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), st)
+                    sub, sub_lb = DeviceMatrix(CSR, M.shape, codes, M.indices, M.indptr), a
+                _lib.check(rc, f"illico_recode_{M.fmt}")
             f2 = _lib.Flags(flags.is_log1p, flags.use_continuity, flags.tie_correct, flags.alternative, flags.tie_order,
                             0, sums.data_ptr())
             dbg = {} if debug is not None else None
-            self.run_batch(sub, 0, z - a, f2, results, result_gene0 + (a - lb), dbg)
+            self.run_batch(sub, sub_lb, sub_lb + b, f2, results, result_gene0 + (a - lb), dbg)
             if debug is not None:
                 for k, v in dbg.items():
                     debug.setdefault("_parts", {}).setdefault(k, []).append(v)
-            torch.cuda.current_stream(self.device).synchronize()  # sums/codes must outlive the kernels
+            torch.cuda.current_stream(dev).synchronize()  # sums / codes / workspace must outlive the kernels
         if debug is not None and "_parts" in debug:
             for k, parts in debug.pop("_parts").items():
                 debug[k] = torch.cat(parts, dim=-1)
@@ -308,54 +342,34 @@ def upload_sparse(X, fmt: str, device, gene_lb: int = 0, gene_ub: int | None = N
     return DeviceMatrix(fmt, (n, N), None, d_idx, d_indptr, gene_offset=offset, pending=pend, unconverted=d_data)
 
 
-def _dense_block_f64(M: DeviceMatrix, lb: int, ub: int) -> torch.Tensor:
-    """Genes [lb, ub) of a wide matrix as a dense float64 block [n, ub - lb] on the device."""
-    if M.fmt == DENSE:
-        return M.raw[:, lb:ub].contiguous()
-    n = M.shape[0]
-    if M.fmt == CSC:
-        lo, hi = int(M.indptr[lb]), int(M.indptr[ub])
-        ptr = (M.indptr[lb:ub + 1] - lo)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore", UserWarning)  # "sparse CSC support is in beta"
-            t = torch.sparse_csc_tensor(ptr, M.indices[lo:hi].to(torch.int64), M.raw[lo:hi], size=(n, ub - lb))
-            return t.to_dense()
-    # CSR: rows x all genes -> dense columns of the batch
-    cols = M.indices.to(torch.int64)
-    sel = (cols >= lb) & (cols < ub)
-    rows = torch.repeat_interleave(torch.arange(n, device=cols.device), M.indptr[1:] - M.indptr[:-1])
-    out = torch.zeros((n, ub - lb), dtype=torch.float64, device=cols.device)
-    out[rows[sel], cols[sel] - lb] = M.raw[sel]
-    return out
+_DTYPE_CODE = {torch.float32: _lib.DTYPE_F32, torch.float64: _lib.DTYPE_F64, torch.float16: _lib.DTYPE_F16, torch.int8: _lib.DTYPE_I8,
+               torch.uint8: _lib.DTYPE_U8, torch.int16: _lib.DTYPE_I16, torch.int32: _lib.DTYPE_I32, torch.int64: _lib.DTYPE_I64}
 
 
 def _to_f32_or_wide(t: torch.Tensor):
     """``(float32 tensor, None)`` when float32 holds every value exactly, else ``(None, float64 tensor)``.
-    Never rounds: rounding would create ties that are not in the data."""
-    f = t.to(torch.float32)
-    if bool((f.to(t.dtype) == t).all()):
-        return f, None
-    return None, t.to(torch.float64)
-
-
-def recode_order_preserving(Xb: torch.Tensor) -> torch.Tensor:
-    """Per column, replaces float64 values by small integers (as float32) with the same order, the same ties,
-    zero -> 0, negatives < 0 < positives.  Ranks, U and tie sums only depend on that, so the float32 kernels
-    stay exact for wider input types.  Plumbing (torch sort/scan), used only for such inputs."""
-    n = Xb.shape[0]
-    if n >= (1 << 24):
-        raise NotImplementedError("more than 2^24 cells with values float32 cannot hold")
-    s, idx = torch.sort(Xb, dim=0)
-    d = torch.zeros(s.shape, dtype=torch.int32, device=Xb.device)
-    d[1:] = (s[1:] != s[:-1]).to(torch.int32)
-    r = torch.cumsum(d, dim=0)
-    big = int(n) + 2
-    r0 = torch.where(s >= 0, r, torch.full_like(r, big)).min(dim=0).values
-    has_zero = (s == 0).any(dim=0)
-    code = (r - r0) + ((s > 0) & ~has_zero).to(r.dtype)
-    out = torch.empty(s.shape, dtype=torch.float32, device=Xb.device)
-    out.scatter_(0, idx, code.to(torch.float32))
-    return out
+    Never rounds: rounding would create ties that are not in the data.  (``illico_convert_values``; one host read of
+    the verdict.)"""
+    lib = _lib.load()
+    code = _DTYPE_CODE.get(t.dtype)
+    if code is None:
+        raise TypeError(f"unsupported value dtype {t.dtype}")
+    src = t if t.is_contiguous() else t.contiguous()
+    dev = src.device
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        f = torch.empty(src.shape, dtype=torch.float32, device=dev)
+        flag = torch.empty(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.illico_convert_values(src.data_ptr(), code, src.numel(), f.data_ptr(), None, flag.data_ptr(), st),
+                   "illico_convert_values")
+        if int(flag.item()) == 0:
+            return f, None
+        del f
+        if src.dtype == torch.float64:
+            return None, src
+        d = torch.empty(src.shape, dtype=torch.float64, device=dev)
+        _lib.check(lib.illico_convert_values(src.data_ptr(), code, src.numel(), None, d.data_ptr(), None, st), "illico_convert_values")
+        return None, d
 
 
 def make_flags(is_log1p: bool, use_continuity: bool, tie_correct: bool, alternative: str, fmt: str) -> _lib.Flags:

@@ -29,6 +29,8 @@
  *                                                             illico/utils/math.py:168-221,
  *                                                             illico/utils/sparse/csc.py:186-211, csr.py:261-286
  *   illico_check_csr_sorted  check_indices_sorted_per_parcel  illico/utils/ranking.py:245-273
+ *   illico_recode_*          the dtype specialisations of the numba kernels (float64 input)   illico/ovr/dense_ovr.py:46-53
+ *   illico_csr_shard_*       csr_get_contig_cols_into_csr, across GPUs                        illico/utils/sparse/csr.py:144-196
  *   illico_{ovr,ovo}_{dense,csc,csr}_f32   the six dispatchers registered in
  *                            illico/utils/registry.py:193-202 (call site illico/asymptotic_wilcoxon.py:59-67)
  *
@@ -208,6 +210,40 @@ int illico_ovo_csc_f32(const float* data, const int32_t* indices, const int64_t*
                        int32_t n_genes_batch, const illico_plan_t* plan, const illico_flags_t* flags,
                        const illico_batch_buffers_t* buf, double* results, int64_t result_group_stride,
                        const illico_debug_t* dbg, void* stream);
+
+/* ---- input dtypes ----------------------------------------------------------------------------
+ * The dispatchers above take float32 values.  The reference ranks whatever dtype the matrix has (numba specialises its
+ * kernels per dtype, illico/ovr/dense_ovr.py:46-53); here every real dtype that float32 holds exactly (integer counts,
+ * float16, ...) is converted on upload, and ILLICO_DTYPE_F64 -- values float32 cannot hold -- goes through the recode
+ * entry points: per gene, the values become order-preserving float32 codes (the signed rank among the gene's distinct
+ * values: zero -> 0, negatives < 0 < positives, equal values equal -- ranks, U and tie sums only depend on that) in the
+ * input's own layout, and the fold change's float64 group sums (illico/utils/math.py:168-221) are computed from the
+ * original values into `group_sums` [n_groups, n_genes_batch], to be passed on in illico_flags_t::group_sums.  The
+ * ordinary dispatcher is then called on the codes.  cell_group: [n_cells] group of every cell (GroupContainer
+ * .encoded_groups).  Hand-written kernels (64-bit LSD radix sort per gene, csrc/recode.cu); workspace from
+ * illico_recode_workspace_bytes(total_keys, n_genes_batch) with total_keys = n_cells * n_genes_batch (dense, CSR) or the
+ * batch's stored values (CSC). */
+enum illico_dtype {
+    ILLICO_DTYPE_F32 = 0, ILLICO_DTYPE_F64 = 1, ILLICO_DTYPE_F16 = 2, ILLICO_DTYPE_I8 = 3, ILLICO_DTYPE_U8 = 4,
+    ILLICO_DTYPE_I16 = 5, ILLICO_DTYPE_I32 = 6, ILLICO_DTYPE_I64 = 7
+};
+/* Conversion on upload: `count` values of `dtype` -> dst_f32 (optional) and / or dst_f64 (optional); *inexact (device int,
+ * zeroed by this call) is set when float32 changes some value -- such a matrix keeps its float64 copy and goes through
+ * the recode entry points, nothing is ever rounded (rounding would create ties that are not in the data). */
+int illico_convert_values(const void* src, int32_t dtype, int64_t count, float* dst_f32, double* dst_f64, int32_t* inexact,
+                          void* stream);
+size_t illico_recode_workspace_bytes(int64_t total_keys, int32_t n_genes_batch);
+/* X: row-major [n_cells, ld] of `dtype`; codes: row-major [n_cells, n_genes_batch] */
+int illico_recode_dense(const void* X, int32_t dtype, int64_t ld, int32_t gene_lb, int32_t n_genes_batch, int64_t n_cells,
+                        const int32_t* cell_group, int32_t n_groups, int32_t is_log1p, float* codes, double* group_sums,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* codes: parallel to `data` (the whole array; only the batch's entries are written) */
+int illico_recode_csc(const void* data, int32_t dtype, const int32_t* indices, const int64_t* indptr, int32_t gene_lb,
+                      int32_t n_genes_batch, int64_t batch_nnz, const int32_t* cell_group, int32_t n_groups, int32_t is_log1p,
+                      float* codes, double* group_sums, void* workspace, size_t workspace_bytes, void* stream);
+int illico_recode_csr(const void* data, int32_t dtype, const int32_t* indices, const int64_t* indptr, int64_t n_cells,
+                      int32_t gene_lb, int32_t n_genes_batch, const int32_t* cell_group, int32_t n_groups, int32_t is_log1p,
+                      float* codes, double* group_sums, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- rows -> genes repartition of a CSR matrix across GPUs -------------------------------------
  * Replaces, across GPUs, csr_get_contig_cols_into_csr (illico/utils/sparse/csr.py:144-196): every GPU holds a block of

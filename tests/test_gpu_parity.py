@@ -908,3 +908,72 @@ def test_csr_repartition_matches_host_slicing(n_shards):
     Y.indices[a], Y.indices[a + 1] = Y.indices[a + 1], Y.indices[a]
     with pytest.raises(ValueError, match="indices are not sorted"):
         repartition.repartition_csr(Y, [dev] * n_shards, list(edges))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["dense", "csr", "csc"])
+def test_native_recoding_of_float64_values(fmt):
+    """csrc/recode.cu (illico_recode_*): float64 values become, per gene, float32 codes that keep order, ties, zero and
+    sign -- in the input's own layout -- and the float64 group sums of the original values come with them."""
+    import ctypes as Ct
+
+    import torch
+    from scipy import sparse
+
+    from illico_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.RandomState(0)
+    n, N, G = 3000, 9, 7
+    X = np.round(rng.randn(n, N) * 3, 1)
+    X[rng.rand(n, N) < 0.4] = 0.0
+    X[:, 1] = np.abs(X[:, 1]) + 1.0          # no zeros, all positive
+    X[:, 2] = -np.abs(X[:, 2]) - 1.0         # all negative
+    X[:, 3] += 2.0**40 * (X[:, 3] > 0)       # beyond float32 resolution
+    X[:, 4] = 0.0                            # nothing stored
+    X[0, 5] = -0.0
+    X[:, 6] = rng.randn(n) * 1e-3            # all distinct
+    groups = rng.randint(0, G, n).astype(np.int32)
+    lb, ub = 1, 8                            # a window of the genes
+    b = ub - lb
+    dev = torch.device("cuda", 0)
+    enc = torch.from_numpy(groups).to(dev)
+    sums = torch.empty((G, b), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    if fmt == "dense":
+        d = torch.from_numpy(X).to(dev)
+        codes = torch.empty((n, b), dtype=torch.float32, device=dev)
+        ws = torch.empty(int(lib.illico_recode_workspace_bytes(n * b, b)), dtype=torch.uint8, device=dev)
+        rc = lib.illico_recode_dense(d.data_ptr(), _lib.DTYPE_F64, N, lb, b, n, enc.data_ptr(), G, 0, codes.data_ptr(), sums.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), st)
+        _lib.check(rc, "illico_recode_dense")
+        got = codes.cpu().numpy()
+    else:
+        S = (sparse.csr_matrix if fmt == "csr" else sparse.csc_matrix)(X)
+        S.sort_indices()
+        data = torch.from_numpy(S.data.astype(np.float64)).to(dev)
+        idx = torch.from_numpy(S.indices.astype(np.int32)).to(dev)
+        ptr = torch.from_numpy(S.indptr.astype(np.int64)).to(dev)
+        codes = torch.zeros(S.nnz, dtype=torch.float32, device=dev)
+        keys = n * b if fmt == "csr" else int(S.indptr[ub] - S.indptr[lb])
+        ws = torch.empty(int(lib.illico_recode_workspace_bytes(keys, b)), dtype=torch.uint8, device=dev)
+        if fmt == "csr":
+            rc = lib.illico_recode_csr(data.data_ptr(), _lib.DTYPE_F64, idx.data_ptr(), ptr.data_ptr(), n, lb, b, enc.data_ptr(), G, 0,
+                                       codes.data_ptr(), sums.data_ptr(), ws.data_ptr(), ws.numel(), st)
+        else:
+            rc = lib.illico_recode_csc(data.data_ptr(), _lib.DTYPE_F64, idx.data_ptr(), ptr.data_ptr(), lb, b, keys, enc.data_ptr(), G, 0,
+                                       codes.data_ptr(), sums.data_ptr(), ws.data_ptr(), ws.numel(), st)
+        _lib.check(rc, f"illico_recode_{fmt}")
+        C_ = (sparse.csr_matrix if fmt == "csr" else sparse.csc_matrix)((codes.cpu().numpy(), S.indices, S.indptr), shape=S.shape)
+        got = np.asarray(C_[:, lb:ub].todense(), dtype=np.float32)
+    torch.cuda.synchronize()
+    assert got.dtype == np.float32 and Ct is not None
+    for j in range(b):
+        x, c = X[:, lb + j], got[:, j]
+        assert np.array_equal(np.sign(c), np.sign(x)), j
+        order = np.argsort(x, kind="stable")
+        assert np.all(np.diff(c[order]) >= 0), j
+        assert np.array_equal(np.diff(c[order]) == 0, np.diff(x[order]) == 0), j
+    want = np.zeros((G, b))
+    np.add.at(want, groups, X[:, lb:ub])
+    np.testing.assert_allclose(sums.cpu().numpy(), want, rtol=1e-12, atol=1e-9)

@@ -183,29 +183,6 @@ def test_bench_reference_arm_runs_on_cpu():
     assert line["e2e"]["h2d_bytes_per_step"] == 0
 
 
-def test_order_preserving_recoding_on_cpu():
-    """float64 / big-integer input: per-column codes keep order, ties, zero and sign (torch plumbing, CPU here)."""
-    import torch
-
-    from illico_b200.engine import recode_order_preserving
-
-    rng = np.random.RandomState(0)
-    X = np.round(rng.randn(500, 7) * 3, 1)
-    X[rng.rand(500, 7) < 0.3] = 0.0
-    X[:, 1] = np.abs(X[:, 1]) + 1.0          # no zeros, all positive
-    X[:, 2] = -np.abs(X[:, 2]) - 1.0         # all negative
-    X[:, 3] += 2.0**40 * (X[:, 3] > 0)       # beyond float32 resolution
-    X[0, 4] = -0.0
-    codes = recode_order_preserving(torch.from_numpy(X)).numpy()
-    assert codes.dtype == np.float32
-    for j in range(X.shape[1]):
-        x, c = X[:, j], codes[:, j]
-        assert np.array_equal(np.sign(c), np.sign(x))
-        order = np.argsort(x, kind="stable")
-        assert np.all(np.diff(c[order]) >= 0)
-        assert np.array_equal(np.diff(c[order]) == 0, np.diff(x[order]) == 0)
-
-
 def test_categorical_labels_encode_like_strings():
     """AnnData obs columns are categorical: the fast path gives the same groups / codes as the string path,
     drops unused categories and keeps np.unique's order even when the categories are not sorted."""
