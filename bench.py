@@ -39,6 +39,11 @@ WORKLOADS = {
     "dense_ovo_continuous": dict(fmt="dense", test="ovo", data="continuous",
                                  what="K562-shape dense OVO, log1p of library-normalised counts (no ties among non-zeros)"),
     "dense_ovr_continuous": dict(fmt="dense", test="ovr", data="continuous", what="K562-shape dense OVR, continuous values"),
+    "dense_ovo_unique": dict(fmt="dense", test="ovo", data="unique",
+                             what="K562-shape dense OVO, log1p of counts normalised by library sizes spread over a decade "
+                                  "(every non-zero value of a gene distinct)"),
+    "dense_ovr_unique": dict(fmt="dense", test="ovr", data="unique",
+                             what="K562-shape dense OVR, every non-zero value of a gene distinct"),
     "csr_ovo_continuous": dict(fmt="csr", test="ovo", data="continuous", what="K562-shape CSR OVO, continuous values"),
     "dense_ovo_highcount": dict(fmt="dense", test="ovo", data="highcount",
                                 what="K562-shape dense OVO, 20 % of the genes (scattered) dense Poisson(30) counts"),
@@ -50,8 +55,8 @@ WORKLOADS = {
     "c5_shard": dict(fmt="csr", test="ovo", data="counts", cells=2_000_000, genes=2_500, perts=10_000,
                      what="configs[4]: one GPU's gene shard (20000 / 8 genes) of the 2M-cell CSR, 10000 perturbations OVO"),
 }
-OTHERS_DEFAULT = ["dense_ovr", "csr_ovo", "csr_ovr", "dense_ovo_continuous", "dense_ovr_continuous", "dense_ovo_highcount",
-                  "dense_ovo_lambda", "backed_csc_ovr", "c5_shard"]
+OTHERS_DEFAULT = ["dense_ovr", "csr_ovo", "csr_ovr", "dense_ovo_continuous", "dense_ovr_continuous", "dense_ovo_unique",
+                  "dense_ovr_unique", "dense_ovo_highcount", "dense_ovo_lambda", "backed_csc_ovr", "c5_shard"]
 
 
 def parse():
@@ -191,10 +196,13 @@ def gen_dense(kind, seed, cells, genes, dev):
         for r0 in range(0, cells, 16384):
             blk = X[r0:r0 + 16384]
             blk[:, gsel] = torch.poisson(torch.full((blk.shape[0], gsel.numel()), 30.0, device=dev))
-    elif kind == "continuous":
+    elif kind in ("continuous", "unique"):
+        g = torch.Generator(device=dev).manual_seed(11)
         for r0 in range(0, cells, 16384):   # in place, chunked: log1p(x / library size * 1e4)
             blk = X[r0:r0 + 16384]
             lib = blk.sum(dim=1, keepdim=True) + 1.0
+            if kind == "unique":            # library sizes spread over a decade, as in real data: (almost) every value is unique
+                lib = lib * torch.exp(2.3 * torch.rand(lib.shape, device=dev, generator=g))
             blk.copy_(torch.log1p(blk / lib * 1.0e4))
     return X
 

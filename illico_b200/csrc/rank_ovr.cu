@@ -56,13 +56,15 @@ struct OvrParams {
     int* todo_count;
     uint4* table_rec;          // table kernel: per-CTA [n_segments][2] segment records (NULL: second pass re-reads the values)
     long long table_rec_stride;  // uint4 per CTA
+    int bucket_index;          // 1 = ranks of path S go through a bucket index of the sorted keys
+    int hash_max;              // most distinct values path H takes (<= MAX_DISTINCT); more: path S
 };
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key) { return (key * 2654435761u) >> 20; }  // 12 bits
 
 __device__ __forceinline__ void hash_insert(uint32_t* hkeys, uint32_t* hvals, int* ndist, int* overflow, uint32_t key,
-                                            uint32_t c) {
-    if (*(volatile int*)ndist >= MAX_DISTINCT) { *overflow = 1; return; }
+                                            uint32_t c, int max_distinct) {
+    if (*(volatile int*)ndist >= max_distinct) { *overflow = 1; return; }
     uint32_t h = hash_slot(key);
     for (;;) {
         uint32_t prev = atomicCAS(&hkeys[h], HASH_EMPTY, key);
@@ -123,7 +125,9 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
 
         long long nnz = 0, n0 = 0, n_neg = 0;
         unsigned long long tie_nz_exact = 0;
-        bool path_s = false;
+        bool path_s = false, bk_on = false;
+        uint32_t bk_kmin = 0;
+        int bk_shift = 0, bk_last = 0;
         const uint32_t* sk = nullptr;  // sorted keys (path S)
         {
         // ================= phase A: value -> multiplicity hash (path H attempt) =================
@@ -136,6 +140,9 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
             const int c = (s < S) ? (int)cnt[s] : 0;
             my_nnz += c;
             const float* src = vals + ((s < S) ? pl.seg_base[s] : 0);
+            // continuous data overflows the table within the first segments: from then on only the counts are needed
+            // (warp-uniform decision: the loop below votes)
+            if (__any_sync(FULL, *(volatile int*)&sc[1] != 0)) continue;
             int maxc = c;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(FULL, maxc, o));
@@ -152,13 +159,13 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
                     if (act && key == HASH_EMPTY) key = 1u;  // only a NaN payload maps here
                     const unsigned peers = __match_any_sync(FULL, key);
                     if (act && lane == __ffs(peers) - 1 && !*(volatile int*)&sc[1])
-                        hash_insert(hkeys, hvals, &sc[0], &sc[1], key, __popc(peers));
+                        hash_insert(hkeys, hvals, &sc[0], &sc[1], key, __popc(peers), P.hash_max);
                 }
             }
         }
         nnz = (long long)block_sum<unsigned long long>(my_nnz, redu);  // syncs
         n0 = n - nnz;
-        path_s = sc[1] != 0 || sc[0] > MAX_DISTINCT;
+        path_s = sc[1] != 0 || sc[0] > P.hash_max;
         __syncthreads();
 
         if (!path_s) {
@@ -228,6 +235,7 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
             }
             __syncthreads();
         } else {
+            {
             // ---- path S: gather keys, sort, scan runs
             const bool in_smem = nnz <= P.sort_cap;
             uint32_t* A = in_smem ? sortA : gsortA;
@@ -242,39 +250,88 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
             __syncthreads();
             sk = block_radix_sort(A, B, (int)nnz, hist, aux);
             n_neg = lower_bound_u32(sk, (int)nnz, KEY_ZERO);
+            // ---- bucket index of the sorted keys (they sit in the global slab: region0 is free): the key range is cut
+            // into equal buckets, bk[b] = first position of bucket b or later, so a rank reads its bucket's bounds from
+            // shared memory and halves a few times in L2 instead of 15 times
+            bk_on = !in_smem && nnz > 1 && nnz < 65536 && P.bucket_index;
+            if (bk_on) {
+                uint16_t* bk = reinterpret_cast<uint16_t*>(smem);
+                const int cap = 4 * HASH_CAP - 2;                                   // u16 entries in region0, one spare
+                const uint32_t kmin = sk[0], span = sk[nnz - 1] - kmin;
+                int shift = 0;
+                while ((span >> shift) > (uint32_t)(cap - 2)) ++shift;
+                const int NB = (int)(span >> shift) + 1;
+                for (int i = tid; i < (int)nnz; i += OVR_THREADS) {
+                    const int bi = (int)((sk[i] - kmin) >> shift);
+                    const int bp = i ? (int)((sk[i - 1] - kmin) >> shift) : -1;
+                    for (int bb = bp + 1; bb <= bi; ++bb) bk[bb] = (uint16_t)i;
+                    if (i == (int)nnz - 1) for (int bb = bi + 1; bb <= NB; ++bb) bk[bb] = (uint16_t)nnz;
+                }
+                bk_kmin = kmin; bk_shift = shift; bk_last = NB - 1;
+                __syncthreads();
+            }
             unsigned long long t_exact = 0;
             for (int i = tid; i < (int)nnz; i += OVR_THREADS) {
                 const uint32_t k = sk[i];
-                if (i == 0 || sk[i - 1] != k) t_exact += (unsigned long long)cube_minus(upper_bound_u32(sk, (int)nnz, k) - i);
+                if ((i == 0 || sk[i - 1] != k) && i + 1 < (int)nnz && sk[i + 1] == k)      // (a run of one adds nothing)
+                    t_exact += (unsigned long long)cube_minus(upper_bound_u32(sk, (int)nnz, k) - i);
             }
             tie_nz_exact = block_sum<unsigned long long>(t_exact, redu);
             const unsigned long long zterm = (unsigned long long)cube_minus(n0);
             const bool sparse_order = P.flags.tie_order == ILLICO_TIES_SPARSE;
             const bool need_walk = sparse_order ? ((double)tie_nz_exact >= TWO53)
                                                 : ((double)tie_nz_exact + (double)zterm >= TWO53);
+            // The reference adds the runs' terms one by one in ascending value order (the zero block where the values cross
+            // zero, or last for the sparse kernels): once the partial sum passes 2^53 that order decides the bits.  Only runs
+            // of two or more equal values contribute, so their terms are compacted, in order, into the sort's free buffer
+            // by the whole CTA and one thread adds up that (for continuous data empty) list -- not the 30 000 sorted keys.
+            int n_terms = 0, n_terms_neg = 0;
+            if (need_walk && tie_nz_exact != 0) {
+                unsigned long long* terms = reinterpret_cast<unsigned long long*>(const_cast<uint32_t*>(sk == A ? B : A));
+                const int w = tid >> 5;
+                const unsigned lt = (1u << lane) - 1u;
+                for (int i0 = 0; i0 < (int)nnz; i0 += OVR_THREADS) {
+                    const int i = i0 + tid;
+                    bool head = false;
+                    uint32_t k = 0;
+                    if (i < (int)nnz) {
+                        k = sk[i];
+                        head = (i == 0 || sk[i - 1] != k) && i + 1 < (int)nnz && sk[i + 1] == k;
+                    }
+                    const unsigned bal = __ballot_sync(FULL, head), bal_neg = __ballot_sync(FULL, head && i < (int)n_neg);
+                    if (lane == 0) { hist[w] = (uint32_t)__popc(bal); hist[OVR_NW + w] = (uint32_t)__popc(bal_neg); }
+                    __syncthreads();
+                    int before = 0, total = 0, total_neg = 0;
+                    for (int ww = 0; ww < OVR_NW; ++ww) {
+                        const int c = (int)hist[ww];
+                        if (ww < w) before += c;
+                        total += c;
+                        total_neg += (int)hist[OVR_NW + ww];
+                    }
+                    if (head) terms[n_terms + before + __popc(bal & lt)] = (unsigned long long)cube_minus((long long)(upper_bound_u32(sk, (int)nnz, k) - i));
+                    n_terms += total;
+                    n_terms_neg += total_neg;
+                    __syncthreads();
+                }
+            }
             if (tid == 0) {
                 double acc;
                 if (!need_walk) {
                     acc = sparse_order ? (double)tie_nz_exact : (double)(tie_nz_exact + zterm);
                 } else {
+                    const unsigned long long* terms = reinterpret_cast<const unsigned long long*>(sk == A ? B : A);
                     acc = 0.0;
                     bool zero_done = sparse_order || n0 == 0;
-                    int i = 0;
-                    const int m = (int)nnz;
-                    while (i < m) {
-                        const uint32_t k = sk[i];
-                        int r = i + 1;
-                        while (r < m && sk[r] == k) ++r;
-                        if (!zero_done && k > KEY_ZERO) { acc += (double)(long long)zterm; zero_done = true; }
-                        if (r - i > 1) acc += (double)cube_minus((long long)(r - i));
-                        i = r;
-                    }
+                    for (int t = 0; t < n_terms_neg; ++t) acc += (double)(long long)terms[t];
+                    if (!zero_done && (long long)n_neg < nnz) { acc += (double)(long long)zterm; zero_done = true; }   // a positive value follows
+                    for (int t = n_terms_neg; t < n_terms; ++t) acc += (double)(long long)terms[t];
                     if (!zero_done) acc += (double)(long long)zterm;
                 }
                 if (sparse_order) acc = __dadd_rn(acc, zero_block_term_f64(n0));
                 *tie_slot = acc;
             }
             __syncthreads();
+            }
         }
         }
         const double tie = *tie_slot;
@@ -301,7 +358,19 @@ __global__ void __launch_bounds__(OVR_THREADS, 2) ovr_kernel(const OvrParams P) 
                         if (!path_s) {
                             acc += hvals[hash_find(hkeys, key)];
                         } else {
-                            const int lo = lower_bound_u32(sk, (int)nnz, key), hi = upper_bound_u32(sk, (int)nnz, key);
+                            int lo, hi;
+                            if (bk_on) {
+                                const uint16_t* bk = reinterpret_cast<const uint16_t*>(smem);
+                                const uint32_t bq = min((key - bk_kmin) >> bk_shift, (uint32_t)bk_last);   // (key is one of the sorted keys)
+                                lo = bk[bq];
+                                int e = bk[bq + 1];
+                                while (lo < e) { const int mid = (lo + e) >> 1; if (sk[mid] < key) lo = mid + 1; else e = mid; }
+                            } else {
+                                lo = lower_bound_u32(sk, (int)nnz, key);
+                            }
+                            // the run of the key: continuous values are alone in theirs
+                            hi = lo + 1;
+                            if (hi < (int)nnz && sk[hi] == key) hi = upper_bound_u32(sk, (int)nnz, key);
                             acc += (unsigned long long)lo + hi + 1 + ((key > KEY_ZERO) ? 2ull * (unsigned long long)n0 : 0ull);
                         }
                         sum += fc_value(v, P.flags.is_log1p);
@@ -649,6 +718,10 @@ int launch_ovr_mapped(const float* ir_vals, const uint32_t* ir_cnt, int n_genes,
     P.n_genes_dev = n_genes_dev; P.gene_map = gene_map; P.n_cols = n_cols;
     P.dbg_u2 = dbg ? (long long*)dbg->u2 : nullptr; P.dbg_tie = dbg ? dbg->tie_sum : nullptr;
     P.dbg_tie_exact = dbg ? (long long*)dbg->tie_exact : nullptr;
+    { const char* benv = getenv("ILLICO_OVR_BUCKETS"); P.bucket_index = benv ? atoi(benv) : 1; }
+    { const char* henv = getenv("ILLICO_OVR_HASH_MAX"); P.hash_max = henv ? atoi(henv) : MAX_DISTINCT; }
+    if (P.hash_max > MAX_DISTINCT) P.hash_max = MAX_DISTINCT;
+    if (P.hash_max < 1) P.hash_max = 1;
 
     // two CTAs per SM: ~113 KB each.  Fixed part: histogram / distinct table 16 KB + scalars.
     const size_t fixed = (size_t)(OVR_NW * 256 + RADIX_AUX_WORDS + 8) * 4 + 32 * 8 * 2 + 8 + 64;

@@ -30,10 +30,14 @@ static __device__ __noinline__ KeyT* block_radix_sort_t(KeyT* a, KeyT* b, int n,
         if (tid == 0) aux[32] = 0;
         __syncthreads();
         // ---- per-warp digit counts (warp-private counters: match_any aggregates equal digits)
+        // (the next 32 keys are requested before the current ones are counted: the loop is one dependent load per round)
+        KeyT nxt = (beg + lane < end) ? a[beg + lane] : KeyT(0);
         for (int i0 = beg; i0 < end; i0 += 32) {
             int i = i0 + lane;
             bool valid = i < end;
-            uint32_t d = valid ? ((uint32_t)(a[i] >> shift) & 255u) : (256u + lane);
+            const KeyT cur = nxt;
+            if (i + 32 < end) nxt = a[i + 32];
+            uint32_t d = valid ? ((uint32_t)(cur >> shift) & 255u) : (256u + lane);
             unsigned peers = __match_any_sync(FULL, d);
             if (valid && lane == __ffs(peers) - 1) myhist[d] += __popc(peers);
             __syncwarp();
@@ -62,10 +66,12 @@ static __device__ __noinline__ KeyT* block_radix_sort_t(KeyT* a, KeyT* b, int n,
         }
         __syncthreads();
         // ---- stable scatter: each warp walks its chunk in order
+        nxt = (beg + lane < end) ? a[beg + lane] : KeyT(0);
         for (int i0 = beg; i0 < end; i0 += 32) {
             int i = i0 + lane;
             bool valid = i < end;
-            KeyT key = valid ? a[i] : KeyT(0);
+            const KeyT key = nxt;
+            if (i + 32 < end) nxt = a[i + 32];
             uint32_t d = valid ? ((uint32_t)(key >> shift) & 255u) : (256u + lane);
             unsigned peers = __match_any_sync(FULL, d);
             uint32_t pos = valid ? myhist[d] + __popc(peers & lt) : 0u;
