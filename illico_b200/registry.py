@@ -57,6 +57,13 @@ class DataHandlerRegistry(dict):
         for klass in type(key).__mro__:
             if klass in self:
                 return self[klass](key)
+        # device arrays of other libraries (CuPy ndarray, numba device arrays, ...): anything that exposes the CUDA array
+        # interface is viewed as a torch tensor in place -- no copy, no host round trip
+        if hasattr(key, "__cuda_array_interface__"):
+            import torch
+
+            if torch.Tensor in self:
+                return self[torch.Tensor](torch.as_tensor(key, device="cuda"))
         raise KeyError(f"Support for data type {type(key)} is not implemented.")
 
 

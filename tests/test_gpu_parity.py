@@ -591,6 +591,28 @@ def test_fused_gate_falls_back_when_many_genes_are_handed_back(monkeypatch, fmt)
     assert_parity(got, (p, U, fc), ref_row=int(np.searchsorted(groups, ref)), what=f"gate {fmt}")
 
 
+def test_cuda_array_interface_input():
+    """A device array of another library (CuPy, numba): anything exposing ``__cuda_array_interface__`` is ranked in
+    place, like a CUDA tensor.  CuPy is not in this image: a minimal stand-in carries the
+    interface of a CUDA buffer."""
+    import torch
+
+    from illico_b200 import synth
+
+    X, labels = synth.k562_like(seed=12, n_cells=3000, n_genes=40, n_perts=8)
+    dev = torch.from_numpy(X).cuda()
+
+    class DeviceArray:                      # what cupy.ndarray looks like from outside
+        def __init__(self, t):
+            self._keep = t
+            self.shape = tuple(t.shape)
+            self.__cuda_array_interface__ = t.__cuda_array_interface__
+
+    groups, got = _run(DeviceArray(dev), labels, synth.CONTROL, is_log1p=False)
+    g, p, U, fc = oracle.run(X, labels, synth.CONTROL, is_log1p=False)
+    assert_parity(got, (p, U, fc), ref_row=int(np.searchsorted(groups, synth.CONTROL)), what="cuda array interface")
+
+
 def test_device_resident_torch_input():
     """a CUDA tensor is used where it is (no host round trip); same answer as the ndarray path."""
     import torch
