@@ -420,8 +420,11 @@ class Workload:
 
         from illico_b200 import asymptotic_wilcoxon
 
+        from illico_b200 import hostio
+
         ad = Ad(Xh, self.labels, self.genes)
         times = []
+        hostio.LAST_UPLOAD.clear()
         for i in range(warm + reps):
             self.barrier()
             t0 = time.perf_counter()
@@ -432,14 +435,24 @@ class Workload:
             if i >= warm:
                 times.append(dt)
             del out
+        upload = None
+        if hostio.LAST_UPLOAD:      # the dense matrix went up packed (hostio._h2d_2d_packed): bytes that crossed the link
+            st = dict(hostio.LAST_UPLOAD)
+            upload = {"mode": "packed on the host (bit mask + non-zero values), rebuilt in HBM", "host_matrix_bytes": int(h2d),
+                      "chunks_packed": int(st.get("packed", 0)), "chunks_sent_as_they_are": int(st.get("raw", 0)),
+                      "host_threads": hostio.pack_threads()}
+            h2d = st.get("bytes", h2d)
         tt = torch.tensor([float(np.median(times))], dtype=torch.float64, device=self.dev)
         if self.world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         s = float(tt.item())
-        return {"value": round(self.n_tests * self.world / s, 1), "unit": "tests/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(self.G * self.genes * 24), "s_per_step": round(s, 4),
-                "returns": "DataFrame" if frame else "result array (return_array=True)",
-                "timing": f"median of {reps} calls after {warm} warm-ups, max over ranks"}
+        out = {"value": round(self.n_tests * self.world / s, 1), "unit": "tests/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(self.G * self.genes * 24), "s_per_step": round(s, 4),
+               "returns": "DataFrame" if frame else "result array (return_array=True)",
+               "timing": f"median of {reps} calls after {warm} warm-ups, max over ranks"}
+        if upload:
+            out["upload"] = upload
+        return out
 
     def backed_e2e(self, reps=3, warm=1):
         """configs[3]: the matrix lives on disk as a CSC triplet (np.memmap behind the `[:, lb:ub]` protocol; h5py /

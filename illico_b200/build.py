@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libillico_b200.so")
-SOURCES = ["api.cu", "stage.cu", "stage_dense_tma.cu", "fused.cu", "rank_ovr.cu", "rank_ovo.cu", "extras.cu", "repart.cu", "recode.cu"]
+SOURCES = ["api.cu", "stage.cu", "stage_dense_tma.cu", "fused.cu", "rank_ovr.cu", "rank_ovo.cu", "extras.cu", "repart.cu", "recode.cu", "hostpack.c"]
 HEADERS = ["common.cuh", "sort.cuh", "epilogue.cuh", "tma.cuh", os.path.join("..", "..", "include", "illico_b200.h")]
 
 NVCC_FLAGS = [
@@ -47,14 +47,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     flags = [f for f in NVCC_FLAGS if f != "-shared"]
 
     def compile_one(src):
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, src.replace(".cu", ".o").replace(".c", ".o"))
         path = os.path.join(CSRC, src)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), hdr_time):
             return obj, ""
-        cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        if src.endswith(".c"):      # host-only code (the packed upload's squeeze loop): plain gcc
+            cmd = [shutil.which("gcc") or "gcc", "-O3", "-fPIC", "-c", path, "-o", obj]
+        else:
+            cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            raise RuntimeError("compiler failed:\n" + res.stdout + res.stderr)
         return obj, res.stderr
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:

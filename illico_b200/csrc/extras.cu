@@ -83,6 +83,36 @@ __global__ void compute_pval_batch_kernel(const long long* n_ref, const long lon
     if (i < count) out[i] = compute_pval(n_ref[i], n_tgt[i], n[i], tie[i], U[i], mu[i], cc[i], alt[i]);
 }
 
+// ---- packed upload: rebuilds dense float32 rows from (bit mask, values) -- see csrc/hostpack.c
+// Warp per row.  The lanes fetch 32 mask words at a time (coalesced), then word by word: lane k is element k of the
+// word, its value sits at the row's running offset + the number of set bits below it; one coalesced 128-byte store per
+// word, zeros included (the destination is written exactly once, nothing has to be cleared first).
+__global__ void __launch_bounds__(256) unpack_rows_kernel(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ row_off,
+                                                          const float* __restrict__ vals, long long n_rows, int n_cols,
+                                                          float* __restrict__ dst, long long ld) {
+    const int lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int W = (n_cols + 31) >> 5;
+    for (long long r = warp; r < n_rows; r += nwarps) {
+        const uint32_t* m = mask + r * W;
+        uint32_t base = row_off[r];
+        float* out = dst + r * ld;
+        for (int w0 = 0; w0 < W; w0 += 32) {
+            const uint32_t mine = (w0 + lane < W) ? m[w0 + lane] : 0u;
+            const int nw = min(32, W - w0);
+            for (int k = 0; k < nw; ++k) {
+                const uint32_t word = __shfl_sync(FULL, mine, k);
+                const int c = ((w0 + k) << 5) + lane;
+                float v = 0.0f;
+                if ((word >> lane) & 1u) v = __ldcs(vals + base + __popc(word & below));
+                if (c < n_cols) out[c] = v;
+                base += __popc(word);
+            }
+        }
+    }
+}
+
 }  // namespace
 }  // namespace illico
 
@@ -120,6 +150,18 @@ int illico_compute_pval_batch(const int64_t* n_ref, const int64_t* n_tgt, const 
                   compute_pval_batch_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(
                       (const long long*)n_ref, (const long long*)n_tgt, (const long long*)n, tie_sum, U, mu, contin_corr, alternative,
                       out, (long long)count));
+    ILLICO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int illico_unpack_rows_f32(const uint32_t* mask, const uint32_t* row_off, const float* vals, int64_t n_rows, int32_t n_cols, float* dst,
+                           int64_t dst_ld, void* stream) {
+    if (n_rows <= 0 || n_cols <= 0) return 0;
+    if (!mask || !row_off || !vals || !dst || dst_ld < n_cols) { set_error("illico_unpack_rows_f32: bad argument"); return 1; }
+    long long blocks = (n_rows + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ILLICO_LAUNCH("unpack_rows_kernel", (cudaStream_t)stream,
+                  unpack_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, row_off, vals, n_rows, n_cols, dst, dst_ld));
     ILLICO_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -265,6 +265,21 @@ int illico_csr_shard_scatter(const float* data, const int32_t* indices, const in
                              const int32_t* bounds, int32_t n_shards, const int32_t* cnt, const int64_t* out_pos,
                              float* const* out_data, int32_t* const* out_indices, int32_t* const* out_row_cnt, void* stream);
 
+/* ---- packed upload of a dense float32 matrix (host input; replaces the zero-copy InRAMDataHandler.fetch of
+ * illico/utils/registry.py:97-100 at the device boundary) ---------------------------------------------------------------
+ * A dense expression matrix is mostly zeros and its upload is the end-to-end time.  The host threads that stage row chunks
+ * squeeze them (csrc/hostpack.c: plain C, AVX-512 / AVX2 / scalar code chosen at run time) into
+ *   mask [n_rows][(n_cols + 31) / 32] uint32 (bit k of word w: element 32 w + k is non-zero), row_off [n_rows + 1] uint32
+ *   (position of each row's first value), vals: the non-zero values row by row (capacity vals_cap floats, 8 of them slack);
+ * the packed chunk crosses PCIe and the device call rebuilds the dense rows in HBM (every element written once, zeros
+ * included).  All pointers of the host call are HOST pointers; it returns the number of values, or -1 when they do not fit
+ * (the caller then sends the chunk as it is).  The isa call returns 2 / 1 / 0 = AVX-512 / AVX2 / scalar. */
+long illico_host_pack_rows_f32(const float* src, long row_stride, long n_rows, long n_cols, uint32_t* mask, uint32_t* row_off,
+                               float* vals, long vals_cap);
+int illico_host_pack_isa(void);
+int illico_unpack_rows_f32(const uint32_t* mask, const uint32_t* row_off, const float* vals, int64_t n_rows, int32_t n_cols,
+                           float* dst, int64_t dst_ld, void* stream);
+
 /* ---- next to the path and a test hook ------------------------------------------- */
 
 /* Benjamini-Hochberg adjusted p-values over the genes of each group (statsmodels multipletests(method="fdr_bh") /

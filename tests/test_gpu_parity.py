@@ -999,3 +999,48 @@ def test_native_recoding_of_float64_values(fmt):
     want = np.zeros((G, b))
     np.add.at(want, groups, X[:, lb:ub])
     np.testing.assert_allclose(sums.cpu().numpy(), want, rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("source", ["pageable", "pinned", "shard", "mixed"])
+def test_packed_upload_rebuilds_the_matrix(monkeypatch, source):
+    """hostio._h2d_2d_packed (csrc/hostpack.c + unpack_rows_kernel): a mostly-zero float32 matrix squeezed on the host
+    (bit mask + values), sent packed and rebuilt in HBM is the matrix, bit for bit -- NaN kept, -0.0 a zero; pinned
+    sources (with the plain-DMA worker taking chunks off the same queue), column shards of a wider matrix, and chunks too
+    dense to squeeze (sent as they are)."""
+    import torch
+
+    from illico_b200 import hostio
+
+    monkeypatch.setenv("ILLICO_STAGE_CHUNK_MB", "4")
+    monkeypatch.setattr(hostio, "CHUNK_BYTES", 4 << 20)
+    monkeypatch.setenv("ILLICO_PACK_UPLOAD", "1")
+    rng = np.random.RandomState(4)
+    n, N = 9000, 2117
+    X = (rng.poisson(1.0, (n, N)) * (rng.rand(n, N) < 0.12)).astype(np.float32)
+    X[5, 7] = -0.0
+    X[6, 8] = np.nan
+    X[:, -1] = 3.0
+    if source == "mixed":
+        X[2000:4500] = rng.rand(2500, N).astype(np.float32) + 1.0        # chunks that do not squeeze
+    if source == "pinned":
+        hp = torch.empty((n, N), dtype=torch.float32, pin_memory=True)
+        hp.copy_(torch.from_numpy(X))
+        src = hp.numpy()
+    elif source == "shard":
+        src = X[:, 100:2050]
+    else:
+        src = X
+    dev = torch.device("cuda", 0)
+    dst = torch.full(src.shape, 7.0, dtype=torch.float32, device=dev)
+    hostio.h2d_2d(dst, src).finish()
+    torch.cuda.synchronize()
+    got = dst.cpu().numpy()
+    want = np.where(src == 0, np.float32(0.0), src)                       # (-0.0 arrives as +0.0)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    st = hostio.LAST_UPLOAD
+    assert st["packed"] + st["raw"] == -(-n // ((4 << 20) // (src.shape[1] * 4)))
+    if source == "mixed":
+        assert st["raw"] >= 2
+    if source in ("pageable", "shard"):
+        assert st["raw"] == 0 and st["bytes"] < 0.35 * src.size * 4
