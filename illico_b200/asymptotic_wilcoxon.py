@@ -212,6 +212,7 @@ def asymptotic_wilcoxon(
             sh.error = e
 
     workers = []
+    hostio.CONCURRENT_UPLOADS = len(shards)
     if len(shards) > 1:
         workers = [threading.Thread(target=run_shard, args=(sh,), daemon=True) for sh in shards]
         for t in workers:

@@ -26,6 +26,7 @@ from . import _lib
 CHUNK_BYTES = int(os.environ.get("ILLICO_STAGE_CHUNK_MB", "32")) << 20
 _rings: dict = {}
 _rings_lock = threading.Lock()
+CONCURRENT_UPLOADS = 1     # GPUs this process is feeding at once (asymptotic_wilcoxon(devices=...) sets it): the cores are shared
 LAST_UPLOAD: dict = {}     # the last packed upload: chunks squeezed / sent as they are, bytes that crossed the link
 
 
@@ -43,7 +44,7 @@ def pack_threads() -> int:
     env = os.environ.get("ILLICO_STAGE_THREADS")
     if env:
         return max(1, int(env))
-    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1) * max(1, CONCURRENT_UPLOADS)
     return max(1, min(32, ((os.cpu_count() or 8) - 2) // max(1, local_world)))
 
 
@@ -274,9 +275,8 @@ def _h2d_2d_packed(dst: torch.Tensor, src: np.ndarray, pinned_src: bool, n_threa
     """The upload of a mostly-zero float32 matrix with the host threads squeezing the row chunks (bit mask + non-zero
     values, ``illico_host_pack_rows_f32``) instead of copying them: the packed chunk crosses PCIe (about 1/8 of the bytes
     at 10 % density) and ``illico_unpack_rows_f32`` rebuilds the rows in the destination.  The threads share one queue
-    of chunks.  When the source is pinned an extra worker takes chunks off the same queue and sends them as they are
-    (plain DMA, no CPU work), two in flight at a time -- so the link is never idle while the CPUs squeeze, and a slow
-    host only shifts the split."""
+    of chunks.  (``ILLICO_PACK_DMA_WORKER=1``: when the source is pinned an extra worker takes chunks off the same queue
+    and sends them as they are -- plain DMA, two in flight; measured slower, see below.)"""
     lib = _lib.load()
     device = dst.device
     n, b = src.shape
@@ -377,7 +377,10 @@ def _h2d_2d_packed(dst: torch.Tensor, src: np.ndarray, pinned_src: bool, n_threa
             pending.error = e
 
     threads = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(T)]
-    if pinned_src and os.environ.get("ILLICO_PACK_DMA_WORKER", "1") != "0":
+    # (off by default: measured on the K562 matrix, scripts/exp/pack_chunks.py, the squeeze threads slow down ten-fold
+    # while plain DMA out of the same pinned pages is running, and the DMA worker ends up with most chunks: 0.17 s
+    # against 0.10 s with the threads alone)
+    if pinned_src and os.environ.get("ILLICO_PACK_DMA_WORKER", "0") == "1":
         threads.append(threading.Thread(target=dma_worker, daemon=True))
     pending.threads, pending.events = threads, final_events
     for th in threads:

@@ -1015,6 +1015,7 @@ def test_packed_upload_rebuilds_the_matrix(monkeypatch, source):
     monkeypatch.setenv("ILLICO_STAGE_CHUNK_MB", "4")
     monkeypatch.setattr(hostio, "CHUNK_BYTES", 4 << 20)
     monkeypatch.setenv("ILLICO_PACK_UPLOAD", "1")
+    monkeypatch.setenv("ILLICO_PACK_DMA_WORKER", "1")
     rng = np.random.RandomState(4)
     n, N = 9000, 2117
     X = (rng.poisson(1.0, (n, N)) * (rng.rand(n, N) < 0.12)).astype(np.float32)
