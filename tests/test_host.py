@@ -296,3 +296,37 @@ def test_dispatch_cache_keys_follow_content_not_addresses():
     assert dispatch._fingerprint(big) != f
     assert dispatch._fingerprint(np.asfortranarray(X)) == dispatch._fingerprint(np.asfortranarray(X))
     assert isinstance(dispatch._fingerprint(X[::2, ::3]), int)   # non-contiguous views are sampled too
+
+
+def test_host_pack_rows_matches_numpy():
+    """csrc/hostpack.c (the host half of the packed upload; no GPU involved): bit masks, row offsets and the values in
+    order, for full and ragged widths, strided rows, NaN and -0.0, and the no-room answer."""
+    import ctypes as C
+
+    from illico_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.illico_host_pack_isa() in (0, 1, 2)
+    rng = np.random.RandomState(2)
+    for n, N, lo, hi in ((37, 96, 0, 96), (50, 203, 5, 198), (11, 64, 0, 33), (3, 40, 1, 2)):
+        X = (rng.poisson(1.0, (n, N)) * (rng.rand(n, N) < 0.3)).astype(np.float32)
+        X[0, lo] = -0.0
+        X[n - 1, hi - 1] = np.nan
+        view = X[:, lo:hi]
+        b = hi - lo
+        W = (b + 31) // 32
+        mask = np.full((n, W), 0xFFFFFFFF, dtype=np.uint32)
+        off = np.zeros(n + 1, dtype=np.uint32)
+        vals = np.full(n * b + 8, -1.0, dtype=np.float32)
+        nnz = lib.illico_host_pack_rows_f32(view.ctypes.data, N, n, b, mask.ctypes.data, off.ctypes.data, vals.ctypes.data, vals.size)
+        nz = view != 0
+        assert nnz == int(nz.sum())
+        bits = np.unpackbits(mask.view(np.uint8).reshape(n, -1), axis=1, bitorder="little")[:, :b].astype(bool)
+        assert np.array_equal(bits, nz)
+        assert np.array_equal(np.diff(off.astype(np.int64)), nz.sum(1))
+        assert np.array_equal(vals[:nnz].view(np.uint32), view[nz].view(np.uint32))
+        # padding bits of the last word stay clear
+        if b % 32:
+            assert not (mask[:, -1] >> np.uint32(b % 32)).any()
+        assert lib.illico_host_pack_rows_f32(view.ctypes.data, N, n, b, mask.ctypes.data, off.ctypes.data, vals.ctypes.data, b) == -1
+    assert C is not None
