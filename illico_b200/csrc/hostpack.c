@@ -35,9 +35,11 @@ __attribute__((target("avx512f"))) static void row_avx512(const float* row, long
     for (long c = 0; c < full; c += 32) {
         const __m512 a = _mm512_loadu_ps(row + c), b = _mm512_loadu_ps(row + c + 16);
         const __mmask16 ma = _mm512_cmp_ps_mask(a, zero, _CMP_NEQ_UQ), mb = _mm512_cmp_ps_mask(b, zero, _CMP_NEQ_UQ);
-        _mm512_mask_compressstoreu_ps(o, ma, a);
+        /* compress in a register, store all 16 lanes, advance by the count: the memory form of vcompressps is microcoded
+         * (very slow) on some CPUs; the caller leaves 16 floats of slack */
+        _mm512_storeu_ps(o, _mm512_maskz_compress_ps(ma, a));
         o += __builtin_popcount((unsigned)ma);
-        _mm512_mask_compressstoreu_ps(o, mb, b);
+        _mm512_storeu_ps(o, _mm512_maskz_compress_ps(mb, b));
         o += __builtin_popcount((unsigned)mb);
         mask[c >> 5] = (uint32_t)ma | ((uint32_t)mb << 16);
     }
@@ -88,7 +90,7 @@ int illico_host_pack_isa(void) {
 /* Packs rows [0, n_rows) of a row-major float32 matrix (row stride in elements, n_cols columns read per row):
  *   mask    [n_rows][W] uint32, W = (n_cols + 31) / 32: bit k of word w = element 32 w + k is non-zero
  *   row_off [n_rows + 1] uint32: position of each row's first value in vals
- *   vals    the non-zero values, row by row, in column order; capacity vals_cap floats (8 floats of slack included)
+ *   vals    the non-zero values, row by row, in column order; capacity vals_cap floats (16 floats of slack included)
  * Returns the number of values, or -1 when they do not fit (the caller then sends the chunk as it is). */
 long illico_host_pack_rows_f32(const float* src, long row_stride, long n_rows, long n_cols, uint32_t* mask, uint32_t* row_off,
                                float* vals, long vals_cap) {
@@ -97,7 +99,7 @@ long illico_host_pack_rows_f32(const float* src, long row_stride, long n_rows, l
     const long W = (n_cols + 31) / 32;
     float* o = vals;
     for (long r = 0; r < n_rows; ++r) {
-        if ((o - vals) + n_cols + 8 > vals_cap) return -1;
+        if ((o - vals) + n_cols + 16 > vals_cap) return -1;
         row_off[r] = (uint32_t)(o - vals);
         const float* row = src + r * row_stride;
         if (isa == 2) row_avx512(row, n_cols, mask + r * W, &o);

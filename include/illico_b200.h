@@ -270,7 +270,7 @@ int illico_csr_shard_scatter(const float* data, const int32_t* indices, const in
  * A dense expression matrix is mostly zeros and its upload is the end-to-end time.  The host threads that stage row chunks
  * squeeze them (csrc/hostpack.c: plain C, AVX-512 / AVX2 / scalar code chosen at run time) into
  *   mask [n_rows][(n_cols + 31) / 32] uint32 (bit k of word w: element 32 w + k is non-zero), row_off [n_rows + 1] uint32
- *   (position of each row's first value), vals: the non-zero values row by row (capacity vals_cap floats, 8 of them slack);
+ *   (position of each row's first value), vals: the non-zero values row by row (capacity vals_cap floats, 16 of them slack);
  * the packed chunk crosses PCIe and the device call rebuilds the dense rows in HBM (every element written once, zeros
  * included).  All pointers of the host call are HOST pointers; it returns the number of values, or -1 when they do not fit
  * (the caller then sends the chunk as it is).  The isa call returns 2 / 1 / 0 = AVX-512 / AVX2 / scalar. */

@@ -317,7 +317,7 @@ def test_host_pack_rows_matches_numpy():
         W = (b + 31) // 32
         mask = np.full((n, W), 0xFFFFFFFF, dtype=np.uint32)
         off = np.zeros(n + 1, dtype=np.uint32)
-        vals = np.full(n * b + 8, -1.0, dtype=np.float32)
+        vals = np.full(n * b + 16, -1.0, dtype=np.float32)
         nnz = lib.illico_host_pack_rows_f32(view.ctypes.data, N, n, b, mask.ctypes.data, off.ctypes.data, vals.ctypes.data, vals.size)
         nz = view != 0
         assert nnz == int(nz.sum())
