@@ -25,8 +25,13 @@
 //   3. a per-gene kernel turns the table into per-slot weights (OVO: 2 #{ref > v} + a; OVR: doubled mid-ranks, tie sum
 //      in the reference's accumulation order), and an epilogue kernel turns each 24-byte histogram into
 //      (p, U, fold change) in place, in the reference's f64 operation order (epilogue.cuh).
-// Genes that do not qualify (a 13th distinct value, negative values, NaN) are flagged and go through the general
-// stage + rank path afterwards, in merged runs; batches that are mostly such genes skip the fused path altogether.
+//   4. (round 2) one-versus-reference on raw counts: genes with up to DW = 64 distinct integer values take the WIDE table
+//      instead (fused_wide_pass_kernel: counters indexed by the value, folded against the control at the end of each
+//      group); which pass owns which gene is decided per tile of 256 genes by fused_mode_kernel.
+// Genes that fit neither table (continuous values, negative values, NaN) are flagged, listed ON THE DEVICE after the
+// epilogue (fused_list_kernel) and go through the general stage + rank path -- gene by gene when they are few, the whole
+// batch when they are many; nothing is read back to the host, every launch is enqueued unconditionally and the kernels
+// that find nothing to do leave at once.
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "tma.cuh"
