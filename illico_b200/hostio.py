@@ -352,7 +352,9 @@ def _h2d_2d_packed(dst: torch.Tensor, src: np.ndarray, pinned_src: bool, n_threa
                         ev.record(st)
                     ring.events[t][k] = ev
                     final_events[t] = ev
-                    k ^= 1
+                    # (one staging buffer per thread is enough here: the DMA of a packed chunk -- ~4 MB -- takes a
+                    # fortieth of the time the next squeeze does, and page-locking a second 32 MB buffer per thread
+                    # would double what the first call pays for the ring)
         except BaseException as e:  # surfaced by finish()
             pending.error = e
 
