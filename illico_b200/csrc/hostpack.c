@@ -13,6 +13,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#define PREFETCH_AHEAD 4096
+
 static void scalar_words(const float* row, long c0, long c1, uint32_t* mask, float** out) {
     /* columns [c0, c1) of one row, c0 a multiple of 32 */
     float* o = *out;
@@ -33,6 +35,10 @@ __attribute__((target("avx512f"))) static void row_avx512(const float* row, long
     const __m512 zero = _mm512_setzero_ps();
     const long full = n_cols & ~31L;
     for (long c = 0; c < full; c += 32) {
+        /* the scan is bound by how many cache lines a core keeps in flight: ask for the lines 4 KB ahead (they may belong
+         * to the next row -- rows of a chunk are adjacent or a fixed stride apart -- or lie past the end: harmless) */
+        _mm_prefetch((const char*)(row + c) + PREFETCH_AHEAD, _MM_HINT_T0);
+        _mm_prefetch((const char*)(row + c) + PREFETCH_AHEAD + 64, _MM_HINT_T0);
         const __m512 a = _mm512_loadu_ps(row + c), b = _mm512_loadu_ps(row + c + 16);
         const __mmask16 ma = _mm512_cmp_ps_mask(a, zero, _CMP_NEQ_UQ), mb = _mm512_cmp_ps_mask(b, zero, _CMP_NEQ_UQ);
         /* compress in a register, store all 16 lanes, advance by the count: the memory form of vcompressps is microcoded
@@ -65,6 +71,8 @@ __attribute__((target("avx2"))) static void row_avx2(const float* row, long n_co
     const long full = n_cols & ~31L;
     for (long c = 0; c < full; c += 32) {
         uint32_t m = 0;
+        _mm_prefetch((const char*)(row + c) + PREFETCH_AHEAD, _MM_HINT_T0);
+        _mm_prefetch((const char*)(row + c) + PREFETCH_AHEAD + 64, _MM_HINT_T0);
         for (int q = 0; q < 4; ++q) {
             const __m256 v = _mm256_loadu_ps(row + c + 8 * q);
             const int mm = _mm256_movemask_ps(_mm256_cmp_ps(v, zero, _CMP_NEQ_UQ));
