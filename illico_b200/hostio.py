@@ -1,7 +1,11 @@
 """Host <-> device transfers for host matrices (plumbing; the reference has no device boundary, this replaces its
 zero-copy ``InRAMDataHandler.fetch``, ``illico/utils/registry.py:97-100``).
 
-Three cases:
+Four cases:
+  * a large float32 matrix that is mostly zeros (what a dense ``adata.X`` is), in pageable memory -- or in pinned memory
+    when this host feeds a single GPU: the staging threads SQUEEZE the row chunks (bit mask + non-zero values,
+    ``illico_host_pack_rows_f32``) instead of copying them, an eighth of the bytes crosses PCIe and
+    ``illico_unpack_rows_f32`` rebuilds the rows in HBM (:func:`_h2d_2d_packed`);
   * pinned source (``torch.Tensor.pin_memory()`` behind the ndarray, or ``cudaHostRegister``-ed memory): one asynchronous
     ``cudaMemcpy2DAsync`` straight from the user's buffer -- also for a column shard ``X[:, lb:ub]`` of a C-order matrix
     (a strided source), which is how the genes are split across GPUs;
