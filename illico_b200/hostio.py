@@ -197,11 +197,12 @@ def h2d_2d(dst: torch.Tensor, src: np.ndarray, n_threads: int | None = None, all
     cur = torch.cuda.current_stream(device)
     row_bytes = b * item
     pinned_src = is_pinned(src)
-    # A pinned source is squeezed only when this host feeds ONE GPU: plain DMA needs no CPU at all and the links of
-    # several GPUs together (111 / 115 / 186 GB/s for 2 / 4 / 8 GPUs on the measured box) carry the raw matrix as fast
-    # as, or faster than, the cores can scan it (~100-130 GB/s); a pageable source has to be touched by the CPU anyway.
+    # A pinned source is squeezed while this host feeds at most FOUR GPUs: plain DMA needs no CPU at all, but the links
+    # of 2 / 4 GPUs together carry 111 / 115 GB/s on the measured box and its cores scan ~135 GB/s of raw matrix into an
+    # eighth of the bytes (two ranks, each its own K562 matrix: 0.201 -> 0.140 s; one matrix split over two: 0.093 ->
+    # 0.075 s); eight links carry 186 GB/s and win.  A pageable source has to be touched by the CPU anyway.
     feeding = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1) * max(1, CONCURRENT_UPLOADS)
-    if allow_pack and (not pinned_src or feeding == 1 or os.environ.get("ILLICO_PACK_UPLOAD") == "1") and _pack_wanted(src, n, b):
+    if allow_pack and (not pinned_src or feeding <= 4 or os.environ.get("ILLICO_PACK_UPLOAD") == "1") and _pack_wanted(src, n, b):
         return _h2d_2d_packed(dst, src, pinned_src, n_threads)
     if pinned_src:
         if src.strides[0] == b * item:      # contiguous: one linear asynchronous copy
