@@ -330,3 +330,39 @@ def test_host_pack_rows_matches_numpy():
             assert not (mask[:, -1] >> np.uint32(b % 32)).any()
         assert lib.illico_host_pack_rows_f32(view.ctypes.data, N, n, b, mask.ctypes.data, off.ctypes.data, vals.ctypes.data, b) == -1
     assert C is not None
+
+
+def test_row_blocks_balance_stored_values():
+    """repartition.row_blocks: contiguous row ranges that cover every row once and hold about the same number of stored
+    values (what each GPU uploads before the rows -> genes exchange)."""
+    from illico_b200.repartition import row_blocks
+
+    rng = np.random.RandomState(0)
+    counts = rng.poisson(700, 10_000)
+    counts[2000:2500] = 0                                  # a stretch of empty rows
+    indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    for k in (1, 2, 3, 8):
+        blocks = row_blocks(indptr, k)
+        assert len(blocks) == k and blocks[0][0] == 0 and blocks[-1][1] == counts.size
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(k - 1))
+        nnz = [indptr[b] - indptr[a] for a, b in blocks]
+        assert max(nnz) - min(nnz) <= 2 * counts.max()
+    empty = row_blocks(np.zeros(6, dtype=np.int64), 3)      # a matrix without stored values: the rows are still covered once
+    assert empty[0][0] == 0 and empty[-1][1] == 5 and sum(b - a for a, b in empty) == 5
+
+
+def test_pack_decision_samples_the_density(monkeypatch):
+    """hostio._pack_wanted: only large float32 matrices whose sampled rows are mostly zeros are squeezed."""
+    from illico_b200 import hostio
+
+    monkeypatch.delenv("ILLICO_PACK_UPLOAD", raising=False)
+    rng = np.random.RandomState(1)
+    n, b = 20_000, 1024                                     # 82 MB
+    sparse_x = (rng.rand(n, b) < 0.1).astype(np.float32)
+    dense_x = rng.rand(n, b).astype(np.float32)
+    assert hostio._pack_wanted(sparse_x, n, b)
+    assert not hostio._pack_wanted(dense_x, n, b)
+    assert not hostio._pack_wanted(sparse_x.astype(np.float64), n, b)
+    assert not hostio._pack_wanted(sparse_x[:1000], 1000, b)          # small: not worth the threads
+    monkeypatch.setenv("ILLICO_PACK_UPLOAD", "0")
+    assert not hostio._pack_wanted(sparse_x, n, b)
